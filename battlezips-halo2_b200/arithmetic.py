@@ -1,0 +1,76 @@
+"""Mirror of `halo2_proofs::arithmetic` and `halo2_proofs::poly::EvaluationDomain` entry points over the C ABI
+(U: halo2_proofs 0.2.0 src/arithmetic.rs, src/poly/domain.rs).
+
+Arrays are numpy uint64 of shape (n, 4) [field elements], (n, 8) [affine points], (12,) [Jacobian], holding
+pasta's in-memory Montgomery limbs -- exactly the bytes the Rust side owns."""
+import ctypes
+import numpy as np
+from .binding import _np_ptr
+
+
+def best_multiexp(ctx, curve, coeffs, bases):
+    """arithmetic::best_multiexp(coeffs, bases) -> C::Curve (Jacobian, 12 limbs)."""
+    coeffs = np.ascontiguousarray(coeffs, dtype=np.uint64).reshape(-1, 4)
+    bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, 8)
+    assert len(coeffs) == len(bases), "assert_eq!(coeffs.len(), bases.len())"
+    out = np.zeros(12, dtype=np.uint64)
+    ctx._check(ctx.lib.bz_best_multiexp(ctx.h, curve, _np_ptr(coeffs), _np_ptr(bases), len(coeffs), _np_ptr(out)))
+    return out
+
+
+def best_fft(ctx, field, a, omega, log_n):
+    """arithmetic::best_fft(&mut a, omega, log_n): in place on a copy, returned."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4).copy()
+    assert len(a) == 1 << log_n, "assert_eq!(n, 1 << log_n)"
+    omega = np.ascontiguousarray(omega, dtype=np.uint64).reshape(4)
+    ctx._check(ctx.lib.bz_best_fft(ctx.h, field, _np_ptr(a), _np_ptr(omega), log_n))
+    return a
+
+
+def lagrange_to_coeff(ctx, field, a, k):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4).copy()
+    assert len(a) == 1 << k
+    ctx._check(ctx.lib.bz_lagrange_to_coeff(ctx.h, field, _np_ptr(a), k))
+    return a
+
+
+def coeff_to_extended(ctx, field, a, k, extended_k):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    assert len(a) == 1 << k
+    out = np.empty((1 << extended_k, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_coeff_to_extended(ctx.h, field, _np_ptr(a), _np_ptr(out), k, extended_k))
+    return out
+
+
+def extended_to_coeff(ctx, field, a, extended_k):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4).copy()
+    assert len(a) == 1 << extended_k
+    ctx._check(ctx.lib.bz_extended_to_coeff(ctx.h, field, _np_ptr(a), extended_k))
+    return a
+
+
+_FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "from_u512": 4, "from_mont": 5, "to_mont": 6, "neg": 7, "sqr": 8}
+
+
+def field_op(ctx, field, op, a, b=None):
+    """Element-wise ff::Field operation on slices (see bz_field_op)."""
+    code = _FIELD_OPS[op]
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 8 if code == 4 else 4)
+    n = len(a)
+    if b is None:
+        b = np.zeros((n, 4), dtype=np.uint64)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 4)
+    out = np.empty((n, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_field_op(ctx.h, field, code, _np_ptr(a), _np_ptr(b), _np_ptr(out), n))
+    return out
+
+
+_CURVE_OPS = {"add": 0, "double": 1, "sub": 2, "double_add": 3, "mul_u32": 4}
+
+
+def curve_op(ctx, curve, op, a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 8)
+    b = np.ascontiguousarray(b, dtype=np.uint64).reshape(-1, 8)
+    out = np.empty_like(a)
+    ctx._check(ctx.lib.bz_curve_op(ctx.h, curve, _CURVE_OPS[op], _np_ptr(a), _np_ptr(b), _np_ptr(out), len(a)))
+    return out

@@ -1,0 +1,154 @@
+"""ctypes binding of libbzhalo2.so (include/bzhalo2.h).  Plain pointers and sizes only."""
+import ctypes, os, re, subprocess
+import numpy as np
+
+FIELD_FP, FIELD_FQ = 0, 1
+CURVE_VESTA, CURVE_PALLAS = 0, 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+_lib = None
+
+
+class BzError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bzhalo2 error {code}: {msg}")
+        self.code = code
+
+
+def lib_path():
+    return os.path.join(_HERE, "lib", "libbzhalo2.so")
+
+
+def header_path():
+    return os.path.join(_ROOT, "include", "bzhalo2.h")
+
+
+def build_library(verbose=False):
+    """Compile every CUDA source for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    subprocess.run(["make", "-C", os.path.join(_HERE, "csrc"), "-j8"], check=True,
+                   stdout=None if verbose else subprocess.DEVNULL)
+    return lib_path()
+
+
+def _declared_exports():
+    """Every function name include/bzhalo2.h declares."""
+    src = open(header_path()).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bz_[a-z0-9_]+)\s*\(", src)))
+
+
+EXPORTS = _declared_exports()
+
+
+def load_library():
+    """dlopen the CUDA library; fails loudly when it has not been built (no fallback path exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise BzError(-1, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(the product has no CPU fallback)")
+    lib = ctypes.CDLL(path)
+    vp, u64, u32, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint32, ctypes.c_int
+    sigs = {
+        "bz_ctx_create": (i32, [i32, vp, ctypes.POINTER(vp)]),
+        "bz_ctx_destroy": (None, [vp]),
+        "bz_last_error": (ctypes.c_char_p, [vp]),
+        "bz_sync": (i32, [vp]),
+        "bz_kernel_launches": (u64, [vp]),
+        "bz_version": (ctypes.c_char_p, []),
+        "bz_dev_alloc": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
+        "bz_dev_free": (i32, [vp, vp]),
+        "bz_h2d": (i32, [vp, vp, vp, ctypes.c_size_t]),
+        "bz_d2h": (i32, [vp, vp, vp, ctypes.c_size_t]),
+        "bz_field_op": (i32, [vp, i32, i32, vp, vp, vp, u64]),
+        "bz_curve_op": (i32, [vp, i32, i32, vp, vp, vp, u64]),
+        "bz_best_multiexp": (i32, [vp, i32, vp, vp, u64, vp]),
+        "bz_msm_dev": (i32, [vp, i32, vp, vp, u64, vp, i32]),
+        "bz_batch_normalize_dev": (i32, [vp, i32, vp, vp, u64]),
+        "bz_best_fft": (i32, [vp, i32, vp, vp, u32]),
+        "bz_ntt_dev": (i32, [vp, i32, vp, vp, u32, i32, i32]),
+        "bz_lagrange_to_coeff_dev": (i32, [vp, i32, vp, vp, u32, i32]),
+        "bz_coeff_to_extended_dev": (i32, [vp, i32, vp, vp, u32, u32, i32]),
+        "bz_extended_to_coeff_dev": (i32, [vp, i32, vp, vp, u32, i32]),
+        "bz_lagrange_to_coeff": (i32, [vp, i32, vp, u32]),
+        "bz_coeff_to_extended": (i32, [vp, i32, vp, vp, u32, u32]),
+        "bz_extended_to_coeff": (i32, [vp, i32, vp, u32]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def _np_ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+class DeviceBuffer:
+    def __init__(self, ctx, nbytes):
+        self.ctx, self.nbytes = ctx, nbytes
+        p = ctypes.c_void_p()
+        ctx._check(ctx.lib.bz_dev_alloc(ctx.h, nbytes, ctypes.byref(p)))
+        self.ptr = p
+
+    def upload(self, arr):
+        arr = np.ascontiguousarray(arr)
+        assert arr.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.bz_h2d(self.ctx.h, self.ptr, _np_ptr(arr), arr.nbytes))
+        return self
+
+    def download(self, shape, dtype=np.uint64):
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= self.nbytes
+        self.ctx._check(self.ctx.lib.bz_d2h(self.ctx.h, _np_ptr(out), self.ptr, out.nbytes))
+        return out
+
+    def free(self):
+        if self.ptr:
+            self.ctx.lib.bz_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+
+class Context:
+    """One GPU + one CUDA stream.  stream: an int cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream) or None."""
+
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        h = ctypes.c_void_p()
+        rc = self.lib.bz_ctx_create(device, ctypes.c_void_p(stream) if stream else None, ctypes.byref(h))
+        if rc != 0:
+            raise BzError(rc, "bz_ctx_create failed (no CUDA device / driver?) -- the product has no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BzError(rc, self.lib.bz_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bz_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._check(self.lib.bz_sync(self.h))
+
+    def kernel_launches(self):
+        return int(self.lib.bz_kernel_launches(self.h))
+
+    def alloc(self, nbytes):
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr):
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 32)).upload(arr)

@@ -1,0 +1,236 @@
+// extern "C" surface of libbzhalo2 (declared in include/bzhalo2.h).
+#include "../../include/bzhalo2.h"
+#include "common.h"
+#include <set>
+
+namespace bz {
+void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
+void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
+void curve_op_run(Ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n);
+
+Ctx::~Ctx() {}
+}  // namespace bz
+
+struct bz_ctx {
+  bz::Ctx c;
+  bool own_stream = false;
+  std::set<void*> allocs;
+};
+
+#define BZ_TRY(ctx_, ...)                                    \
+  try {                                                      \
+    cudaSetDevice((ctx_)->c.device);                         \
+    __VA_ARGS__;                                             \
+    return BZ_OK;                                            \
+  } catch (const bz::Error& e) {                             \
+    (ctx_)->c.last_error = e.what();                         \
+    return e.code;                                           \
+  } catch (const std::exception& e) {                        \
+    (ctx_)->c.last_error = e.what();                         \
+    return BZ_ERR_INVALID;                                   \
+  }
+
+extern "C" {
+
+__attribute__((visibility("default"))) const char* bz_version(void) { return "bzhalo2-b200 0.1 (sm_100a)"; }
+
+__attribute__((visibility("default"))) int bz_ctx_create(int device, void* stream, bz_ctx** out) {
+  if (!out) return BZ_ERR_INVALID;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return BZ_ERR_CUDA;   // no CPU fallback
+  if (cudaSetDevice(device) != cudaSuccess) return BZ_ERR_CUDA;
+  bz_ctx* h = new (std::nothrow) bz_ctx();
+  if (!h) return BZ_ERR_INVALID;
+  h->c.device = device;
+  if (stream) h->c.stream = (cudaStream_t)stream;
+  else {
+    if (cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BZ_ERR_CUDA; }
+    h->own_stream = true;
+  }
+  cudaDeviceGetAttribute(&h->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  *out = h;
+  return BZ_OK;
+}
+
+__attribute__((visibility("default"))) void bz_ctx_destroy(bz_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->c.device);
+  cudaStreamSynchronize(ctx->c.stream);
+  for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
+  delete ctx;
+}
+
+__attribute__((visibility("default"))) const char* bz_last_error(bz_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
+__attribute__((visibility("default"))) uint64_t bz_kernel_launches(bz_ctx* ctx) { return ctx ? ctx->c.kernel_launches : 0; }
+
+__attribute__((visibility("default"))) int bz_sync(bz_ctx* ctx) { BZ_TRY(ctx, BZ_CUDA(cudaStreamSynchronize(ctx->c.stream))); }
+
+__attribute__((visibility("default"))) int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(dptr, "null out pointer");
+    BZ_CUDA(cudaMalloc(dptr, bytes ? bytes : 1));
+    ctx->allocs.insert(*dptr);
+  });
+}
+__attribute__((visibility("default"))) int bz_dev_free(bz_ctx* ctx, void* dptr) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(ctx->allocs.erase(dptr) == 1, "bz_dev_free: pointer not owned by this context");
+    BZ_CUDA(cudaStreamSynchronize(ctx->c.stream));
+    BZ_CUDA(cudaFree(dptr));
+  });
+}
+__attribute__((visibility("default"))) int bz_h2d(bz_ctx* ctx, void* dptr, const void* host, size_t bytes) {
+  BZ_TRY(ctx, BZ_CUDA(cudaMemcpyAsync(dptr, host, bytes, cudaMemcpyHostToDevice, ctx->c.stream)));
+}
+__attribute__((visibility("default"))) int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes) {
+  BZ_TRY(ctx, {
+    BZ_CUDA(cudaMemcpyAsync(host, dptr, bytes, cudaMemcpyDeviceToHost, ctx->c.stream));
+    BZ_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  });
+}
+
+// ---- element-wise field / point ops on host slices ------------------------------------------------
+__attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    BZ_CHECK(op >= 0 && op <= 8, "bad op");
+    size_t in_sz = op == 4 ? 64 : 32;
+    bz::DevBuf da, db, dout;
+    da.alloc(n * in_sz + 32); db.alloc(n * 32 + 32); dout.alloc(n * 32 + 32);
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(da.p, a, n * in_sz, cudaMemcpyHostToDevice, st));
+    if (b && op <= 2) BZ_CUDA(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, st));
+    bz::field_op_run(&ctx->c, field, op, da.p, db.p, dout.p, n);
+    BZ_CUDA(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+__attribute__((visibility("default"))) int bz_curve_op(bz_ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    BZ_CHECK(op >= 0 && op <= 4, "bad op");
+    bz::DevBuf da, db, dout;
+    da.alloc(n * 64 + 64); db.alloc(n * 64 + 64); dout.alloc(n * 64 + 64);
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(da.p, a, n * 64, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(db.p, b, n * 64, cudaMemcpyHostToDevice, st));
+    bz::curve_op_run(&ctx->c, curve, op, da.p, db.p, dout.p, n);
+    BZ_CUDA(cudaMemcpyAsync(out, dout.p, n * 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// ---- MSM ----------------------------------------------------------------------------------------
+__attribute__((visibility("default"))) int bz_msm_dev(bz_ctx* ctx, int curve, const void* d_coeffs, const void* d_bases, uint64_t n, void* d_out_jac, int window_bits) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    BZ_CHECK(n < (1ull << 31), "msm: n too large");
+    BZ_CHECK(window_bits == 0 || (window_bits >= 2 && window_bits <= 16), "msm: window_bits out of range");
+    bz::msm_run(&ctx->c, curve, d_coeffs, d_bases, (uint32_t)n, d_out_jac, window_bits);
+  });
+}
+
+__attribute__((visibility("default"))) int bz_best_multiexp(bz_ctx* ctx, int curve, const void* coeffs, const void* bases, uint64_t n, void* out_jac) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    BZ_CHECK(n < (1ull << 31), "msm: n too large");
+    bz::DevBuf ds, db, dout;
+    ds.alloc(n * 32 + 32); db.alloc(n * 64 + 64); dout.alloc(96);
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(ds.p, coeffs, n * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(db.p, bases, n * 64, cudaMemcpyHostToDevice, st));
+    bz::msm_run(&ctx->c, curve, ds.p, db.p, (uint32_t)n, dout.p, 0);
+    BZ_CUDA(cudaMemcpyAsync(out_jac, dout.p, 96, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+__attribute__((visibility("default"))) int bz_batch_normalize_dev(bz_ctx* ctx, int curve, const void* d_jac, void* d_affine, uint64_t n) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    bz::jac_to_affine_run(&ctx->c, curve, d_jac, d_affine, (uint32_t)n);
+  });
+}
+
+// ---- NTT ----------------------------------------------------------------------------------------
+__attribute__((visibility("default"))) int bz_ntt_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t log_n, int inverse, int batch) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::NttFusion fu;
+    bz::ntt_run(&ctx->c, field, d_in, d_out, (int)log_n, inverse != 0, batch, fu);
+  });
+}
+__attribute__((visibility("default"))) int bz_lagrange_to_coeff_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t k, int batch) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::NttFusion fu; fu.post_mode = 1;
+    bz::ntt_run(&ctx->c, field, d_in, d_out, (int)k, true, batch, fu);
+  });
+}
+__attribute__((visibility("default"))) int bz_coeff_to_extended_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t k, uint32_t extended_k, int batch) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    BZ_CHECK(extended_k >= k, "extended_k < k");
+    bz::NttFusion fu; fu.n_in = extended_k > k ? (1ull << k) : 0; fu.pre_zeta = true;
+    bz::ntt_run(&ctx->c, field, d_in, d_out, (int)extended_k, false, batch, fu);
+  });
+}
+__attribute__((visibility("default"))) int bz_extended_to_coeff_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t extended_k, int batch) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::NttFusion fu; fu.post_mode = 3;
+    bz::ntt_run(&ctx->c, field, d_in, d_out, (int)extended_k, true, batch, fu);
+  });
+}
+
+static int host_ntt(bz_ctx* ctx, int field, const void* in, size_t n_in, void* out, size_t n_out, int logN, bool inverse, const bz::NttFusion& fu) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::DevBuf din, dout;
+    din.alloc(n_in * 32); dout.alloc(n_out * 32);
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(din.p, in, n_in * 32, cudaMemcpyHostToDevice, st));
+    bz::ntt_run(&ctx->c, field, din.p, dout.p, logN, inverse, 1, fu);
+    BZ_CUDA(cudaMemcpyAsync(out, dout.p, n_out * 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+__attribute__((visibility("default"))) int bz_best_fft(bz_ctx* ctx, int field, void* a, const void* omega, uint32_t log_n) {
+  if (!ctx) return BZ_ERR_INVALID;
+  if ((field != 0 && field != 1) || log_n > 30) { ctx->c.last_error = "bad field id or log_n"; return BZ_ERR_INVALID; }
+  const bzh::Field& F = ctx->c.field(field);
+  bzh::Fe w = F.root_of_unity();
+  for (uint32_t i = log_n; i < 32; ++i) w = F.sqr(w);
+  bzh::Fe om; memcpy(om.l, omega, 32);
+  bool inverse;
+  if (om == w) inverse = false;
+  else if (om == F.inv(w)) inverse = true;
+  else { ctx->c.last_error = "bz_best_fft: omega is not the 2^log_n domain generator or its inverse"; return BZ_ERR_UNSUPPORTED; }
+  bz::NttFusion fu;
+  size_t n = (size_t)1 << log_n;
+  return host_ntt(ctx, field, a, n, a, n, (int)log_n, inverse, fu);
+}
+__attribute__((visibility("default"))) int bz_lagrange_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t k) {
+  if (!ctx) return BZ_ERR_INVALID;
+  bz::NttFusion fu; fu.post_mode = 1;
+  size_t n = (size_t)1 << k;
+  return host_ntt(ctx, field, a, n, a, n, (int)k, true, fu);
+}
+__attribute__((visibility("default"))) int bz_coeff_to_extended(bz_ctx* ctx, int field, const void* coeffs, void* out_extended, uint32_t k, uint32_t extended_k) {
+  if (!ctx) return BZ_ERR_INVALID;
+  if (extended_k < k) { ctx->c.last_error = "extended_k < k"; return BZ_ERR_INVALID; }
+  bz::NttFusion fu; fu.n_in = extended_k > k ? (1ull << k) : 0; fu.pre_zeta = true;
+  return host_ntt(ctx, field, coeffs, (size_t)1 << k, out_extended, (size_t)1 << extended_k, (int)extended_k, false, fu);
+}
+__attribute__((visibility("default"))) int bz_extended_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t extended_k) {
+  if (!ctx) return BZ_ERR_INVALID;
+  bz::NttFusion fu; fu.post_mode = 3;
+  size_t n = (size_t)1 << extended_k;
+  return host_ntt(ctx, field, a, n, a, n, (int)extended_k, true, fu);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// Shared internal declarations of libbzhalo2 (not part of the C ABI; see include/bzhalo2.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+#include "host_field.h"
+
+namespace bz {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define BZ_CUDA(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess)                                                                              \
+      throw ::bz::Error(-2, std::string(#expr) + ": " + cudaGetErrorString(_e) + " @" + __FILE__ + ":" + \
+                                std::to_string(__LINE__));                                              \
+  } while (0)
+
+#define BZ_CHECK(cond, msg)                                  \
+  do {                                                       \
+    if (!(cond)) throw ::bz::Error(-1, std::string(msg));    \
+  } while (0)
+
+// device buffer owned by a context (freed with it)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), bytes(o.bytes) { o.p = nullptr; o.bytes = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept { release(); p = o.p; bytes = o.bytes; o.p = nullptr; o.bytes = 0; return *this; }
+  ~DevBuf() { release(); }
+  void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+  void alloc(size_t n) { release(); if (n) { BZ_CUDA(cudaMalloc(&p, n)); bytes = n; } }
+  void ensure(size_t n) { if (n > bytes) alloc(n); }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct NttTableKey {
+  int field, inverse, logM;
+  bool operator<(const NttTableKey& o) const { return std::tie(field, inverse, logM) < std::tie(o.field, o.inverse, o.logM); }
+};
+struct NttTable { DevBuf lo, hi; };
+
+// One context = one GPU + one stream family.  Callable from one thread at a time.
+struct Ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int sm_count = 148;
+  std::string last_error;
+  bzh::Field fp{0}, fq{1};
+
+  // NTT tables: wsmall[field][inverse] = w_{4096}^{+-i}, i < 2048; inter-pass tables by (field, inverse, logM)
+  DevBuf wsmall[2][2];
+  std::map<NttTableKey, NttTable> ntt_tables;
+  DevBuf ntt_tmp;          // ping-pong scratch for multi-pass transforms
+  DevBuf scratch[4];       // general reusable scratch (msm, staging)
+  uint64_t kernel_launches = 0;   // counted by every launch site (bench.py's gpu_launches)
+
+  const bzh::Field& field(int f) const { return f == 0 ? fp : fq; }
+  ~Ctx();
+};
+
+constexpr int WSMALL_LOG = 12;
+
+// ---- ntt.cu ----
+struct NttFusion {
+  // input side (first pass): zero padding + coset pre-scale by zeta^(i mod 3)
+  uint64_t n_in = 0;        // 0: input has N elements; else input has n_in (< N, power of two) elements, rest zero
+  bool pre_zeta = false;    // multiply input coefficient i by zeta^(i mod 3)  (coeff_to_extended)
+  // output side (last pass)
+  int post_mode = 0;        // 0 none, 1 scale by N^-1 (ifft), 3 scale by N^-1 * zeta^-(i mod 3) (extended_to_coeff)
+};
+// Transform `batch` polynomials.  in: batch x n_in(or N) elements, out: batch x N elements (may alias in when
+// n_in == 0).  Natural order in, natural order out.  omega = primitive 2^logN-th root from the field's
+// ROOT_OF_UNITY (inverse -> its inverse).
+void ntt_run(Ctx* ctx, int field, const void* in, void* out, int logN, bool inverse, int batch, const NttFusion& fu);
+
+}  // namespace bz

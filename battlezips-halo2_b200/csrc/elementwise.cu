@@ -1,0 +1,68 @@
+// Element-wise field / point operations exposed for the parity suite and for the small host-driven
+// steps of the prover (ff::Field ops on slices; group add on slices).  One thread per element.
+#include "common.h"
+#include "curve.cuh"
+
+namespace bz {
+
+template <class P>
+__global__ void field_op_kernel(int op, const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, Fe<P>* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<P> r;
+  if (op == 4) {          // from_u512: a holds 16 limbs per element
+    uint32_t w[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) w[j] = a[i * 16 + j];
+    r = fe_from_u512<P>(w);
+  } else {
+    Fe<P> x = fe_load(reinterpret_cast<const Fe<P>*>(a) + i);
+    Fe<P> y = (op <= 2) ? fe_load(reinterpret_cast<const Fe<P>*>(b) + i) : fe_zero<P>();
+    switch (op) {
+      case 0: r = fe_mul(x, y); break;
+      case 1: r = fe_add(x, y); break;
+      case 2: r = fe_sub(x, y); break;
+      case 3: r = fe_inv(x); break;
+      case 5: r = fe_from_mont(x); break;
+      case 6: r = fe_to_mont(x); break;
+      case 7: r = fe_neg(x); break;
+      default: r = fe_sqr(x); break;
+    }
+  }
+  fe_store(out + i, r);
+}
+
+// op 0: a + b (mixed), 1: 2a, 2: a - b, 3: full XYZZ add of (a+a) and b, 4: [k]a with k = low 32 bits of b.x raw
+template <class BP>
+__global__ void curve_op_kernel(int op, const Affine<BP>* __restrict__ a, const Affine<BP>* __restrict__ b, Affine<BP>* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Affine<BP> p = aff_load(a + i), q = aff_load(b + i);
+  Xyzz<BP> acc = xyzz_from_affine(p);
+  if (op == 0) xyzz_add_mixed(acc, q);
+  else if (op == 1) acc = xyzz_dbl(acc);
+  else if (op == 2) xyzz_add_mixed_signed(acc, q, true);
+  else if (op == 3) acc = xyzz_add(xyzz_dbl(acc), xyzz_from_affine(q));
+  else acc = xyzz_mul_u32(acc, q.x.l[0]);
+  Affine<BP> r = xyzz_to_affine(acc);
+  fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
+}
+
+void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
+  if (!n) return;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (field == 0) field_op_kernel<FpP><<<blocks, 128, 0, ctx->stream>>>(op, (const uint32_t*)a, (const uint32_t*)b, (Fe<FpP>*)out, n);
+  else field_op_kernel<FqP><<<blocks, 128, 0, ctx->stream>>>(op, (const uint32_t*)a, (const uint32_t*)b, (Fe<FqP>*)out, n);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+void curve_op_run(Ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n) {
+  if (!n) return;
+  unsigned blocks = (unsigned)((n + 63) / 64);
+  if (curve == 0) curve_op_kernel<FqP><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<FqP>*)a, (const Affine<FqP>*)b, (Affine<FqP>*)out, n);
+  else curve_op_kernel<FpP><<<blocks, 64, 0, ctx->stream>>>(op, (const Affine<FpP>*)a, (const Affine<FpP>*)b, (Affine<FpP>*)out, n);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+
+}  // namespace bz

@@ -1,0 +1,215 @@
+// Variable-base multi-scalar multiplication  sum_i s_i * B_i  over Vesta / Pallas for sm_100a.
+// Replaces halo2_proofs 0.2.0 `arithmetic::best_multiexp` (U: src/arithmetic.rs).
+// The reference algorithm (per-thread chunks, unsigned ceil(ln n)-bit windows, serial buckets) is
+// NOT followed: the result is a group element, canonical after to_affine, so any evaluation order
+// is bit-exact.  Here: signed-digit windows (2^(c-1) buckets per window),
+// counting sort of (window, bucket) keys with L2 atomics, one accumulator per bucket in XYZZ
+// coordinates (8M+2S mixed additions, complete formulas), chunk-parallel running-sum reduction
+// per window and a final Horner over the windows.  Everything is integer-pipe work (IMAD); the
+// only HBM traffic is 32 B/scalar + 64 B/point gathers.
+#include "common.h"
+#include "curve.cuh"
+
+namespace bz {
+
+// ---- 1. signed-digit decomposition + histogram ------------------------------------------------
+template <class SP>
+__global__ void msm_digits_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
+                                  uint32_t nb, uint32_t* __restrict__ keys, uint32_t* __restrict__ counts) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Fe<SP> s = fe_from_mont(fe_load(scalars + i));
+  uint32_t carry = 0;
+  const uint32_t half = 1u << (c - 1), full = 1u << c;
+  for (uint32_t w = 0; w < W; ++w) {
+    uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      raw = s.l[limb] >> sh;
+      if (sh + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh);
+      raw &= full - 1;
+    }
+    uint32_t v = raw + carry, key = 0;
+    if (v > half) { key = (full - v) | 0x80000000u; carry = 1; }
+    else { key = v; carry = 0; }
+    keys[(size_t)w * n + i] = key;
+    uint32_t b = key & 0x7fffffffu;
+    if (b) atomicAdd(&counts[w * nb + b - 1], 1u);
+  }
+}
+
+// ---- 2. exclusive scan of bucket counts over all windows (single CTA; W*nb <= 2^21) ------------
+__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
+                                uint32_t* __restrict__ cursor, uint32_t total) {
+  __shared__ uint32_t part[1024];
+  uint32_t tid = threadIdx.x, per = (total + blockDim.x - 1) / blockDim.x;
+  uint32_t lo = tid * per, hi = min(lo + per, total), sum = 0;
+  for (uint32_t j = lo; j < hi; ++j) sum += counts[j];
+  part[tid] = sum;
+  __syncthreads();
+  for (uint32_t d = 1; d < blockDim.x; d <<= 1) {
+    uint32_t v = tid >= d ? part[tid - d] : 0;
+    __syncthreads();
+    part[tid] += v;
+    __syncthreads();
+  }
+  uint32_t run = part[tid] - sum;
+  for (uint32_t j = lo; j < hi; ++j) { offsets[j] = run; cursor[j] = run; run += counts[j]; }
+}
+
+// ---- 3. scatter point indices into bucket order --------------------------------------------------
+__global__ void msm_scatter_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t W, uint32_t nb,
+                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t w = blockIdx.y;
+  if (i >= n) return;
+  uint32_t key = keys[(size_t)w * n + i];
+  uint32_t b = key & 0x7fffffffu;
+  if (!b) return;
+  uint32_t pos = atomicAdd(&cursor[w * nb + b - 1], 1u);
+  sorted[pos] = i | (key & 0x80000000u);
+}
+
+// ---- 4. bucket accumulation: one thread per (window, bucket) --------------------------------------
+template <class BP>
+__global__ void __launch_bounds__(128) msm_bucket_kernel(const Affine<BP>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                  uint32_t total_buckets, Xyzz<BP>* __restrict__ buckets) {
+  uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= total_buckets) return;
+  uint32_t off = offsets[gb], cnt = counts[gb];
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = 0; j < cnt; ++j) {
+    uint32_t e = sorted[off + j];
+    Affine<BP> pt = aff_load(bases + (e & 0x7fffffffu));
+    xyzz_add_mixed_signed(acc, pt, (e >> 31) != 0);
+  }
+  Xyzz<BP>* o = buckets + gb;
+  fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
+}
+
+template <class BP> __device__ __forceinline__ Xyzz<BP> xyzz_load(const Xyzz<BP>* p) {
+  Xyzz<BP> r; r.x = fe_load(&p->x); r.y = fe_load(&p->y); r.zz = fe_load(&p->zz); r.zzz = fe_load(&p->zzz); return r;
+}
+template <class BP> __device__ __forceinline__ void xyzz_store(Xyzz<BP>* p, const Xyzz<BP>& v) {
+  fe_store(&p->x, v.x); fe_store(&p->y, v.y); fe_store(&p->zz, v.zz); fe_store(&p->zzz, v.zzz);
+}
+
+// ---- 5. per-window reduction  R_w = sum_b (b+1) * bucket[w][b] ------------------------------------
+// CTA per window; thread t owns a contiguous chunk of buckets: running sums give
+// acc_t = sum (b - lo_t + 1) B_b and S_t = sum B_b; contribution = acc_t + lo_t * S_t (lo_t 0-based).
+template <class BP>
+__global__ void __launch_bounds__(256) msm_reduce_kernel(const Xyzz<BP>* __restrict__ buckets, uint32_t nb, Xyzz<BP>* __restrict__ window_sums) {
+  extern __shared__ unsigned char smem_raw[];
+  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(smem_raw);
+  uint32_t w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+  uint32_t per = (nb + nt - 1) / nt;
+  uint32_t lo = tid * per, hi = min(lo + per, nb);
+  Xyzz<BP> run = xyzz_identity<BP>(), acc = xyzz_identity<BP>();
+  for (uint32_t b = hi; b > lo; --b) {
+    Xyzz<BP> bk = xyzz_load(buckets + (size_t)w * nb + (b - 1));
+    run = xyzz_add(run, bk);
+    acc = xyzz_add(acc, run);
+  }
+  if (lo < hi && lo > 0) acc = xyzz_add(acc, xyzz_mul_u32(run, lo));
+  sh[tid] = acc;
+  __syncthreads();
+  for (uint32_t d = nt >> 1; d > 0; d >>= 1) {
+    if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) xyzz_store(window_sums + w, sh[0]);
+}
+
+// ---- 6. Horner over windows: R = sum_w 2^(c w) R_w ; writes Jacobian (x,y,z) -----------------------
+template <class BP>
+__global__ void msm_combine_kernel(const Xyzz<BP>* __restrict__ window_sums, uint32_t W, uint32_t c, Jac<BP>* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (int w = (int)W - 1; w >= 0; --w) {
+    for (uint32_t j = 0; j < c; ++j) acc = xyzz_dbl(acc);
+    acc = xyzz_add(acc, xyzz_load(window_sums + w));
+  }
+  Jac<BP> j = xyzz_to_jac(acc);
+  fe_store(&out->x, j.x); fe_store(&out->y, j.y); fe_store(&out->z, j.z);
+}
+
+// Jacobian -> affine, one thread per point (one inversion each; used on a handful of commitments)
+template <class BP>
+__global__ void jac_to_affine_kernel(const Jac<BP>* __restrict__ in, Affine<BP>* __restrict__ out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Jac<BP> p; p.x = fe_load(&in[i].x); p.y = fe_load(&in[i].y); p.z = fe_load(&in[i].z);
+  Affine<BP> r;
+  if (fe_is_zero(p.z)) { r.x = fe_zero<BP>(); r.y = fe_zero<BP>(); }
+  else {
+    Fe<BP> zi = fe_inv(p.z), zi2 = fe_sqr(zi);
+    r.x = fe_mul(p.x, zi2);
+    r.y = fe_mul(p.y, fe_mul(zi2, zi));
+  }
+  fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
+}
+
+static uint32_t pick_window(uint32_t n) {
+  uint32_t lg = 0;
+  while ((1ull << (lg + 1)) <= n) ++lg;
+  int c = (int)lg - 2;          // ~n/4 points per... tuned on B200 later (profiles/)
+  if (c < 4) c = 4;
+  if (c > 16) c = 16;
+  return (uint32_t)c;
+}
+
+template <class BP, class SP>
+static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, uint32_t n, Jac<BP>* out, int c_override) {
+  cudaStream_t st = ctx->stream;
+  if (n == 0) {
+    Jac<BP> id{}; memset(&id, 0, sizeof(id));
+    bzh::Fe one = ctx->field(BP::ID).one(); memcpy(id.y.l, one.l, 32);
+    BZ_CUDA(cudaMemcpyAsync(out, &id, sizeof(id), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  uint32_t c = c_override > 0 ? (uint32_t)c_override : pick_window(n);
+  uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1), total = W * nb;
+  BZ_CHECK(total <= (1u << 21), "msm: too many buckets");
+  // scratch layout
+  size_t keys_b = (size_t)W * n * 4, sorted_b = keys_b, cnt_b = (size_t)total * 4;
+  ctx->scratch[0].ensure(keys_b);
+  ctx->scratch[1].ensure(sorted_b);
+  ctx->scratch[2].ensure(cnt_b * 3);
+  ctx->scratch[3].ensure((size_t)(total + W) * sizeof(Xyzz<BP>));
+  uint32_t* keys = ctx->scratch[0].as<uint32_t>();
+  uint32_t* sorted = ctx->scratch[1].as<uint32_t>();
+  uint32_t* counts = ctx->scratch[2].as<uint32_t>();
+  uint32_t* offsets = counts + total;
+  uint32_t* cursor = offsets + total;
+  Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
+  Xyzz<BP>* wsums = buckets + total;
+
+  BZ_CUDA(cudaMemsetAsync(counts, 0, cnt_b, st));
+  msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, counts);
+  msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
+  msm_scatter_kernel<<<dim3((n + 255) / 256, W), 256, 0, st>>>(keys, n, W, nb, cursor, sorted);
+  msm_bucket_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, total, buckets);
+  uint32_t rthreads = nb >= 256 ? 256 : (nb >= 32 ? nb : 32);
+  msm_reduce_kernel<BP><<<W, rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, wsums);
+  msm_combine_kernel<BP><<<1, 32, 0, st>>>(wsums, W, c, out);
+  ctx->kernel_launches += 6;
+  BZ_CUDA(cudaGetLastError());
+}
+
+// curve: 0 = Vesta (scalars Fp, coordinates Fq), 1 = Pallas (scalars Fq, coordinates Fp).  All pointers device.
+void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override) {
+  if (curve == 0) msm_run_t<FqP, FpP>(ctx, (const Fe<FpP>*)scalars, (const Affine<FqP>*)bases, n, (Jac<FqP>*)out_jac, c_override);
+  else msm_run_t<FpP, FqP>(ctx, (const Fe<FqP>*)scalars, (const Affine<FpP>*)bases, n, (Jac<FpP>*)out_jac, c_override);
+}
+
+void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n) {
+  if (!n) return;
+  if (curve == 0) jac_to_affine_kernel<FqP><<<(n + 63) / 64, 64, 0, ctx->stream>>>((const Jac<FqP>*)jac, (Affine<FqP>*)aff, n);
+  else jac_to_affine_kernel<FpP><<<(n + 63) / 64, 64, 0, ctx->stream>>>((const Jac<FpP>*)jac, (Affine<FpP>*)aff, n);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+
+}  // namespace bz

@@ -1,0 +1,103 @@
+/* libbzhalo2 -- C ABI of the B200-native Halo2 (IPA / Pasta) prover hot path.
+ *
+ * This is the drop-in boundary for the path BASELINE.json names: the arithmetic that
+ * `halo2_proofs 0.2.0` (pinned at /root/reference/Cargo.lock:382-393, not vendored) executes inside
+ * `create_proof`, as called by the reference at
+ *   /root/reference/benches/shot.rs:58-71, /root/reference/benches/board.rs:51-86,
+ *   /root/reference/src/circuits/shot.rs:915-940, /root/reference/src/circuits/board.rs:907-932.
+ * A patched halo2_proofs binds these symbols one-for-one from
+ * `arithmetic.rs`, `poly/domain.rs`, `poly/commitment.rs` and the prover modules.
+ *
+ * Data layout across the ABI:
+ *   field element : 32 B = pasta's in-memory [u64;4], little-endian, Montgomery form (R = 2^256)
+ *                   -> `&[Fp]` / `&[Fq]` pass through with zero conversion
+ *   affine point  : 64 B  x || y (Montgomery); identity = 64 zero bytes
+ *   Jacobian point: 96 B  x || y || z (Montgomery); identity has z = 0
+ *   field id      : 0 = Fp (pallas::Base = vesta::Scalar), 1 = Fq (pallas::Scalar = vesta::Base)
+ *   curve id      : 0 = Vesta (scalars Fp, coordinates Fq) -- the commitment curve of Board/Shot
+ *                   1 = Pallas (scalars Fq, coordinates Fp)
+ * Every function returns 0 on success, <0 on failure (bz_last_error gives the message); no C++
+ * exception or abort crosses the boundary.  A context is bound to one GPU and one CUDA stream and
+ * may be used by one thread at a time; contexts are independent.  There is NO CPU fallback:
+ * without a CUDA device bz_ctx_create fails.
+ */
+#ifndef BZHALO2_H
+#define BZHALO2_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bz_ctx bz_ctx;
+
+#define BZ_OK 0
+#define BZ_ERR_INVALID (-1)
+#define BZ_ERR_CUDA (-2)
+#define BZ_ERR_UNSUPPORTED (-3)
+#define BZ_ERR_SYNTHESIS (-4) /* maps to plonk::Error::ConstraintSystemFailure / Synthesis */
+
+#define BZ_FIELD_FP 0
+#define BZ_FIELD_FQ 1
+#define BZ_CURVE_VESTA 0
+#define BZ_CURVE_PALLAS 1
+
+/* ---- context ---------------------------------------------------------------------------------- */
+/* stream = a cudaStream_t owned by the caller (e.g. torch's current stream) or NULL for a private one */
+int bz_ctx_create(int device, void* stream, bz_ctx** out);
+void bz_ctx_destroy(bz_ctx* ctx);
+const char* bz_last_error(bz_ctx* ctx);
+int bz_sync(bz_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t bz_kernel_launches(bz_ctx* ctx);
+const char* bz_version(void);
+
+/* ---- device memory (library-owned, freed by bz_dev_free or with the context) ------------------- */
+int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr);
+int bz_dev_free(bz_ctx* ctx, void* dptr);
+int bz_h2d(bz_ctx* ctx, void* dptr, const void* host, size_t bytes);
+int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes);
+
+/* ---- ff::Field / group ops on host slices (pasta_curves semantics; used by the parity suite and by the
+ * shim for the few scalar-sized steps it does not want to do on the CPU) ------------------------------ */
+/* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 (0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
+ *     6 canonical -> Montgomery, 7 -a, 8 a^2 */
+int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
+/* affine in, affine out (64 B each): op 0 a+b, 1 2a, 2 a-b, 3 2a+b (full projective add), 4 [k]a, k = first u32 of b */
+int bz_curve_op(bz_ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n);
+
+/* ---- arithmetic::best_multiexp(coeffs, bases) -> C::Curve  (U: halo2_proofs/src/arithmetic.rs) -- */
+/* host buffers; copies are part of the call.  out_jac: 96 B. */
+int bz_best_multiexp(bz_ctx* ctx, int curve, const void* coeffs, const void* bases, uint64_t n, void* out_jac);
+/* device-resident variant (all pointers from bz_dev_alloc); window_bits = 0 picks automatically */
+int bz_msm_dev(bz_ctx* ctx, int curve, const void* d_coeffs, const void* d_bases, uint64_t n, void* d_out_jac,
+               int window_bits);
+/* group::Curve::batch_normalize: n Jacobian -> n affine (device pointers) */
+int bz_batch_normalize_dev(bz_ctx* ctx, int curve, const void* d_jac, void* d_affine, uint64_t n);
+
+/* ---- arithmetic::best_fft(a, omega, log_n)  (U: halo2_proofs/src/arithmetic.rs) ----------------- */
+/* In-place, natural order in/out.  omega must be the domain generator ROOT_OF_UNITY^(2^(32-log_n))
+ * or its inverse -- the only values halo2_proofs ever passes (EvaluationDomain::new, Params::new);
+ * anything else returns BZ_ERR_UNSUPPORTED. */
+int bz_best_fft(bz_ctx* ctx, int field, void* a, const void* omega, uint32_t log_n);
+/* device-resident batched transform: `batch` arrays of 2^log_n elements, contiguous */
+int bz_ntt_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t log_n, int inverse, int batch);
+
+/* ---- EvaluationDomain (U: halo2_proofs/src/poly/domain.rs) --------------------------------------- */
+/* lagrange_to_coeff: inverse NTT of size 2^k with the 1/n scale fused into the last pass */
+int bz_lagrange_to_coeff_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t k, int batch);
+/* coeff_to_extended: zeta^(i mod 3) pre-scale + zero-pad n -> 2^extended_k + forward NTT, one fused transform */
+int bz_coeff_to_extended_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t k, uint32_t extended_k,
+                             int batch);
+/* extended_to_coeff: inverse NTT of size 2^extended_k, 1/N and zeta^-(i mod 3) fused (caller truncates) */
+int bz_extended_to_coeff_dev(bz_ctx* ctx, int field, const void* d_in, void* d_out, uint32_t extended_k, int batch);
+/* host-buffer conveniences mirroring the Rust signatures (copies inside the call) */
+int bz_lagrange_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t k);
+int bz_coeff_to_extended(bz_ctx* ctx, int field, const void* coeffs, void* out_extended, uint32_t k, uint32_t extended_k);
+int bz_extended_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t extended_k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BZHALO2_H */
