@@ -64,6 +64,8 @@ def test_curve_ops(curve, ctx, oracle_c):
 def _bases(co, curve, n):
     """n distinct points: hash-to-curve for a few, then a doubling/adding chain through the C oracle."""
     C, sf, bf = co.CURVES[curve]
+    if n == 0:
+        return []
     h = C.hash_to_curve("Halo2-Parameters")
     seed = [h(b"\x00" + i.to_bytes(4, "little")) for i in range(min(n, 8))]
     pts = list(seed)
