@@ -59,6 +59,8 @@ def load_library():
         "bz_sync": (i32, [vp]),
         "bz_kernel_launches": (u64, [vp]),
         "bz_version": (ctypes.c_char_p, []),
+        "bz_profile_enable": (i32, [vp, i32]),
+        "bz_profile_read": (i32, [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
         "bz_dev_alloc": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
         "bz_dev_free": (i32, [vp, vp]),
         "bz_h2d": (i32, [vp, vp, vp, ctypes.c_size_t]),
@@ -145,6 +147,22 @@ class Context:
 
     def kernel_launches(self):
         return int(self.lib.bz_kernel_launches(self.h))
+
+    PROF_TAGS = ["ntt_pass", "msm_digits", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "fixed_msm",
+                 "quotient", "scan", "eval", "poly", "ipa", "other"]
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.bz_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self):
+        """{tag: (total_ms, launches)} measured with CUDA events on this context's stream."""
+        out = {}
+        for i, name in enumerate(self.PROF_TAGS):
+            ms, cnt = ctypes.c_double(), ctypes.c_uint64()
+            self._check(self.lib.bz_profile_read(self.h, i, ctypes.byref(ms), ctypes.byref(cnt)))
+            if cnt.value:
+                out[name] = (ms.value, cnt.value)
+        return out
 
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)

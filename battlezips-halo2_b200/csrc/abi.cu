@@ -92,6 +92,32 @@ __attribute__((visibility("default"))) int bz_d2h(bz_ctx* ctx, void* host, const
   });
 }
 
+// ---- per-kernel-class device timing ------------------------------------------------------------------
+static void prof_drain(bz_ctx* ctx) {
+  cudaStreamSynchronize(ctx->c.stream);
+  for (auto& r : ctx->c.prof) {
+    float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+    ctx->c.prof_ms[r.tag] += ms; ctx->c.prof_count[r.tag]++;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  ctx->c.prof.clear();
+}
+__attribute__((visibility("default"))) int bz_profile_enable(bz_ctx* ctx, int on) {
+  BZ_TRY(ctx, {
+    prof_drain(ctx);
+    ctx->c.profiling = on != 0;
+    for (int i = 0; i < bz::PROF_NTAGS; ++i) { ctx->c.prof_ms[i] = 0; ctx->c.prof_count[i] = 0; }
+  });
+}
+__attribute__((visibility("default"))) int bz_profile_read(bz_ctx* ctx, int tag, double* total_ms, uint64_t* count) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(tag >= 0 && tag < bz::PROF_NTAGS, "bad profile tag");
+    prof_drain(ctx);
+    if (total_ms) *total_ms = ctx->c.prof_ms[tag];
+    if (count) *count = ctx->c.prof_count[tag];
+  });
+}
+
 // ---- element-wise field / point ops on host slices ------------------------------------------------
 __attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
   BZ_TRY(ctx, {

@@ -53,6 +53,12 @@ struct NttTableKey {
 };
 struct NttTable { DevBuf lo, hi; };
 
+// Per-kernel-class device timing (CUDA events on the launching stream), switched on by bz_profile_enable:
+// bench.py reads the dominant kernel's average launch duration from here for the roofline object.
+enum ProfTag { PROF_NTT_PASS = 0, PROF_MSM_DIGITS, PROF_MSM_SORT, PROF_MSM_BUCKET, PROF_MSM_REDUCE, PROF_MSM_COMBINE,
+               PROF_FIXED_MSM, PROF_QUOTIENT, PROF_SCAN, PROF_EVAL, PROF_POLY, PROF_IPA, PROF_OTHER, PROF_NTAGS };
+struct ProfRec { cudaEvent_t a, b; int tag; };
+
 // One context = one GPU + one stream family.  Callable from one thread at a time.
 struct Ctx {
   int device = 0;
@@ -67,9 +73,29 @@ struct Ctx {
   DevBuf ntt_tmp;          // ping-pong scratch for multi-pass transforms
   DevBuf scratch[4];       // general reusable scratch (msm, staging)
   uint64_t kernel_launches = 0;   // counted by every launch site (bench.py's gpu_launches)
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  double prof_ms[PROF_NTAGS] = {0};
+  uint64_t prof_count[PROF_NTAGS] = {0};
 
   const bzh::Field& field(int f) const { return f == 0 ? fp : fq; }
   ~Ctx();
+};
+
+// RAII scope: records a start/stop event pair around the launches issued inside it (only when profiling)
+struct ProfScope {
+  Ctx* c; ProfRec r; bool on;
+  ProfScope(Ctx* ctx, int tag) : c(ctx), on(ctx->profiling) {
+    if (!on) return;
+    r.tag = tag;
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, c->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.b, c->stream);
+    c->prof.push_back(r);
+  }
 };
 
 constexpr int WSMALL_LOG = 12;

@@ -187,13 +187,18 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   Xyzz<BP>* wsums = buckets + total;
 
   BZ_CUDA(cudaMemsetAsync(counts, 0, cnt_b, st));
-  msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, counts);
-  msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
-  msm_scatter_kernel<<<dim3((n + 255) / 256, W), 256, 0, st>>>(keys, n, W, nb, cursor, sorted);
-  msm_bucket_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, total, buckets);
+  { ProfScope p(ctx, PROF_MSM_DIGITS);
+    msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, counts); }
+  { ProfScope p(ctx, PROF_MSM_SORT);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
+    msm_scatter_kernel<<<dim3((n + 255) / 256, W), 256, 0, st>>>(keys, n, W, nb, cursor, sorted); }
+  { ProfScope p(ctx, PROF_MSM_BUCKET);
+    msm_bucket_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, total, buckets); }
   uint32_t rthreads = nb >= 256 ? 256 : (nb >= 32 ? nb : 32);
-  msm_reduce_kernel<BP><<<W, rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, wsums);
-  msm_combine_kernel<BP><<<1, 32, 0, st>>>(wsums, W, c, out);
+  { ProfScope p(ctx, PROF_MSM_REDUCE);
+    msm_reduce_kernel<BP><<<W, rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, wsums); }
+  { ProfScope p(ctx, PROF_MSM_COMBINE);
+    msm_combine_kernel<BP><<<1, 32, 0, st>>>(wsums, W, c, out); }
   ctx->kernel_launches += 6;
   BZ_CUDA(cudaGetLastError());
 }

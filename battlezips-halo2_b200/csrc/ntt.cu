@@ -184,6 +184,7 @@ template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t
     attr_set[P::ID] = true;
   }
   dim3 grid((unsigned)(nlines >> a.logT), (unsigned)batch);
+  ProfScope prof(ctx, PROF_NTT_PASS);
   ntt_pass_kernel<P><<<grid, threads, smem, ctx->stream>>>(a);
   ctx->kernel_launches++;
   BZ_CUDA(cudaGetLastError());

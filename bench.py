@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- driver contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
+
+Workloads (BASELINE.json configs; `--workload`):
+  msm   raw MSM over Vesta/Pallas, 2^LOG points resident in HBM       (config 4)   metric msm_points_per_sec
+  ntt   Fp NTT / coset extension, 2^LOG elements                      (config 4)   metric ntt_gbytes_per_sec
+  (the Board / Shot proof workloads plug in here as the prover lands; see DESIGN.md "Measurement")
+
+A "step" = one pass of the hot path over one batch of synthetic input.  `value` = device-resident throughput,
+`e2e` = same metric through the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed
+region).  `roofline` = dominant kernel, timed live with CUDA events on the launching stream (library profile
+scopes).  `cpu_baseline` = the oracle (C restatement of halo2_proofs' rayon algorithms) on this box's host cores
+over a bounded sample.  `--impl reference` times that CPU restatement alone (the Rust reference cannot be built
+or run here: no cargo, crates not vendored -- DESIGN.md).
+"""
+import argparse, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "msm"))
+    ap.add_argument("--log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
+    ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
+    ap.add_argument("--cpu-sample-log", type=int, default=18)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def rand_field(rng, n):
+    """n x 4 uint64 limbs < 2^253: valid Montgomery residues of either field (synthetic data)."""
+    a = rng.integers(0, 2**63, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 61) - 1)
+    return a
+
+
+def make_bases(co, curve, n):
+    """n valid, pairwise distinct-looking curve points without n hash-to-curves: take 256 hash-derived points
+    P_j and build B_i = P_{i mod 256} + [i div 256] Q' by repeated addition in the C oracle (setup only)."""
+    import ctypes
+    C = co.CURVES[curve][0]
+    h = C.hash_to_curve("Halo2-Parameters")
+    m = min(n, 256)
+    seed = co.points_to_mont(curve, [h(b"\x00" + i.to_bytes(4, "little")) for i in range(m)])
+    step = co.points_to_mont(curve, [h(b"\x01")])
+    out = np.empty((n, 8), dtype=np.uint64)
+    out[:m] = seed
+    cur = seed.copy()
+    tmp = np.empty(8, dtype=np.uint64)
+    done = m
+    while done < n:
+        for j in range(m):
+            co.lib().orc_point_add(curve, co._p(cur[j]), co._p(step), co._p(tmp))
+            cur[j] = tmp
+        take = min(m, n - done)
+        out[done:done + take] = cur[:take]
+        done += take
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------
+class MsmWorkload:
+    dtype = "u32x8 (255-bit Montgomery, integer pipe)"
+
+    def __init__(self, args):
+        self.log, self.curve = args.log, args.curve
+        self.n = 1 << self.log
+        self.metric, self.unit = "msm_points_per_sec", "points/s"
+        self.name = f"raw {'Pallas' if self.curve else 'Vesta'} MSM 2^{self.log} points, uniform scalars (BASELINE config 4)"
+
+    def host_inputs(self, rank):
+        from oracle import c_oracle as co            # setup only: valid curve points for the synthetic bases
+        rng = np.random.default_rng(1234 + rank)
+        t = time.time()
+        # 2^16 distinct points tiled: the MSM cost does not depend on distinctness, setup time does
+        m = min(self.n, 1 << 14)
+        pts = make_bases(co, self.curve, m)
+        bases = np.tile(pts, (self.n // m, 1))
+        scalars = rand_field(rng, self.n)
+        return scalars, bases
+
+    def setup(self, ctx, rank):
+        self.ctx = ctx
+        self.scalars, self.bases = self.host_inputs(rank)
+        import torch
+        self.h_scalars = torch.from_numpy(self.scalars.view(np.int64)).pin_memory()
+        self.h_bases = torch.from_numpy(self.bases.view(np.int64)).pin_memory()
+        self.d_scalars = ctx.to_device(self.scalars)
+        self.d_bases = ctx.to_device(self.bases)
+        self.d_out = ctx.alloc(96)
+        self.h2d, self.d2h = self.n * 96, 96
+
+    def step_device(self):
+        c = self.ctx
+        c._check(c.lib.bz_msm_dev(c.h, self.curve, self.d_scalars.ptr, self.d_bases.ptr, self.n, self.d_out.ptr, 0))
+        return self.n
+
+    def step_e2e(self):
+        import ctypes
+        c = self.ctx
+        out = np.empty(12, dtype=np.uint64)
+        c._check(c.lib.bz_best_multiexp(c.h, self.curve, ctypes.c_void_p(self.h_scalars.data_ptr()),
+                                        ctypes.c_void_p(self.h_bases.data_ptr()), self.n, out.ctypes.data_as(ctypes.c_void_p)))
+        return self.n
+
+    def dominant(self):
+        # MSM algorithmic bytes: 32 B scalar + 64 B base per point (96*N); dominant kernel = bucket accumulation
+        return "msm_bucket", 96.0 * self.n
+
+    def cpu(self, sample_log, steps=1):
+        from oracle import c_oracle as co
+        m = 1 << min(sample_log, self.log)
+        s, b = self.scalars[:m].copy(), self.bases[:m].copy()
+        co.best_multiexp(self.curve, s[:1024], b[:1024])
+        t = time.perf_counter()
+        for _ in range(steps):
+            co.best_multiexp(self.curve, s, b)
+        dt = (time.perf_counter() - t) / steps
+        return m / dt, f"best_multiexp restated (C, {co.get_threads()} threads) on the first 2^{min(sample_log, self.log)} points of the same input", co.get_threads(), dt
+
+
+class NttWorkload:
+    dtype = "u32x8 (255-bit Montgomery, integer pipe)"
+
+    def __init__(self, args):
+        self.log = args.log
+        self.n = 1 << self.log
+        self.metric, self.unit = "ntt_gbytes_per_sec", "GB/s"
+        self.name = f"Fp forward NTT 2^{self.log} (64*N algorithmic bytes) (BASELINE config 4)"
+
+    def setup(self, ctx, rank):
+        import torch
+        self.ctx = ctx
+        rng = np.random.default_rng(99 + rank)
+        self.a = rand_field(rng, self.n)
+        self.h_a = torch.from_numpy(self.a.view(np.int64)).pin_memory()
+        self.d_a = ctx.to_device(self.a)
+        self.d_b = ctx.alloc(self.n * 32)
+        self.h2d = self.d2h = self.n * 32
+        F = ctx  # omega for the host-API call
+        p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+        root = 0x2bce74deac30ebda362120830561f81aea322bf2b7bb7584bdad6fabd87ea32f
+        om = pow(root, 1 << (32 - self.log), p)
+        self.omega = np.frombuffer(((om << 256) % p).to_bytes(32, "little"), dtype=np.uint64).copy()
+
+    def step_device(self):
+        c = self.ctx
+        c._check(c.lib.bz_ntt_dev(c.h, 0, self.d_a.ptr, self.d_b.ptr, self.log, 0, 1))
+        return 64.0 * self.n / 1e9
+
+    def step_e2e(self):
+        import ctypes
+        c = self.ctx
+        c._check(c.lib.bz_best_fft(c.h, 0, ctypes.c_void_p(self.h_a.data_ptr()), self.omega.ctypes.data_as(ctypes.c_void_p), self.log))
+        return 64.0 * self.n / 1e9
+
+    def dominant(self):
+        npass = 1 if self.log <= 12 else (2 if self.log <= 20 else 3)
+        return "ntt_pass", 64.0 * self.n / npass      # per launch: each pass reads+writes the array once
+
+    def cpu(self, sample_log, steps=1):
+        from oracle import c_oracle as co
+        lg = min(sample_log + 2, self.log)
+        a = self.a[: 1 << lg].copy()
+        p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+        root = 0x2bce74deac30ebda362120830561f81aea322bf2b7bb7584bdad6fabd87ea32f
+        om = co.to_mont(0, [pow(root, 1 << (32 - lg), p)])
+        t = time.perf_counter()
+        for _ in range(steps):
+            co.best_fft(0, a, om, lg)
+        dt = (time.perf_counter() - t) / steps
+        return 64.0 * (1 << lg) / 1e9 / dt, f"best_fft restated (C, {co.get_threads()} threads) at 2^{lg}", co.get_threads(), dt
+
+
+WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload}
+
+
+# ------------------------------------------------------------------------------------------------------
+def run_reference(args, rank):
+    """--impl reference: the CPU restatement of the reference path on this box's host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload](args)
+    if hasattr(wl, "host_inputs"):
+        wl.scalars, wl.bases = wl.host_inputs(0)
+    else:
+        wl.a = rand_field(np.random.default_rng(99), wl.n)
+    for _ in range(max(1, min(args.warmup, 1))):
+        wl.cpu(args.cpu_sample_log - 2)
+    vals, dts = [], []
+    for _ in range(args.steps):
+        v, sample, cores, dt = wl.cpu(args.cpu_sample_log)
+        vals.append(v); dts.append(dt)
+    v = float(np.mean(vals))
+    print(json.dumps({
+        "impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
+        "config": {"workload": wl.name, "note": "restated halo2_proofs 0.2.0 arithmetic (C oracle); the rustc reference cannot be built here"},
+        "cpu_baseline": {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import battlezips_halo2_b200 as bz
+    stream = torch.cuda.current_stream()
+    ctx = bz.Context(local_rank, stream=stream.cuda_stream)
+    wl = WORKLOADS[args.workload](args)
+    wl.setup(ctx, rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(args.warmup):
+        wl.step_device()
+    barrier()
+    launches0 = ctx.kernel_launches()
+    ctx.profile_enable(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    units = 0.0
+    for _ in range(args.steps):
+        units += wl.step_device()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ctx.kernel_launches() - launches0
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
+
+    # ---- end-to-end through the host-buffer ABI (H2D + D2H inside the timed region) ----
+    for _ in range(min(args.warmup, 2)):
+        wl.step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    units_e = 0.0
+    for _ in range(args.steps):
+        units_e += wl.step_e2e()
+    e3.record(stream)
+    barrier()
+    wall_e = time.perf_counter() - t0
+    ms_e = torch.tensor([max(e2.elapsed_time(e3), 1e3 * wall_e)], device="cuda")   # host-synchronous calls: wall clock bounds it
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms_e = float(ms_e.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    value = units * world / (ms / 1e3)
+    e2e_value = units_e * world / (ms_e / 1e3)
+    tag, alg_bytes = wl.dominant()
+    peak, peak_kind = peaks()
+    roof = None
+    if tag in prof:
+        tot_ms, cnt = prof[tag]
+        avg_s = tot_ms / cnt / 1e3
+        ach = alg_bytes / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
+                "share_of_step": tot_ms / ms,
+                "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
+    cpu = None
+    if world == 1 or rank == 0:
+        v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
+        cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
+    print(json.dumps({
+        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": wl.dtype, "data": "synthetic",
+        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "inputs < L2; not flushed"},
+        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -53,6 +53,12 @@ int bz_sync(bz_ctx* ctx);
 uint64_t bz_kernel_launches(bz_ctx* ctx);
 const char* bz_version(void);
 
+/* ---- per-kernel-class device timing (CUDA events on the context's stream) ------------------------ */
+/* tags: 0 ntt_pass, 1 msm_digits, 2 msm_sort, 3 msm_bucket, 4 msm_reduce, 5 msm_combine, 6 fixed_msm,
+ *       7 quotient, 8 scan, 9 eval, 10 poly, 11 ipa, 12 other */
+int bz_profile_enable(bz_ctx* ctx, int on);
+int bz_profile_read(bz_ctx* ctx, int tag, double* total_ms, uint64_t* count);
+
 /* ---- device memory (library-owned, freed by bz_dev_free or with the context) ------------------- */
 int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr);
 int bz_dev_free(bz_ctx* ctx, void* dptr);
