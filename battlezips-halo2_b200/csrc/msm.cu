@@ -70,22 +70,60 @@ __global__ void msm_scatter_kernel(const uint32_t* __restrict__ keys, uint32_t n
   sorted[pos] = i | (key & 0x80000000u);
 }
 
-// ---- 4. bucket accumulation: one thread per (window, bucket) --------------------------------------
-template <class BP>
-__global__ void __launch_bounds__(128) msm_bucket_kernel(const Affine<BP>* __restrict__ bases, const uint32_t* __restrict__ sorted,
-                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
-                                  uint32_t total_buckets, Xyzz<BP>* __restrict__ buckets) {
+// ---- 4. bucket accumulation, skew-proof: every bucket's entry list is cut into segments of <= SEG
+// entries; one thread per segment (so a bucket holding 30% of all points -- witness-like scalars, or the
+// few-bit top window -- is spread over thousands of threads), then one thread per bucket folds its
+// segment partials.
+constexpr uint32_t SEG = 32;
+
+__global__ void msm_segcount_kernel(const uint32_t* __restrict__ counts, uint32_t total_buckets, uint32_t* __restrict__ nseg) {
+  uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb < total_buckets) nseg[gb] = (counts[gb] + SEG - 1) / SEG;
+}
+__global__ void msm_segmap_kernel(const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff, uint32_t total_buckets,
+                                  uint32_t* __restrict__ seg_bucket) {
   uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb >= total_buckets) return;
-  uint32_t off = offsets[gb], cnt = counts[gb];
+  uint32_t o = segoff[gb], m = nseg[gb];
+  for (uint32_t j = 0; j < m; ++j) seg_bucket[o + j] = gb;
+}
+
+template <class BP>
+__global__ void __launch_bounds__(128) msm_segment_kernel(const Affine<BP>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+                                  const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                  const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff,
+                                  const uint32_t* __restrict__ seg_bucket, uint32_t total_buckets, uint32_t max_segs,
+                                  Xyzz<BP>* __restrict__ partial) {
+  uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t total_segs = segoff[total_buckets - 1] + nseg[total_buckets - 1];
+  if (s >= total_segs || s >= max_segs) return;
+  uint32_t gb = seg_bucket[s];
+  uint32_t j0 = (s - segoff[gb]) * SEG;
+  uint32_t off = offsets[gb] + j0, cnt = min(SEG, counts[gb] - j0);
   Xyzz<BP> acc = xyzz_identity<BP>();
   for (uint32_t j = 0; j < cnt; ++j) {
     uint32_t e = sorted[off + j];
     Affine<BP> pt = aff_load(bases + (e & 0x7fffffffu));
     xyzz_add_mixed_signed(acc, pt, (e >> 31) != 0);
   }
-  Xyzz<BP>* o = buckets + gb;
+  Xyzz<BP>* o = partial + s;
   fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
+}
+
+template <class BP>
+__global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ nseg,
+                                  const uint32_t* __restrict__ segoff, uint32_t total_buckets, Xyzz<BP>* __restrict__ buckets) {
+  uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= total_buckets) return;
+  uint32_t o = segoff[gb], m = nseg[gb];
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = 0; j < m; ++j) {
+    const Xyzz<BP>* q = partial + o + j;
+    Xyzz<BP> v; v.x = fe_load(&q->x); v.y = fe_load(&q->y); v.zz = fe_load(&q->zz); v.zzz = fe_load(&q->zzz);
+    acc = (j == 0) ? v : xyzz_add(acc, v);
+  }
+  Xyzz<BP>* ob = buckets + gb;
+  fe_store(&ob->x, acc.x); fe_store(&ob->y, acc.y); fe_store(&ob->zz, acc.zz); fe_store(&ob->zzz, acc.zzz);
 }
 
 template <class BP> __device__ __forceinline__ Xyzz<BP> xyzz_load(const Xyzz<BP>* p) {
@@ -176,15 +214,20 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   size_t keys_b = (size_t)W * n * 4, sorted_b = keys_b, cnt_b = (size_t)total * 4;
   ctx->scratch[0].ensure(keys_b);
   ctx->scratch[1].ensure(sorted_b);
-  ctx->scratch[2].ensure(cnt_b * 3);
-  ctx->scratch[3].ensure((size_t)(total + W) * sizeof(Xyzz<BP>));
+  uint32_t max_segs = (uint32_t)(((uint64_t)W * n) / SEG + total);
+  ctx->scratch[2].ensure(cnt_b * 5 + (size_t)max_segs * 4);
+  ctx->scratch[3].ensure((size_t)(total + W + max_segs) * sizeof(Xyzz<BP>));
   uint32_t* keys = ctx->scratch[0].as<uint32_t>();
   uint32_t* sorted = ctx->scratch[1].as<uint32_t>();
   uint32_t* counts = ctx->scratch[2].as<uint32_t>();
   uint32_t* offsets = counts + total;
   uint32_t* cursor = offsets + total;
+  uint32_t* nseg = cursor + total;
+  uint32_t* segoff = nseg + total;
+  uint32_t* seg_bucket = segoff + total;
   Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
   Xyzz<BP>* wsums = buckets + total;
+  Xyzz<BP>* partial = wsums + W;
 
   BZ_CUDA(cudaMemsetAsync(counts, 0, cnt_b, st));
   { ProfScope p(ctx, PROF_MSM_DIGITS);
@@ -192,14 +235,19 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   { ProfScope p(ctx, PROF_MSM_SORT);
     msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
     msm_scatter_kernel<<<dim3((n + 255) / 256, W), 256, 0, st>>>(keys, n, W, nb, cursor, sorted); }
+  { ProfScope p(ctx, PROF_MSM_SORT);
+    msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*unused cursor copy, overwritten below*/, total);
+    msm_segmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket); }
   { ProfScope p(ctx, PROF_MSM_BUCKET);
-    msm_bucket_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, total, buckets); }
+    msm_segment_kernel<BP><<<(max_segs + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, nseg, segoff, seg_bucket, total, max_segs, partial);
+    msm_bucket_fold_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(partial, nseg, segoff, total, buckets); }
   uint32_t rthreads = nb >= 256 ? 256 : (nb >= 32 ? nb : 32);
   { ProfScope p(ctx, PROF_MSM_REDUCE);
     msm_reduce_kernel<BP><<<W, rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, wsums); }
   { ProfScope p(ctx, PROF_MSM_COMBINE);
     msm_combine_kernel<BP><<<1, 32, 0, st>>>(wsums, W, c, out); }
-  ctx->kernel_launches += 6;
+  ctx->kernel_launches += 10;
   BZ_CUDA(cudaGetLastError());
 }
 

@@ -276,7 +276,11 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import battlezips_halo2_b200 as bz
-    stream = torch.cuda.current_stream()
+    # a non-default torch stream: its handle is what libbzhalo2 launches on, so torch.cuda.Event timings on it
+    # bracket exactly our kernels (the legacy default stream has handle 0, which the ABI reads as "private stream")
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     ctx = bz.Context(local_rank, stream=stream.cuda_stream)
     wl = WORKLOADS[args.workload](args)
     wl.setup(ctx, rank)
