@@ -79,6 +79,10 @@ def load_library():
         "bz_coeff_to_extended": (i32, [vp, i32, vp, vp, u32, u32]),
         "bz_extended_to_coeff": (i32, [vp, i32, vp, u32]),
     }
+    declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",
+                          "bz_pk_num_random", "bz_pk_proof_size", "bz_create_proofs"}     # bound in plonk/prover.py
+    missing = [n for n in EXPORTS if n not in sigs and n not in declared_elsewhere]
+    assert not missing, f"unbound C-ABI symbols: {missing}"
     for name, (res, args) in sigs.items():
         fn = getattr(lib, name)
         fn.restype, fn.argtypes = res, args

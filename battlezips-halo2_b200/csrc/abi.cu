@@ -12,11 +12,6 @@ void curve_op_run(Ctx* ctx, int curve, int op, const void* a, const void* b, voi
 Ctx::~Ctx() {}
 }  // namespace bz
 
-struct bz_ctx {
-  bz::Ctx c;
-  bool own_stream = false;
-  std::set<void*> allocs;
-};
 
 #define BZ_TRY(ctx_, ...)                                    \
   try {                                                      \

@@ -4,6 +4,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <map>
+#include <memory>
+#include <set>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -111,6 +113,16 @@ struct NttFusion {
 // Transform `batch` polynomials.  in: batch x n_in(or N) elements, out: batch x N elements (may alias in when
 // n_in == 0).  Natural order in, natural order out.  omega = primitive 2^logN-th root from the field's
 // ROOT_OF_UNITY (inverse -> its inverse).
-void ntt_run(Ctx* ctx, int field, const void* in, void* out, int logN, bool inverse, int batch, const NttFusion& fu);
+// Optional outer batch (e.g. proofs): batch2 groups at in_stride2 / out_stride2 ELEMENTS apart, each holding `batch`
+// contiguous arrays.
+void ntt_run(Ctx* ctx, int field, const void* in, void* out, int logN, bool inverse, int batch, const NttFusion& fu,
+             int batch2 = 1, uint64_t in_stride2 = 0, uint64_t out_stride2 = 0);
 
 }  // namespace bz
+
+// the opaque handle of the C ABI
+struct bz_ctx {
+  bz::Ctx c;
+  bool own_stream = false;
+  std::set<void*> allocs;
+};

@@ -24,6 +24,7 @@ template <class P> struct NttPassArgs {
   uint64_t in_u, in_v, in_k;
   uint64_t out_u, out_v, out_k;
   uint64_t in_batch, out_batch;
+  uint64_t in_batch2, out_batch2;     // second (outer) batch dimension: blockIdx.z
   const Fe<P>* wsmall;
   uint32_t tw_logM;
   const Fe<P>* tw_lo;
@@ -58,7 +59,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
   const uint64_t line0 = (uint64_t)blockIdx.x << logT;
   const uint64_t u = line0 >> a.logV, v0 = line0 & ((1ull << a.logV) - 1);
   const uint64_t in_off0 = u * a.in_u + v0 * a.in_v;
-  const Fe<P>* in = a.in + (uint64_t)blockIdx.y * a.in_batch + in_off0;
+  const Fe<P>* in = a.in + (uint64_t)blockIdx.z * a.in_batch2 + (uint64_t)blockIdx.y * a.in_batch + in_off0;
 
   // ---- load (bit-reversed placement), fused zero-pad / coset pre-scale ----
   for (uint32_t idx = tid; idx < tile; idx += nth) {
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
 
   // ---- store through the output stride map, fused inter-pass twiddle / post-scale ----
   const uint64_t out_off0 = u * a.out_u + v0 * a.out_v;
-  Fe<P>* out = a.out + (uint64_t)blockIdx.y * a.out_batch + out_off0;
+  Fe<P>* out = a.out + (uint64_t)blockIdx.z * a.out_batch2 + (uint64_t)blockIdx.y * a.out_batch + out_off0;
   for (uint32_t idx = tid; idx < tile; idx += nth) {
     uint32_t k, line;
     if (a.out_k == 1) { k = idx & (L - 1); line = idx >> logL; }
@@ -174,7 +175,7 @@ template <class P> static const NttTable& get_tw(Ctx* ctx, int field, bool inver
   return t;
 }
 
-template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t nlines, int batch) {
+template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t nlines, int batch, int batch2) {
   uint32_t tile = 1u << (a.logL + a.logT);
   size_t smem = (size_t)tile * 32;
   int threads = tile >= 4096 ? 512 : (tile >= 512 ? 256 : (tile >= 64 ? (int)tile / 2 : 32));
@@ -183,7 +184,7 @@ template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t
     BZ_CUDA(cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     attr_set[P::ID] = true;
   }
-  dim3 grid((unsigned)(nlines >> a.logT), (unsigned)batch);
+  dim3 grid((unsigned)(nlines >> a.logT), (unsigned)batch, (unsigned)batch2);
   ProfScope prof(ctx, PROF_NTT_PASS);
   ntt_pass_kernel<P><<<grid, threads, smem, ctx->stream>>>(a);
   ctx->kernel_launches++;
@@ -191,7 +192,8 @@ template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t
 }
 
 template <class P>
-static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN, bool inverse, int batch, const NttFusion& fu) {
+static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN, bool inverse, int batch, const NttFusion& fu,
+                      int batch2, uint64_t in_stride2, uint64_t out_stride2) {
   BZ_CHECK(logN >= 0 && logN <= 30, "ntt: logN out of range");
   const bzh::Field& F = ctx->field(field);
   const uint64_t N = 1ull << logN;
@@ -223,10 +225,12 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
     a.k_limit = (uint32_t)n_in;
     a.pre_mode = fu.pre_zeta ? 1 : 0;
     a.post_mode = fu.post_mode;
-    launch_pass<P>(ctx, a, 1, batch);
+    a.in_batch2 = in_stride2; a.out_batch2 = out_stride2;
+    launch_pass<P>(ctx, a, 1, batch, batch2);
     return;
   }
-  ctx->ntt_tmp.ensure((size_t)batch * N * 32);
+  ctx->ntt_tmp.ensure((size_t)batch * batch2 * N * 32);
+  const uint64_t tmp_stride2 = (uint64_t)batch * N;
   Fe<P>* tmp = ctx->ntt_tmp.as<Fe<P>>();
   if (npass == 2) {
     int l1 = (logN + 1) / 2, l2 = logN - l1;
@@ -242,7 +246,8 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
       a.tw_logM = logN; a.tw_lo = tw.lo.as<Fe<P>>(); a.tw_hi = tw.hi.as<Fe<P>>();
       a.k_limit = (uint32_t)(n_in == N ? N1 : n_in / N2);
       a.pre_mode = fu.pre_zeta ? 1 : 0; a.post_mode = 0;
-      launch_pass<P>(ctx, a, N2, batch);
+      a.in_batch2 = in_stride2; a.out_batch2 = tmp_stride2;
+      launch_pass<P>(ctx, a, N2, batch, batch2);
     }
     {  // pass B: N1 contiguous lines of length N2, output index k1 + N1*k2
       NttPassArgs<P> a = base;
@@ -251,7 +256,8 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
       a.in_u = 0; a.in_v = N2; a.in_k = 1; a.out_u = 0; a.out_v = 1; a.out_k = N1;
       a.in_batch = N; a.out_batch = N;
       a.tw_logM = 0; a.k_limit = (uint32_t)N2; a.pre_mode = 0; a.post_mode = fu.post_mode;
-      launch_pass<P>(ctx, a, N1, batch);
+      a.in_batch2 = tmp_stride2; a.out_batch2 = out_stride2;
+      launch_pass<P>(ctx, a, N1, batch, batch2);
     }
     return;
   }
@@ -270,7 +276,8 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
     a.tw_logM = logN; a.tw_lo = twN.lo.as<Fe<P>>(); a.tw_hi = twN.hi.as<Fe<P>>();
     a.k_limit = (uint32_t)(n_in == N ? N1 : n_in / N23);
     a.pre_mode = fu.pre_zeta ? 1 : 0; a.post_mode = 0;
-    launch_pass<P>(ctx, a, N23, batch);
+    a.in_batch2 = in_stride2; a.out_batch2 = tmp_stride2;
+    launch_pass<P>(ctx, a, N23, batch, batch2);
   }
   {  // pass B1: lines (u = k1, v = j3), length N2 at stride N3, twiddle w_{N2N3}^(k*j3), in place
     NttPassArgs<P> a = base;
@@ -280,7 +287,8 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
     a.in_batch = N; a.out_batch = N;
     a.tw_logM = l2 + l3; a.tw_lo = tw23.lo.as<Fe<P>>(); a.tw_hi = tw23.hi.as<Fe<P>>();
     a.k_limit = (uint32_t)N2; a.pre_mode = 0; a.post_mode = 0;
-    launch_pass<P>(ctx, a, N1 * N3, batch);
+    a.in_batch2 = tmp_stride2; a.out_batch2 = tmp_stride2;
+    launch_pass<P>(ctx, a, N1 * N3, batch, batch2);
   }
   {  // pass B2: lines (u = k2, v = k1), contiguous length N3, output index k1 + N1*k2 + N1*N2*k3
     NttPassArgs<P> a = base;
@@ -289,14 +297,16 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
     a.in_u = N3; a.in_v = N23; a.in_k = 1; a.out_u = N1; a.out_v = 1; a.out_k = N1 * N2;
     a.in_batch = N; a.out_batch = N;
     a.tw_logM = 0; a.k_limit = (uint32_t)N3; a.pre_mode = 0; a.post_mode = fu.post_mode;
-    launch_pass<P>(ctx, a, N1 * N2, batch);
+    a.in_batch2 = tmp_stride2; a.out_batch2 = out_stride2;
+    launch_pass<P>(ctx, a, N1 * N2, batch, batch2);
   }
 }
 
-void ntt_run(Ctx* ctx, int field, const void* in, void* out, int logN, bool inverse, int batch, const NttFusion& fu) {
-  if (batch <= 0) return;
-  if (field == 0) ntt_run_t<FpP>(ctx, field, (const Fe<FpP>*)in, (Fe<FpP>*)out, logN, inverse, batch, fu);
-  else ntt_run_t<FqP>(ctx, field, (const Fe<FqP>*)in, (Fe<FqP>*)out, logN, inverse, batch, fu);
+void ntt_run(Ctx* ctx, int field, const void* in, void* out, int logN, bool inverse, int batch, const NttFusion& fu,
+             int batch2, uint64_t in_stride2, uint64_t out_stride2) {
+  if (batch <= 0 || batch2 <= 0) return;
+  if (field == 0) ntt_run_t<FpP>(ctx, field, (const Fe<FpP>*)in, (Fe<FpP>*)out, logN, inverse, batch, fu, batch2, in_stride2, out_stride2);
+  else ntt_run_t<FqP>(ctx, field, (const Fe<FqP>*)in, (Fe<FqP>*)out, logN, inverse, batch, fu, batch2, in_stride2, out_stride2);
 }
 
 }  // namespace bz

@@ -1,0 +1,1185 @@
+// create_proof on the device, batch-major (B independent proofs in lockstep).
+// Mirrors halo2_proofs 0.2.0 `plonk::create_proof` and the argument provers it drives
+// (U: src/plonk/prover.rs, src/plonk/{permutation,lookup,vanishing}/prover.rs, src/poly/multiopen/prover.rs,
+//  src/poly/commitment/prover.rs, src/transcript.rs; protocol order = SURVEY App. A steps 0-21).
+// Host work here is exactly what stays in Rust in the drop-in: Blake2b transcript, challenge bookkeeping,
+// blind arithmetic, the lookup sort/permute and multiopen set bookkeeping.  Everything that touches an n- or
+// 8n-sized array runs in the kernels of ntt.cu / fixedmsm.cu / poly.cuh.
+#include "../../include/bzhalo2.h"
+#include "common.h"
+#include "fixedmsm.h"
+#include "poly.cuh"
+#include "blake2b.h"
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <map>
+#include <set>
+
+typedef bzh::Fe HFe;
+
+namespace bz {
+
+typedef ::bz::Fe<FpP> DFe;      // device element type of the prover's scalar field (Vesta scalars = Fp)
+
+// ------------------------------------------------------------------------------------------------------
+struct ParamsImpl {
+  uint32_t k = 0, n = 0;
+  int curve = 0;
+  DevBuf g_w_u;         // n + 2 affine points: g || w || u
+  DevBuf gl_w;          // n + 1 affine points: g_lagrange || w
+  FixedBase fb_g, fb_gl;
+};
+
+struct Token { uint32_t op, a; int32_t b; };
+
+struct CircuitCopy {
+  uint32_t k, G, F, I, degree, bf;
+  std::vector<std::pair<int, int>> aq, fq, iq;
+  std::vector<std::pair<uint32_t, uint32_t>> perm;
+  std::vector<HFe> consts;
+  std::vector<Token> tokens;
+  std::vector<uint32_t> gate_off;
+  struct Lookup { std::vector<std::pair<uint32_t, uint32_t>> inputs, tables; };   // token ranges
+  std::vector<Lookup> lookups;
+  HFe vk_repr;
+};
+
+// kinds of the Regions table (see poly.cuh)
+enum { R_VAL = 0, R_POLY = 1, R_MISC = 2, R_RANDPOLY = 3, R_SPOLY = 4, R_SHPOLY = 5, R_SHVAL = 6, R_HCOEF = 7 };
+
+struct Query { int cid; int rot; PolyRef poly; int blind_kind; int blind_idx; };   // blind_kind: 0 = one, 1 = per-proof blind slot
+
+struct PkImpl {
+  ParamsImpl* params = nullptr;
+  CircuitCopy cs;
+  uint32_t n = 0, ext_k = 0, ext_n = 0, qdeg = 0;
+  uint32_t M = 0, L = 0, nsets = 0, chunk_len = 0, NS = 0, NC = 0, usable = 0;
+  HFe omega, omega_inv, ext_omega;
+  // device images
+  DevBuf lval;        // [F + M][n]  fixed values then sigma values (Lagrange)
+  DevBuf shpoly;      // [F + M][n]  coefficient form
+  DevBuf shcoset;     // [F + M + 5][ext_n]: fixed, sigma, l0, l_blind, l_last, active, coset_x
+  DevBuf omega_pows;  // [n]
+  DevBuf tev;         // [2^(ext_k-k)]
+  // programs
+  DevBuf lk_code, q_code, lk_rot, q_rot;
+  uint32_t lk_ninstr = 0, q_ninstr = 0;
+  // const table layout
+  uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, cstride;
+  std::vector<int> rots;                 // distinct rotations of all queries (+1, -1, last)
+  std::map<int, uint32_t> rot_const;     // rotation -> const index of x * omega^rot
+  // randomness layout (indices into the per-proof draw stream)
+  uint32_t R = 0;
+  uint32_t r_adv_rows, r_adv_blind, r_lk0, r_perm0, r_lkz0, r_randpoly, r_rand_blind, r_hblind, r_qprime, r_spoly, r_sblind, r_ipa;
+  // per-proof blind slots (host)
+  uint32_t nblinds = 0;
+  // static multiopen structure
+  std::vector<Query> queries;
+  struct CommInfo { PolyRef poly; int blind_kind, blind_idx; int set; };
+  std::vector<CommInfo> cmap;                  // first-appearance order
+  std::vector<std::vector<int>> point_sets;    // rotations per set, ordered by point index
+  // evaluation list (write order)
+  std::vector<EvalQuery> evals;
+  DevBuf d_evals;
+  // MISC slots
+  uint32_t NM = 0, m_cin0, m_hpoly, m_qset0, m_qtmp0, m_qprime, m_ppoly, m_pprime, m_b, m_coef, m_scl, m_scr;
+  uint32_t proof_size = 0;
+  // slots
+  uint32_t slot_inst(uint32_t i) const { return cs.G + i; }
+  uint32_t slot_lk(uint32_t l, uint32_t which) const { return cs.G + cs.I + 3 * l + which; }   // 0 A', 1 S', 2 Z
+  uint32_t slot_pz(uint32_t s) const { return cs.G + cs.I + 3 * L + s; }
+  // workspace cache
+  struct Work {
+    uint32_t batch = 0;
+    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in;
+    void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+  } work;
+  ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); }
+};
+
+// ------------------------------------------------------------------------------------------------------
+template <class P> __global__ void geometric_kernel(::bz::Fe<P>* out, ::bz::Fe<P> first, ::bz::Fe<P> base, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(out + i, fe_mul(first, fe_pow_u64<P>(base, i)));
+}
+
+static DFe dfe(const HFe& h) { DFe r; memcpy(r.l, h.l, 32); return r; }
+
+static uint32_t enc(uint32_t op, uint32_t x = 0, uint32_t y = 0) { return op | (x << 4) | (y << 16); }
+static uint32_t encc(uint32_t op, uint32_t idx) { return op | (idx << 4); }
+
+struct ProgBuilder {
+  std::vector<uint32_t> code;
+  std::vector<int32_t> rot_table;
+  std::map<int, uint32_t> rot_index;
+  int scale = 1;
+  int depth = 0, max_depth = 0;
+  uint32_t rot(int r) {
+    auto it = rot_index.find(r);
+    if (it != rot_index.end()) return it->second;
+    uint32_t idx = (uint32_t)rot_table.size();
+    rot_table.push_back(r * scale);
+    rot_index[r] = idx;
+    BZ_CHECK(idx < 65536, "too many rotations");
+    return idx;
+  }
+  void push() { if (++depth > max_depth) max_depth = depth; }
+  void pop(int k = 1) { depth -= k; }
+  void pp(uint32_t slot, int r) { BZ_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_P, slot, rot(r))); push(); }
+  void ps(uint32_t slot, int r) { BZ_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_S, slot, rot(r))); push(); }
+  void pc(uint32_t c) { code.push_back(encc(OP_PUSH_C, c)); push(); }
+  void add() { code.push_back(OP_ADD); pop(); }
+  void sub() { code.push_back(OP_SUB); pop(); }
+  void mul() { code.push_back(OP_MUL); pop(); }
+  void neg() { code.push_back(OP_NEG); }
+  void mulc(uint32_t c) { code.push_back(encc(OP_MULC, c)); }
+  void addc(uint32_t c) { code.push_back(encc(OP_ADDC, c)); }
+  void fold(uint32_t c) { code.push_back(encc(OP_FOLD, c)); pop(); }
+  void store(uint32_t k) { code.push_back(encc(OP_STORE, k)); pop(); }
+};
+
+// emit one expression (postfix tokens [lo,hi)); advice -> per-proof slot col, instance -> slot G + col, fixed -> shared slot col
+static void emit_expr(ProgBuilder& pb, const CircuitCopy& cs, uint32_t lo, uint32_t hi) {
+  for (uint32_t t = lo; t < hi; ++t) {
+    const Token& k = cs.tokens[t];
+    switch (k.op) {
+      case 0: pb.pc(k.a); break;
+      case 1: pb.pp(k.a, k.b); break;
+      case 2: pb.ps(k.a, k.b); break;
+      case 3: pb.pp(cs.G + k.a, k.b); break;
+      case 4: pb.neg(); break;
+      case 5: pb.add(); break;
+      case 6: pb.mul(); break;
+      case 7: pb.mulc(k.a); break;
+      default: throw Error(-1, "bad token op");
+    }
+  }
+}
+static void emit_compressed(ProgBuilder& pb, const CircuitCopy& cs, const std::vector<std::pair<uint32_t, uint32_t>>& exprs, uint32_t c_theta) {
+  for (size_t e = 0; e < exprs.size(); ++e) {
+    if (e > 0) pb.mulc(c_theta);
+    emit_expr(pb, cs, exprs[e].first, exprs[e].second);
+    if (e > 0) pb.add();
+  }
+}
+
+static uint32_t shslot_fixed(const PkImpl& pk, uint32_t c) { return c; }
+static uint32_t shslot_sigma(const PkImpl& pk, uint32_t j) { return pk.cs.F + j; }
+static uint32_t shslot_l0(const PkImpl& pk) { return pk.cs.F + pk.M; }
+static uint32_t shslot_llast(const PkImpl& pk) { return pk.cs.F + pk.M + 2; }
+static uint32_t shslot_active(const PkImpl& pk) { return pk.cs.F + pk.M + 3; }
+static uint32_t shslot_x(const PkImpl& pk) { return pk.cs.F + pk.M + 4; }
+
+static void push_column(ProgBuilder& pb, const PkImpl& pk, std::pair<uint32_t, uint32_t> col) {
+  if (col.first == 0) pb.pp(col.second, 0);
+  else if (col.first == 1) pb.ps(shslot_fixed(pk, col.second), 0);
+  else pb.pp(pk.slot_inst(col.second), 0);
+}
+
+static void build_programs(Ctx* ctx, PkImpl& pk) {
+  const CircuitCopy& cs = pk.cs;
+  // ---- lookup compression on the Lagrange domain: outputs 2l (input), 2l+1 (table)
+  {
+    ProgBuilder pb; pb.scale = 1;
+    for (uint32_t l = 0; l < pk.L; ++l) {
+      emit_compressed(pb, cs, cs.lookups[l].inputs, pk.C_THETA); pb.store(2 * l);
+      emit_compressed(pb, cs, cs.lookups[l].tables, pk.C_THETA); pb.store(2 * l + 1);
+    }
+    BZ_CHECK(pb.max_depth <= EVAL_STACK, "lookup expression too deep for the evaluator stack");
+    pk.lk_ninstr = (uint32_t)pb.code.size();
+    if (pk.lk_ninstr) {
+      pk.lk_code.alloc(pb.code.size() * 4);
+      BZ_CUDA(cudaMemcpy(pk.lk_code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
+      if (pb.rot_table.empty()) pb.rot_table.push_back(0);
+      pk.lk_rot.alloc(pb.rot_table.size() * 4);
+      BZ_CUDA(cudaMemcpy(pk.lk_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
+    }
+  }
+  // ---- h(X) on the extended coset
+  {
+    ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
+    const int last_rot = -((int)cs.bf + 1);
+    for (size_t g = 0; g + 1 < cs.gate_off.size(); ++g) {
+      emit_expr(pb, cs, cs.gate_off[g], cs.gate_off[g + 1]);
+      pb.fold(pk.C_Y);
+    }
+    if (pk.nsets) {
+      // l0 * (1 - z_0)
+      pb.pc(pk.C_ONE); pb.pp(pk.slot_pz(0), 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      // l_last * (z_l^2 - z_l)
+      uint32_t zl = pk.slot_pz(pk.nsets - 1);
+      pb.pp(zl, 0); pb.pp(zl, 0); pb.mul(); pb.pp(zl, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      // l0 * (z_i - z_{i-1}(w^last X))
+      for (uint32_t i = 1; i < pk.nsets; ++i) {
+        pb.pp(pk.slot_pz(i), 0); pb.pp(pk.slot_pz(i - 1), last_rot); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      }
+      for (uint32_t s = 0; s < pk.nsets; ++s) {
+        uint32_t c0 = s * pk.chunk_len, c1 = std::min<uint32_t>(pk.M, c0 + pk.chunk_len);
+        pb.pp(pk.slot_pz(s), 1);
+        for (uint32_t j = c0; j < c1; ++j) {
+          push_column(pb, pk, cs.perm[j]); pb.ps(shslot_sigma(pk, j), 0); pb.mulc(pk.C_BETA); pb.add(); pb.addc(pk.C_GAMMA); pb.mul();
+        }
+        pb.pp(pk.slot_pz(s), 0);
+        for (uint32_t j = c0; j < c1; ++j) {
+          push_column(pb, pk, cs.perm[j]); pb.ps(shslot_x(pk), 0); pb.mulc(pk.C_BD0 + j); pb.add(); pb.addc(pk.C_GAMMA); pb.mul();
+        }
+        pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      }
+    }
+    for (uint32_t l = 0; l < pk.L; ++l) {
+      uint32_t a = pk.slot_lk(l, 0), sp = pk.slot_lk(l, 1), z = pk.slot_lk(l, 2);
+      pb.pc(pk.C_ONE); pb.pp(z, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      pb.pp(z, 0); pb.pp(z, 0); pb.mul(); pb.pp(z, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      // z(wX)(a'+beta)(s'+gamma) - z(X)(A_theta+beta)(S_theta+gamma)
+      pb.pp(z, 1); pb.pp(a, 0); pb.addc(pk.C_BETA); pb.mul(); pb.pp(sp, 0); pb.addc(pk.C_GAMMA); pb.mul();
+      pb.pp(z, 0);
+      emit_compressed(pb, cs, cs.lookups[l].inputs, pk.C_THETA); pb.addc(pk.C_BETA); pb.mul();
+      emit_compressed(pb, cs, cs.lookups[l].tables, pk.C_THETA); pb.addc(pk.C_GAMMA); pb.mul();
+      pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      // l0 * (a' - s')
+      pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      // active * (a' - s')(a' - a'(w^-1 X))
+      pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.pp(a, 0); pb.pp(a, -1); pb.sub(); pb.mul(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+    }
+    pb.code.push_back(OP_MUL_T_STORE);
+    BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
+    pk.q_ninstr = (uint32_t)pb.code.size();
+    BZ_CHECK(pk.q_ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
+    pk.q_code.alloc(pb.code.size() * 4);
+    BZ_CUDA(cudaMemcpy(pk.q_code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
+    if (pb.rot_table.empty()) pb.rot_table.push_back(0);
+    pk.q_rot.alloc(pb.rot_table.size() * 4);
+    BZ_CUDA(cudaMemcpy(pk.q_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+static void add_query(PkImpl& pk, int cid, int rot, PolyRef poly, int bk, int bi) { pk.queries.push_back(Query{cid, rot, poly, bk, bi}); }
+
+// static structure of the multiopen argument (U: multiopen.rs::construct_intermediate_sets); points are
+// identified by their rotation (x * omega^rot are distinct for distinct rotations)
+static void build_multiopen(PkImpl& pk) {
+  std::vector<int> point_order;                       // rotation -> point index = position
+  auto point_index = [&](int rot) { for (size_t i = 0; i < point_order.size(); ++i) if (point_order[i] == rot) return (int)i; point_order.push_back(rot); return (int)point_order.size() - 1; };
+  struct Tmp { int cid; PolyRef poly; int bk, bi; std::vector<int> pidx; };
+  std::vector<Tmp> cm;
+  for (const Query& q : pk.queries) {
+    int pi = point_index(q.rot);
+    auto it = std::find_if(cm.begin(), cm.end(), [&](const Tmp& t) { return t.cid == q.cid; });
+    if (it == cm.end()) cm.push_back(Tmp{q.cid, q.poly, q.blind_kind, q.blind_idx, {pi}});
+    else it->pidx.push_back(pi);
+  }
+  std::vector<std::vector<int>> sets;                 // sorted unique point-index sets, first-appearance order
+  for (Tmp& t : cm) {
+    std::vector<int> s = t.pidx; std::sort(s.begin(), s.end()); s.erase(std::unique(s.begin(), s.end()), s.end());
+    int idx = -1;
+    for (size_t i = 0; i < sets.size(); ++i) if (sets[i] == s) idx = (int)i;
+    if (idx < 0) { sets.push_back(s); idx = (int)sets.size() - 1; }
+    pk.cmap.push_back(PkImpl::CommInfo{t.poly, t.bk, t.bi, idx});
+  }
+  for (auto& s : sets) { std::vector<int> r; for (int pi : s) r.push_back(point_order[pi]); pk.point_sets.push_back(r); }
+}
+
+// ------------------------------------------------------------------------------------------------------
+static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
+  PkImpl::Work& w = pk.work;
+  if (w.batch >= B) return;
+  const size_t n = pk.n, en = pk.ext_n, E = 32;
+  w.val.alloc(B * pk.NS * n * E);
+  w.poly.alloc(B * pk.NS * n * E);
+  w.coset.alloc(B * pk.NS * en * E);
+  w.misc.alloc(B * pk.NM * n * E);
+  w.rnd.alloc(B * (size_t)pk.R * E);
+  w.wide.alloc(B * (size_t)pk.R * 64);
+  w.hext.alloc(B * en * E);
+  w.hcoef.alloc(B * en * E);
+  w.nd.alloc(4 * B * n * E);
+  w.consts.alloc(B * (size_t)pk.cstride * E);
+  w.extras.alloc(B * 64 * 2 * E);
+  w.evalout.alloc(B * (pk.evals.size() + pk.point_sets.size() + 8) * E);
+  w.commits.alloc(B * 64 * 64);
+  w.ptrs.alloc(B * 64 * 2 * sizeof(void*));
+  w.descs.alloc(64 * 1024);
+  w.adv_in.alloc(1);
+  if (w.h_pinned) cudaFreeHost(w.h_pinned);
+  w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(64 * 64, (pk.evals.size() + 16) * E)), 1 << 20);
+  BZ_CUDA(cudaMallocHost(&w.h_pinned, w.h_pinned_bytes));
+  w.batch = B;
+}
+
+// ------------------------------------------------------------------------------------------------------
+}  // namespace bz
+
+using namespace bz;
+
+struct bz_params { ParamsImpl p; };
+struct bz_pk { PkImpl p; };
+static bz::Ctx* ctx_of(bz_ctx* c) { return &c->c; }
+
+#define PV_TRY(ctx_, ...)                                     \
+  bz::Ctx* C = ctx_of(ctx_);                                  \
+  try {                                                       \
+    cudaSetDevice(C->device);                                 \
+    __VA_ARGS__;                                              \
+    return BZ_OK;                                             \
+  } catch (const bz::Error& e) {                              \
+    C->last_error = e.what();                                 \
+    return e.code;                                            \
+  } catch (const std::exception& e) {                         \
+    C->last_error = e.what();                                 \
+    return BZ_ERR_INVALID;                                    \
+  }
+
+#define API __attribute__((visibility("default")))
+
+extern "C" {
+
+API int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, const void* g_lagrange, const void* w, const void* u,
+                         int window_bits, bz_params** out) {
+  PV_TRY(ctx, {
+    BZ_CHECK(out && g && g_lagrange && w && u, "null argument");
+    BZ_CHECK(k >= 1 && k <= 24, "k out of range");
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    *out = nullptr;
+    std::unique_ptr<bz_params> h(new bz_params());
+    ParamsImpl& p = h->p;
+    p.k = k; p.n = 1u << k; p.curve = curve;
+    const size_t n = p.n;
+    p.g_w_u.alloc((n + 2) * 64);
+    p.gl_w.alloc((n + 1) * 64);
+    BZ_CUDA(cudaMemcpy(p.g_w_u.p, g, n * 64, cudaMemcpyHostToDevice));
+    BZ_CUDA(cudaMemcpy((char*)p.g_w_u.p + n * 64, w, 64, cudaMemcpyHostToDevice));
+    BZ_CUDA(cudaMemcpy((char*)p.g_w_u.p + (n + 1) * 64, u, 64, cudaMemcpyHostToDevice));
+    BZ_CUDA(cudaMemcpy(p.gl_w.p, g_lagrange, n * 64, cudaMemcpyHostToDevice));
+    BZ_CUDA(cudaMemcpy((char*)p.gl_w.p + n * 64, w, 64, cudaMemcpyHostToDevice));
+    uint32_t c = window_bits > 0 ? (uint32_t)window_bits : 0;
+    if (!c) {
+      const char* e = getenv("BZ_FIXED_WINDOW");
+      c = e ? (uint32_t)atoi(e) : 0;
+      if (!c) {   // largest window whose two tables stay under ~24 GB
+        for (c = 13; c > 4; --c) {
+          double bytes = 2.0 * ((256 + c - 1) / c) * (double)(1u << (c - 1)) * (double)(n + 2) * 64.0;
+          if (bytes <= 24e9) break;
+        }
+      }
+    }
+    fixed_base_build(C, p.fb_g, curve, p.g_w_u.p, (uint32_t)n + 2, c);
+    fixed_base_build(C, p.fb_gl, curve, p.gl_w.p, (uint32_t)n + 1, c);
+    *out = h.release();
+  });
+}
+
+API void bz_params_destroy(bz_params* params) { delete params; }
+
+API int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* poly, const void* blind, void* out_affine) {
+  PV_TRY(ctx, {
+    BZ_CHECK(params && poly && blind && out_affine, "null argument");
+    ParamsImpl& p = params->p;
+    DevBuf d_poly, d_extra, d_ptrs, d_out;
+    d_poly.alloc((size_t)p.n * 32); d_extra.alloc(64); d_ptrs.alloc(2 * sizeof(void*)); d_out.alloc(64);
+    cudaStream_t st = C->stream;
+    BZ_CUDA(cudaMemcpyAsync(d_poly.p, poly, (size_t)p.n * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemsetAsync(d_extra.p, 0, 64, st));
+    BZ_CUDA(cudaMemcpyAsync(d_extra.p, blind, 32, cudaMemcpyHostToDevice, st));
+    void* ptrs[2] = {d_poly.p, d_extra.p};
+    BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+    const FixedBase& fb = lagrange_basis ? p.fb_gl : p.fb_g;
+    fixed_msm_run(C, fb, (const void* const*)d_ptrs.p, p.n, (const void* const*)((void**)d_ptrs.p + 1), 1, 16, d_out.p);
+    BZ_CUDA(cudaMemcpyAsync(out_affine, d_out.p, 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+API void bz_pk_destroy(bz_pk* pk) { delete pk; }
+API uint32_t bz_pk_num_random(const bz_pk* pk) { return pk ? pk->p.R : 0; }
+API uint32_t bz_pk_proof_size(const bz_pk* pk) { return pk ? pk->p.proof_size : 0; }
+
+API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values, bz_pk** out) {
+  PV_TRY(ctx, {
+    BZ_CHECK(out && params && cin, "null argument");
+    *out = nullptr;
+    BZ_CHECK(params->p.curve == 0, "prover: only the Vesta commitment curve (circuits over pallas::Base) is wired up");
+    BZ_CHECK(cin->k == params->p.k, "circuit k != params k");
+    std::unique_ptr<bz_pk> h(new bz_pk());
+    PkImpl& pk = h->p;
+    pk.params = &params->p;
+    const bzh::Field& F = C->fp;
+    CircuitCopy& cs = pk.cs;
+    cs.k = cin->k; cs.G = cin->num_advice; cs.F = cin->num_fixed; cs.I = cin->num_instance; cs.degree = cin->degree; cs.bf = cin->blinding_factors;
+    for (uint32_t i = 0; i < cin->n_advice_queries; ++i) cs.aq.push_back({cin->advice_queries[2 * i], cin->advice_queries[2 * i + 1]});
+    for (uint32_t i = 0; i < cin->n_fixed_queries; ++i) cs.fq.push_back({cin->fixed_queries[2 * i], cin->fixed_queries[2 * i + 1]});
+    for (uint32_t i = 0; i < cin->n_instance_queries; ++i) cs.iq.push_back({cin->instance_queries[2 * i], cin->instance_queries[2 * i + 1]});
+    for (uint32_t i = 0; i < cin->n_perm_columns; ++i) cs.perm.push_back({cin->perm_columns[2 * i], cin->perm_columns[2 * i + 1]});
+    cs.consts.resize(cin->n_constants);
+    if (cin->n_constants) memcpy(cs.consts.data(), cin->constants, (size_t)cin->n_constants * 32);
+    cs.tokens.resize(cin->n_tokens);
+    for (uint32_t i = 0; i < cin->n_tokens; ++i) cs.tokens[i] = Token{cin->tokens[i].op, cin->tokens[i].a, cin->tokens[i].b};
+    cs.gate_off.assign(cin->gate_poly_offsets, cin->gate_poly_offsets + cin->n_gate_polys + 1);
+    {
+      uint32_t e = 0;
+      for (uint32_t l = 0; l < cin->n_lookups; ++l) {
+        CircuitCopy::Lookup lk;
+        for (uint32_t j = 0; j < cin->lookup_input_counts[l]; ++j, ++e) lk.inputs.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
+        for (uint32_t j = 0; j < cin->lookup_table_counts[l]; ++j, ++e) lk.tables.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
+        cs.lookups.push_back(lk);
+      }
+    }
+    {
+      uint64_t raw[4]; memcpy(raw, cin->vk_transcript_repr, 32);
+      cs.vk_repr = F.from_raw(raw);
+    }
+    BZ_CHECK(cs.degree >= 3, "cs degree must be >= 3");
+    pk.n = 1u << cs.k;
+    pk.qdeg = cs.degree - 1;
+    pk.ext_k = cs.k;
+    while ((1ull << pk.ext_k) < (uint64_t)pk.n * pk.qdeg) ++pk.ext_k;
+    pk.ext_n = 1u << pk.ext_k;
+    pk.M = (uint32_t)cs.perm.size(); pk.L = (uint32_t)cs.lookups.size();
+    pk.chunk_len = cs.degree - 2;
+    pk.nsets = pk.M ? (pk.M + pk.chunk_len - 1) / pk.chunk_len : 0;
+    pk.NS = cs.G + cs.I + 3 * pk.L + pk.nsets;
+    pk.NC = (uint32_t)cs.consts.size();
+    pk.usable = pk.n - (cs.bf + 1);
+    BZ_CHECK(pk.chunk_len <= 8, "permutation chunk too wide");
+    const uint32_t n = pk.n, en = pk.ext_n;
+    // domain constants
+    pk.ext_omega = F.root_of_unity();
+    for (uint32_t i = pk.ext_k; i < 32; ++i) pk.ext_omega = F.sqr(pk.ext_omega);
+    pk.omega = pk.ext_omega;
+    for (uint32_t i = cs.k; i < pk.ext_k; ++i) pk.omega = F.sqr(pk.omega);
+    pk.omega_inv = F.inv(pk.omega);
+    cudaStream_t st = C->stream;
+    // ---- Lagrange images, polys, cosets
+    const uint32_t FM = cs.F + pk.M;
+    pk.lval.alloc((size_t)std::max(1u, FM) * n * 32);
+    if (cs.F) BZ_CUDA(cudaMemcpyAsync(pk.lval.p, fixed_values, (size_t)cs.F * n * 32, cudaMemcpyHostToDevice, st));
+    if (pk.M) BZ_CUDA(cudaMemcpyAsync((char*)pk.lval.p + (size_t)cs.F * n * 32, sigma_values, (size_t)pk.M * n * 32, cudaMemcpyHostToDevice, st));
+    pk.shpoly.alloc((size_t)std::max(1u, FM) * n * 32);
+    pk.shcoset.alloc((size_t)(FM + 5) * en * 32);
+    NttFusion inv; inv.post_mode = 1;
+    NttFusion ext; ext.n_in = pk.ext_k > cs.k ? n : 0; ext.pre_zeta = true;
+    if (FM) {
+      ntt_run(C, 0, pk.lval.p, pk.shpoly.p, cs.k, true, FM, inv);
+      ntt_run(C, 0, pk.shpoly.p, pk.shcoset.p, pk.ext_k, false, FM, ext);
+    }
+    {  // l0, l_blind, l_last, active
+      std::vector<HFe> tmp((size_t)4 * n, F.zero());
+      tmp[0] = F.one();
+      for (uint32_t i = n - cs.bf; i < n; ++i) tmp[(size_t)n + i] = F.one();
+      tmp[(size_t)2 * n + (n - cs.bf - 1)] = F.one();
+      for (uint32_t i = 0; i < n - cs.bf - 1; ++i) tmp[(size_t)3 * n + i] = F.one();
+      DevBuf d_l, d_p;
+      d_l.alloc((size_t)4 * n * 32); d_p.alloc((size_t)4 * n * 32);
+      BZ_CUDA(cudaMemcpyAsync(d_l.p, tmp.data(), (size_t)4 * n * 32, cudaMemcpyHostToDevice, st));
+      ntt_run(C, 0, d_l.p, d_p.p, cs.k, true, 4, inv);
+      ntt_run(C, 0, d_p.p, (char*)pk.shcoset.p + (size_t)FM * en * 32, pk.ext_k, false, 4, ext);
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
+    geometric_kernel<FpP><<<(en + 127) / 128, 128, 0, st>>>((DFe*)pk.shcoset.p + (size_t)(FM + 4) * en, dfe(F.zeta()), dfe(pk.ext_omega), en);
+    pk.omega_pows.alloc((size_t)n * 32);
+    geometric_kernel<FpP><<<(n + 127) / 128, 128, 0, st>>>((DFe*)pk.omega_pows.p, dfe(F.one()), dfe(pk.omega), n);
+    C->kernel_launches += 2;
+    {  // t_evaluations
+      uint32_t tn = 1u << (pk.ext_k - cs.k);
+      HFe orig = F.pow_u64(F.zeta(), n), step = F.pow_u64(pk.ext_omega, n), cur = orig;
+      std::vector<HFe> t;
+      for (uint32_t i = 0; i < tn; ++i) { t.push_back(F.inv(F.sub(cur, F.one()))); cur = F.mul(cur, step); }
+      pk.tev.alloc((size_t)tn * 32);
+      BZ_CUDA(cudaMemcpyAsync(pk.tev.p, t.data(), (size_t)tn * 32, cudaMemcpyHostToDevice, st));
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
+    // ---- const table layout
+    uint32_t c = pk.NC;
+    pk.C_ONE = c++; pk.C_THETA = c++; pk.C_BETA = c++; pk.C_GAMMA = c++; pk.C_Y = c++; pk.C_X = c++; pk.C_XN = c++;
+    pk.C_X1 = c++; pk.C_X2 = c++; pk.C_X3 = c++; pk.C_X4 = c++; pk.C_XI = c++; pk.C_Z = c++; pk.C_U = c++; pk.C_UINV = c++;
+    pk.C_BD0 = c; c += pk.M;
+    {
+      std::set<int> rs;
+      for (auto& q : cs.aq) rs.insert(q.second);
+      for (auto& q : cs.fq) rs.insert(q.second);
+      for (auto& q : cs.iq) rs.insert(q.second);
+      rs.insert(0); rs.insert(1); rs.insert(-1); rs.insert(-((int)cs.bf + 1));
+      pk.C_ROT0 = c;
+      for (int r : rs) { pk.rots.push_back(r); pk.rot_const[r] = c++; }
+    }
+    pk.cstride = c;
+    // ---- randomness layout
+    uint32_t r = 0;
+    pk.r_adv_rows = r; r += cs.G * (cs.bf + 1);
+    pk.r_adv_blind = r; r += cs.G;
+    pk.r_lk0 = r; r += pk.L * (2 * (cs.bf + 1) + 2);
+    pk.r_perm0 = r; r += pk.nsets * (cs.bf + 1);
+    pk.r_lkz0 = r; r += pk.L * (cs.bf + 1);
+    pk.r_randpoly = r; r += n;
+    pk.r_rand_blind = r; r += 1;
+    pk.r_hblind = r; r += pk.qdeg;
+    pk.r_qprime = r; r += 1;
+    pk.r_spoly = r; r += n;
+    pk.r_sblind = r; r += 1;
+    pk.r_ipa = r; r += 2 * cs.k;
+    pk.R = r;
+    // ---- MISC slots
+    uint32_t m = 0;
+    pk.m_cin0 = m; m += 2 * pk.L;
+    pk.m_hpoly = m++;
+    // ---- queries.  blind slots: advice[G], lookup (A',S',Z)[3L], perm[nsets], h, random
+    auto b_adv = [&](uint32_t g) { return (int)g; };
+    auto b_lk = [&](uint32_t l, uint32_t w) { return (int)(cs.G + 3 * l + w); };
+    auto b_pz = [&](uint32_t s) { return (int)(cs.G + 3 * pk.L + s); };
+    const int b_h = (int)(cs.G + 3 * pk.L + pk.nsets), b_rand = b_h + 1;
+    pk.nblinds = b_rand + 1;
+    const int last_rot = -((int)cs.bf + 1);
+    int cid_inst = 0, cid_adv = 1000, cid_pz = 2000, cid_lk = 3000, cid_fix = 4000, cid_sig = 5000, cid_h = 6000, cid_rand = 6001;
+    for (auto& q : cs.iq) add_query(pk, cid_inst + q.first, q.second, PolyRef{R_POLY, pk.slot_inst(q.first)}, 0, 0);
+    for (auto& q : cs.aq) add_query(pk, cid_adv + q.first, q.second, PolyRef{R_POLY, (uint32_t)q.first}, 1, b_adv(q.first));
+    for (uint32_t s = 0; s < pk.nsets; ++s) {
+      add_query(pk, cid_pz + s, 0, PolyRef{R_POLY, pk.slot_pz(s)}, 1, b_pz(s));
+      add_query(pk, cid_pz + s, 1, PolyRef{R_POLY, pk.slot_pz(s)}, 1, b_pz(s));
+    }
+    for (int s = (int)pk.nsets - 2; s >= 0; --s) add_query(pk, cid_pz + s, last_rot, PolyRef{R_POLY, pk.slot_pz(s)}, 1, b_pz(s));
+    for (uint32_t l = 0; l < pk.L; ++l) {
+      add_query(pk, cid_lk + 3 * l + 2, 0, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2));
+      add_query(pk, cid_lk + 3 * l + 0, 0, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0));
+      add_query(pk, cid_lk + 3 * l + 1, 0, PolyRef{R_POLY, pk.slot_lk(l, 1)}, 1, b_lk(l, 1));
+      add_query(pk, cid_lk + 3 * l + 0, -1, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0));
+      add_query(pk, cid_lk + 3 * l + 2, 1, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2));
+    }
+    for (auto& q : cs.fq) add_query(pk, cid_fix + q.first, q.second, PolyRef{R_SHPOLY, (uint32_t)q.first}, 0, 0);
+    for (uint32_t j = 0; j < pk.M; ++j) add_query(pk, cid_sig + j, 0, PolyRef{R_SHPOLY, cs.F + j}, 0, 0);
+    add_query(pk, cid_h, 0, PolyRef{R_MISC, pk.m_hpoly}, 1, b_h);
+    add_query(pk, cid_rand, 0, PolyRef{R_RANDPOLY, 0}, 1, b_rand);
+    build_multiopen(pk);
+    const uint32_t nps = (uint32_t)pk.point_sets.size();
+    pk.m_qset0 = m; m += nps;
+    pk.m_qtmp0 = m; m += 2 * nps;
+    pk.m_qprime = m++; pk.m_ppoly = m++; pk.m_pprime = m++; pk.m_b = m++; pk.m_coef = m++; pk.m_scl = m++; pk.m_scr = m++;
+    pk.NM = m;
+    // ---- evaluation list in transcript order (steps 14-18)
+    auto ev = [&](PolyRef p, int rot) { pk.evals.push_back(EvalQuery{p, pk.rot_const.at(rot)}); };
+    for (auto& q : cs.iq) ev(PolyRef{R_POLY, pk.slot_inst(q.first)}, q.second);
+    for (auto& q : cs.aq) ev(PolyRef{R_POLY, (uint32_t)q.first}, q.second);
+    for (auto& q : cs.fq) ev(PolyRef{R_SHPOLY, (uint32_t)q.first}, q.second);
+    ev(PolyRef{R_RANDPOLY, 0}, 0);
+    for (uint32_t j = 0; j < pk.M; ++j) ev(PolyRef{R_SHPOLY, cs.F + j}, 0);
+    for (uint32_t s = 0; s < pk.nsets; ++s) {
+      ev(PolyRef{R_POLY, pk.slot_pz(s)}, 0); ev(PolyRef{R_POLY, pk.slot_pz(s)}, 1);
+      if (s + 1 != pk.nsets) ev(PolyRef{R_POLY, pk.slot_pz(s)}, last_rot);
+    }
+    for (uint32_t l = 0; l < pk.L; ++l) {
+      ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1);
+      ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, -1);
+      ev(PolyRef{R_POLY, pk.slot_lk(l, 1)}, 0);
+    }
+    pk.d_evals.alloc(pk.evals.size() * sizeof(EvalQuery));
+    BZ_CUDA(cudaMemcpy(pk.d_evals.p, pk.evals.data(), pk.evals.size() * sizeof(EvalQuery), cudaMemcpyHostToDevice));
+    // proof size: points (32 B) + scalars (32 B)
+    uint32_t npoints = cs.G + 2 * pk.L + pk.nsets + pk.L + 1 + pk.qdeg + 1 + 1 + 2 * cs.k;
+    uint32_t nscalars = (uint32_t)pk.evals.size() + nps + 2;
+    pk.proof_size = 32 * (npoints + nscalars);
+    build_programs(C, pk);
+    BZ_CUDA(cudaStreamSynchronize(st));
+    *out = h.release();
+  });
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------------
+namespace bz {
+
+struct HostPoint { uint8_t x[32], y[32]; bool identity; };
+
+static void affine_to_host(const bzh::Field& Fq, const uint64_t* mont, HostPoint& p) {
+  HFe x, y; memcpy(x.l, mont, 32); memcpy(y.l, mont + 4, 32);
+  p.identity = x.is_zero() && y.is_zero();
+  Fq.to_repr(x, p.x); Fq.to_repr(y, p.y);
+}
+
+struct ProofState {
+  bzh::Blake2b st{"Halo2-Transcript"};
+  uint8_t* out; size_t pos = 0;
+  std::vector<HFe> blinds;      // per-proof blind slots
+  std::vector<HFe> consts;      // per-proof const table (host copy)
+  const uint8_t* wide;         // this proof's RNG words
+};
+
+static void t_common_scalar(ProofState& ps, const bzh::Field& F, const HFe& s) {
+  uint8_t tag = 2, r[32]; F.to_repr(s, r); ps.st.update(&tag, 1); ps.st.update(r, 32);
+}
+static void t_write_scalar(ProofState& ps, const bzh::Field& F, const HFe& s) {
+  uint8_t tag = 2, r[32]; F.to_repr(s, r); ps.st.update(&tag, 1); ps.st.update(r, 32);
+  memcpy(ps.out + ps.pos, r, 32); ps.pos += 32;
+}
+static void t_common_point(ProofState& ps, const HostPoint& p) {
+  if (p.identity) throw Error(BZ_ERR_INVALID, "cannot write points at infinity to the transcript");
+  uint8_t tag = 1; ps.st.update(&tag, 1); ps.st.update(p.x, 32); ps.st.update(p.y, 32);
+}
+static void t_write_point(ProofState& ps, const HostPoint& p) {
+  t_common_point(ps, p);
+  memcpy(ps.out + ps.pos, p.x, 32);
+  ps.out[ps.pos + 31] |= (uint8_t)((p.y[0] & 1) << 7);
+  ps.pos += 32;
+}
+static HFe t_squeeze(ProofState& ps, const bzh::Field& F) {
+  uint8_t tag = 0, h[64]; ps.st.update(&tag, 1); ps.st.finalize(h);
+  return F.from_bytes_wide(h);
+}
+static HFe rnd_host(const ProofState& ps, const bzh::Field& F, uint32_t idx) { return F.from_bytes_wide(ps.wide + (size_t)idx * 64); }
+
+struct Prover {
+  Ctx* C; PkImpl& pk; uint32_t B;
+  const bzh::Field& F; const bzh::Field& Fq;
+  cudaStream_t st;
+  PkImpl::Work& w;
+  Regions reg;
+  std::vector<ProofState> ps;
+  uint32_t n, en, k;
+  size_t desc_off = 0;
+
+  Prover(Ctx* c, PkImpl& p, uint32_t b) : C(c), pk(p), B(b), F(c->fp), Fq(c->fq), st(c->stream), w(p.work), ps(b) {
+    n = pk.n; en = pk.ext_n; k = pk.cs.k;
+    memset(&reg, 0, sizeof(reg));
+    reg.base[R_VAL] = w.val.p; reg.stride[R_VAL] = (uint64_t)pk.NS * n;
+    reg.base[R_POLY] = w.poly.p; reg.stride[R_POLY] = (uint64_t)pk.NS * n;
+    reg.base[R_MISC] = w.misc.p; reg.stride[R_MISC] = (uint64_t)pk.NM * n;
+    reg.base[R_RANDPOLY] = (DFe*)w.rnd.p + pk.r_randpoly; reg.stride[R_RANDPOLY] = pk.R;
+    reg.base[R_SPOLY] = (DFe*)w.rnd.p + pk.r_spoly; reg.stride[R_SPOLY] = pk.R;
+    reg.base[R_SHPOLY] = pk.shpoly.p; reg.stride[R_SHPOLY] = 0;
+    reg.base[R_SHVAL] = pk.lval.p; reg.stride[R_SHVAL] = 0;
+    reg.base[R_HCOEF] = w.hcoef.p; reg.stride[R_HCOEF] = en;
+  }
+
+  DFe* val(uint32_t b, uint32_t slot) { return (DFe*)w.val.p + ((uint64_t)b * pk.NS + slot) * n; }
+  DFe* polyp(uint32_t b, uint32_t slot) { return (DFe*)w.poly.p + ((uint64_t)b * pk.NS + slot) * n; }
+  DFe* misc(uint32_t b, uint32_t slot) { return (DFe*)w.misc.p + ((uint64_t)b * pk.NM + slot) * n; }
+  DFe* rnd(uint32_t b, uint32_t idx) { return (DFe*)w.rnd.p + (uint64_t)b * pk.R + idx; }
+
+  // small descriptor arena in device memory (reset per phase)
+  template <class T> T* upload_desc(const std::vector<T>& v) {
+    size_t bytes = v.size() * sizeof(T);
+    desc_off = (desc_off + 15) & ~size_t(15);
+    BZ_CHECK(desc_off + bytes <= w.descs.bytes, "descriptor arena overflow");
+    T* d = (T*)((char*)w.descs.p + desc_off);
+    BZ_CUDA(cudaMemcpyAsync(d, v.data(), bytes, cudaMemcpyHostToDevice, st));
+    desc_off += bytes;
+    return d;
+  }
+
+  void upload_consts() {
+    std::vector<HFe> all((size_t)B * pk.cstride);
+    for (uint32_t b = 0; b < B; ++b) memcpy(&all[(size_t)b * pk.cstride], ps[b].consts.data(), (size_t)pk.cstride * 32);
+    BZ_CUDA(cudaMemcpyAsync(w.consts.p, all.data(), all.size() * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));       // `all` goes out of scope
+  }
+
+  // ---- batched NTT helpers over slot ranges ----
+  void to_coeff(uint32_t slot0, uint32_t count) {
+    NttFusion fu; fu.post_mode = 1;
+    ntt_run(C, 0, val(0, slot0), polyp(0, slot0), k, true, count, fu, B, (uint64_t)pk.NS * n, (uint64_t)pk.NS * n);
+  }
+  void to_coset(uint32_t slot0, uint32_t count) {
+    NttFusion fu; fu.n_in = pk.ext_k > k ? n : 0; fu.pre_zeta = true;
+    ntt_run(C, 0, polyp(0, slot0), (DFe*)w.coset.p + (uint64_t)slot0 * en, pk.ext_k, false, count, fu, B, (uint64_t)pk.NS * n, (uint64_t)pk.NS * en);
+  }
+
+  // ---- commitments: a list of (main poly device ptr fn, blind) per proof; results host-side ----
+  struct CommitReq { PolyRef poly; bool lagrange; };
+  // commits reqs (same list for every proof); blinds[b][i] host scalars for point w.  Output points[b][i].
+  void commit(const std::vector<CommitReq>& reqs, const std::vector<std::vector<HFe>>& blinds, std::vector<std::vector<HostPoint>>& pts,
+              const std::vector<std::array<HFe, 2>>* extras_full = nullptr) {
+    const uint32_t nr = (uint32_t)reqs.size();
+    pts.assign(B, std::vector<HostPoint>(nr));
+    // all requests of one call share the basis
+    bool lag = reqs[0].lagrange;
+    const FixedBase& fb = lag ? pk.params->fb_gl : pk.params->fb_g;
+    std::vector<void*> mainp((size_t)B * nr), extrap((size_t)B * nr);
+    std::vector<HFe> ex((size_t)B * nr * 2, F.zero());
+    BZ_CHECK((size_t)B * nr * 2 * 32 <= w.extras.bytes && (size_t)B * nr * 2 * sizeof(void*) <= w.ptrs.bytes && (size_t)B * nr * 64 <= w.commits.bytes,
+             "commit batch too large for the workspace");
+    for (uint32_t b = 0; b < B; ++b)
+      for (uint32_t i = 0; i < nr; ++i) {
+        BZ_CHECK(reqs[i].lagrange == lag, "mixed bases in one commit batch");
+        size_t j = (size_t)b * nr + i;
+        uint64_t len = n;
+        mainp[j] = (DFe*)reg.base[reqs[i].poly.kind] + (uint64_t)b * reg.stride[reqs[i].poly.kind] + (uint64_t)reqs[i].poly.slot * len;
+        extrap[j] = (DFe*)w.extras.p + j * 2;
+        if (extras_full) { ex[j * 2] = (*extras_full)[j][0]; ex[j * 2 + 1] = (*extras_full)[j][1]; }
+        else ex[j * 2] = blinds[b][i];
+      }
+    BZ_CUDA(cudaMemcpyAsync(w.extras.p, ex.data(), ex.size() * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), mainp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + (size_t)B * nr, extrap.data(), extrap.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    uint32_t n_msm = B * nr;
+    uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / std::max(1u, n_msm))));
+    fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + (size_t)B * nr), n_msm, chunks, w.commits.p);
+    read_points(n_msm, nr, pts);
+  }
+  void read_points(uint32_t n_msm, uint32_t nr, std::vector<std::vector<HostPoint>>& pts) {
+    BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.commits.p, (size_t)n_msm * 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    const uint64_t* h = (const uint64_t*)w.h_pinned;
+    for (uint32_t b = 0; b < B; ++b)
+      for (uint32_t i = 0; i < nr; ++i) affine_to_host(Fq, h + ((size_t)b * nr + i) * 8, pts[b][i]);
+  }
+
+  void launch_copy(const std::vector<CopyDesc>& d, uint64_t len) {
+    if (d.empty()) return;
+    CopyDesc* dd = upload_desc(d);
+    copy_rows_kernel<FpP><<<dim3((unsigned)d.size(), B), 64, 0, st>>>(reg, len, dd, (const DFe*)w.rnd.p, pk.R);
+    C->kernel_launches++;
+  }
+
+  void grand_product(PolyRef zref, bool has_z0, PolyRef z0ref, uint32_t z0_index) {
+    DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n; DFe* pnum = den + (uint64_t)B * n; DFe* sden = pnum + (uint64_t)B * n;
+    ProfScope prof(C, PROF_SCAN);
+    product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0);
+    product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
+    grand_product_finish_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(pnum, sden, n, reg, zref, n, z0ref, z0_index, has_z0 ? 1 : 0);
+    C->kernel_launches += 3;
+  }
+
+  void evaluate(const EvalQuery* d_queries, uint32_t nq, std::vector<std::vector<HFe>>& out) {
+    {
+      ProfScope prof(C, PROF_EVAL);
+      eval_queries_kernel<FpP><<<dim3(nq, B), EVALQ_THREADS, 0, st>>>(reg, n, d_queries, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, nq);
+      C->kernel_launches++;
+    }
+    BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.evalout.p, (size_t)B * nq * 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    out.assign(B, std::vector<HFe>(nq));
+    for (uint32_t b = 0; b < B; ++b) memcpy(out[b].data(), (char*)w.h_pinned + (size_t)b * nq * 32, (size_t)nq * 32);
+  }
+
+  void lincomb(const std::vector<LinCombDesc>& descs, const std::vector<PolyRef>& refs) {
+    LinCombDesc* dd = upload_desc(descs);
+    PolyRef* dr = upload_desc(refs);
+    ProfScope prof(C, PROF_POLY);
+    lincomb_kernel<FpP><<<dim3((n + 127) / 128, B, (unsigned)descs.size()), 128, 0, st>>>(reg, n, dd, dr, (const DFe*)w.consts.p, pk.cstride);
+    C->kernel_launches++;
+  }
+
+  void run(const void* instances, const uint32_t* instance_lens, uint32_t instance_stride, const void* advice, const void* rand_wide, uint8_t* proofs);
+};
+
+void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t instance_stride, const void* advice, const void* rand_wide, uint8_t* proofs) {
+  const CircuitCopy& cs = pk.cs;
+  const uint32_t G = cs.G, I = cs.I, L = pk.L, bf = cs.bf, usable = pk.usable;
+  for (uint32_t i = 0; i < I; ++i) if (instance_lens[i] > usable) throw Error(BZ_ERR_INVALID, "Error::InstanceTooLarge");
+  // ---- per-proof host state
+  for (uint32_t b = 0; b < B; ++b) {
+    ps[b].out = proofs + (size_t)b * pk.proof_size;
+    memset(ps[b].out, 0, pk.proof_size);
+    ps[b].wide = (const uint8_t*)rand_wide + (size_t)b * pk.R * 64;
+    ps[b].blinds.assign(pk.nblinds, F.zero());
+    ps[b].consts.assign(pk.cstride, F.zero());
+    for (uint32_t i = 0; i < pk.NC; ++i) ps[b].consts[i] = cs.consts[i];
+    ps[b].consts[pk.C_ONE] = F.one();
+    t_common_scalar(ps[b], F, cs.vk_repr);                                     // step 0
+  }
+  // ---- upload: randomness (reduced on device), advice, instances
+  BZ_CUDA(cudaMemcpyAsync(w.wide.p, rand_wide, (size_t)B * pk.R * 64, cudaMemcpyHostToDevice, st));
+  {
+    uint64_t tot = (uint64_t)B * pk.R;
+    from_u512_kernel<FpP><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>((const uint32_t*)w.wide.p, (DFe*)w.rnd.p, tot);
+    C->kernel_launches++;
+  }
+  BZ_CUDA(cudaMemsetAsync(w.val.p, 0, (size_t)B * pk.NS * n * 32, st));
+  for (uint32_t b = 0; b < B; ++b) {
+    BZ_CUDA(cudaMemcpyAsync(val(b, 0), (const char*)advice + (size_t)b * G * n * 32, (size_t)G * n * 32, cudaMemcpyHostToDevice, st));
+    for (uint32_t i = 0; i < I; ++i)
+      if (instance_lens[i])
+        BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_inst(i)), (const char*)instances + ((size_t)b * I + i) * instance_stride * 32,
+                                (size_t)instance_lens[i] * 32, cudaMemcpyHostToDevice, st));
+  }
+  desc_off = 0;
+  // ---- step 1: instance commitments (blind 1), absorbed
+  std::vector<std::vector<HostPoint>> pts;
+  if (I) {
+    std::vector<CommitReq> reqs;
+    for (uint32_t i = 0; i < I; ++i) reqs.push_back({PolyRef{R_VAL, pk.slot_inst(i)}, true});
+    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(I, F.one()));
+    commit(reqs, bl, pts);
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t i = 0; i < I; ++i) t_common_point(ps[b], pts[b][i]);
+  }
+  // ---- step 2: advice blinding rows, blinds, commitments
+  {
+    std::vector<CopyDesc> cd;
+    for (uint32_t g = 0; g < G; ++g) cd.push_back(CopyDesc{PolyRef{R_VAL, g}, usable, pk.r_adv_rows + g * (bf + 1), bf + 1});
+    launch_copy(cd, n);
+    std::vector<CommitReq> reqs;
+    for (uint32_t g = 0; g < G; ++g) reqs.push_back({PolyRef{R_VAL, g}, true});
+    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(G));
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t g = 0; g < G; ++g) { bl[b][g] = rnd_host(ps[b], F, pk.r_adv_blind + g); ps[b].blinds[g] = bl[b][g]; }
+    commit(reqs, bl, pts);
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t g = 0; g < G; ++g) t_write_point(ps[b], pts[b][g]);
+    to_coeff(0, G + I);
+    to_coset(0, G + I);
+  }
+  // ---- step 3
+  for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_THETA] = t_squeeze(ps[b], F);
+  upload_consts();
+  // ---- steps 4-5: lookups
+  if (L) {
+    {
+      EvalArgs<FpP> a{};
+      a.code = (const uint32_t*)pk.lk_code.p; a.n_instr = pk.lk_ninstr; a.logN = k; a.rot = (const int32_t*)pk.lk_rot.p;
+      a.pbase = (const DFe*)w.val.p; a.pstride = (uint64_t)pk.NS * n; a.sbase = (const DFe*)pk.lval.p;
+      a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
+      a.out = misc(0, pk.m_cin0); a.ostride = (uint64_t)pk.NM * n; a.tev = nullptr; a.tn = 1;
+      ProfScope prof(C, PROF_QUOTIENT);
+      eval_program_kernel<FpP><<<dim3((n + 127) / 128, B), 128, pk.lk_ninstr * 4, st>>>(a);
+      C->kernel_launches++;
+    }
+    // host: sort / permute (U: lookup/prover.rs::permute_expression_pair)
+    const size_t per = (size_t)2 * L * n * 32;
+    BZ_CHECK((size_t)B * per <= w.h_pinned_bytes, "pinned staging too small");
+    for (uint32_t b = 0; b < B; ++b) BZ_CUDA(cudaMemcpyAsync((char*)w.h_pinned + b * per, misc(b, pk.m_cin0), per, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    std::vector<HFe> up((size_t)B * L * 2 * n, F.zero());
+    for (uint32_t b = 0; b < B; ++b)
+      for (uint32_t l = 0; l < L; ++l) {
+        const HFe* cinp = (const HFe*)((char*)w.h_pinned + b * per) + (size_t)(2 * l) * n;
+        const HFe* ctab = cinp + n;
+        struct Key { std::array<uint64_t, 4> v; uint32_t idx; };
+        auto canon = [&](const HFe& x) { std::array<uint64_t, 4> r; F.to_raw(x, r.data()); return r; };
+        auto less = [](const std::array<uint64_t, 4>& a, const std::array<uint64_t, 4>& c) { for (int i = 3; i >= 0; --i) { if (a[i] != c[i]) return a[i] < c[i]; } return false; };
+        std::vector<Key> a(usable);
+        for (uint32_t i = 0; i < usable; ++i) a[i] = Key{canon(cinp[i]), i};
+        std::stable_sort(a.begin(), a.end(), [&](const Key& x, const Key& y) { return less(x.v, y.v); });
+        std::map<std::array<uint64_t, 4>, std::pair<uint32_t, HFe>, decltype(less)> leftover(less);
+        for (uint32_t i = 0; i < usable; ++i) { auto key = canon(ctab[i]); auto it = leftover.find(key); if (it == leftover.end()) leftover.emplace(key, std::make_pair(1u, ctab[i])); else it->second.first++; }
+        HFe* ap = &up[((size_t)b * L + l) * 2 * n];
+        HFe* sp = ap + n;
+        std::vector<uint32_t> repeated;
+        for (uint32_t row = 0; row < usable; ++row) {
+          ap[row] = cinp[a[row].idx];
+          if (row == 0 || a[row].v != a[row - 1].v) {
+            sp[row] = ap[row];
+            auto it = leftover.find(a[row].v);
+            if (it == leftover.end() || it->second.first == 0) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure)");
+            it->second.first--;
+          } else repeated.push_back(row);
+        }
+        for (auto& kv : leftover)
+          for (uint32_t c = 0; c < kv.second.first; ++c) { BZ_CHECK(!repeated.empty(), "lookup permutation underflow"); sp[repeated.back()] = kv.second.second; repeated.pop_back(); }
+        BZ_CHECK(repeated.empty(), "lookup permutation leftover");
+      }
+    for (uint32_t b = 0; b < B; ++b)
+      for (uint32_t l = 0; l < L; ++l) {
+        BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 0)), &up[((size_t)b * L + l) * 2 * n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 1)), &up[((size_t)b * L + l) * 2 * n + n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
+      }
+    std::vector<CopyDesc> cd;
+    std::vector<CommitReq> reqs;
+    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(2 * L));
+    for (uint32_t l = 0; l < L; ++l) {
+      uint32_t r0 = pk.r_lk0 + l * (2 * (bf + 1) + 2);
+      cd.push_back(CopyDesc{PolyRef{R_VAL, pk.slot_lk(l, 0)}, usable, r0, bf + 1});
+      cd.push_back(CopyDesc{PolyRef{R_VAL, pk.slot_lk(l, 1)}, usable, r0 + bf + 1, bf + 1});
+      reqs.push_back({PolyRef{R_VAL, pk.slot_lk(l, 0)}, true});
+      reqs.push_back({PolyRef{R_VAL, pk.slot_lk(l, 1)}, true});
+      for (uint32_t b = 0; b < B; ++b) {
+        bl[b][2 * l] = rnd_host(ps[b], F, r0 + 2 * (bf + 1));
+        bl[b][2 * l + 1] = rnd_host(ps[b], F, r0 + 2 * (bf + 1) + 1);
+        ps[b].blinds[G + 3 * l + 0] = bl[b][2 * l]; ps[b].blinds[G + 3 * l + 1] = bl[b][2 * l + 1];
+      }
+    }
+    launch_copy(cd, n);
+    BZ_CUDA(cudaStreamSynchronize(st));      // `up` must outlive the async copies
+    commit(reqs, bl, pts);
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t j = 0; j < 2 * L; ++j) t_write_point(ps[b], pts[b][j]);
+  }
+  // ---- step 6
+  for (uint32_t b = 0; b < B; ++b) {
+    HFe beta = t_squeeze(ps[b], F), gamma = t_squeeze(ps[b], F);
+    ps[b].consts[pk.C_BETA] = beta; ps[b].consts[pk.C_GAMMA] = gamma;
+    HFe bd = beta, delta = F.delta();
+    for (uint32_t j = 0; j < pk.M; ++j) { ps[b].consts[pk.C_BD0 + j] = bd; bd = F.mul(bd, delta); }
+  }
+  upload_consts();
+  desc_off = 0;
+  // ---- steps 7-9: permutation products, lookup products, random polynomial: one commitment batch
+  {
+    DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n;
+    for (uint32_t s = 0; s < pk.nsets; ++s) {
+      PermSetDesc d{};
+      uint32_t c0 = s * pk.chunk_len, c1 = std::min<uint32_t>(pk.M, c0 + pk.chunk_len);
+      d.ncols = c1 - c0;
+      for (uint32_t j = c0; j < c1; ++j) {
+        auto col = cs.perm[j];
+        d.val_kind[j - c0] = col.first == 1 ? R_SHVAL : R_VAL;
+        d.val_slot[j - c0] = col.first == 0 ? col.second : (col.first == 1 ? col.second : pk.slot_inst(col.second));
+        d.sigma_slot[j - c0] = j;
+        d.bd_const[j - c0] = pk.C_BD0 + j;
+      }
+      {
+        ProfScope prof(C, PROF_SCAN);
+        perm_fraction_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, d, (const DFe*)pk.lval.p + (uint64_t)cs.F * n, (const DFe*)pk.omega_pows.p,
+                                                                          (const DFe*)w.consts.p, pk.cstride, pk.C_BETA, pk.C_GAMMA, num, den, n);
+        C->kernel_launches++;
+      }
+      grand_product(PolyRef{R_VAL, pk.slot_pz(s)}, s > 0, PolyRef{R_VAL, s > 0 ? pk.slot_pz(s - 1) : 0}, n - (bf + 1));
+      std::vector<CopyDesc> cd{CopyDesc{PolyRef{R_VAL, pk.slot_pz(s)}, n - bf, pk.r_perm0 + s * (bf + 1), bf}};
+      launch_copy(cd, n);
+    }
+    for (uint32_t l = 0; l < L; ++l) {
+      {
+        ProfScope prof(C, PROF_SCAN);
+        lookup_fraction_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_cin0 + 2 * l}, PolyRef{R_MISC, pk.m_cin0 + 2 * l + 1},
+                                                                            PolyRef{R_VAL, pk.slot_lk(l, 0)}, PolyRef{R_VAL, pk.slot_lk(l, 1)},
+                                                                            (const DFe*)w.consts.p, pk.cstride, pk.C_BETA, pk.C_GAMMA, num, den, n);
+        C->kernel_launches++;
+      }
+      grand_product(PolyRef{R_VAL, pk.slot_lk(l, 2)}, false, PolyRef{R_VAL, 0}, 0);
+      std::vector<CopyDesc> cd{CopyDesc{PolyRef{R_VAL, pk.slot_lk(l, 2)}, n - bf, pk.r_lkz0 + l * (bf + 1), bf}};
+      launch_copy(cd, n);
+    }
+    std::vector<CommitReq> reqs;
+    std::vector<std::vector<HFe>> bl(B);
+    for (uint32_t s = 0; s < pk.nsets; ++s) reqs.push_back({PolyRef{R_VAL, pk.slot_pz(s)}, true});
+    for (uint32_t l = 0; l < L; ++l) reqs.push_back({PolyRef{R_VAL, pk.slot_lk(l, 2)}, true});
+    for (uint32_t b = 0; b < B; ++b) {
+      for (uint32_t s = 0; s < pk.nsets; ++s) { HFe x = rnd_host(ps[b], F, pk.r_perm0 + s * (bf + 1) + bf); bl[b].push_back(x); ps[b].blinds[G + 3 * L + s] = x; }
+      for (uint32_t l = 0; l < L; ++l) { HFe x = rnd_host(ps[b], F, pk.r_lkz0 + l * (bf + 1) + bf); bl[b].push_back(x); ps[b].blinds[G + 3 * l + 2] = x; }
+    }
+    if (!reqs.empty()) {
+      commit(reqs, bl, pts);
+      for (uint32_t b = 0; b < B; ++b) for (size_t j = 0; j < reqs.size(); ++j) t_write_point(ps[b], pts[b][j]);
+    }
+    // random polynomial (coefficient basis g)
+    std::vector<CommitReq> rq{{PolyRef{R_RANDPOLY, 0}, false}};
+    std::vector<std::vector<HFe>> rb(B, std::vector<HFe>(1));
+    for (uint32_t b = 0; b < B; ++b) { rb[b][0] = rnd_host(ps[b], F, pk.r_rand_blind); ps[b].blinds[pk.nblinds - 1] = rb[b][0]; }
+    commit(rq, rb, pts);
+    for (uint32_t b = 0; b < B; ++b) t_write_point(ps[b], pts[b][0]);
+    // polys + cosets of lookup columns and z's
+    to_coeff(G + I, 3 * L + pk.nsets);
+    to_coset(G + I, 3 * L + pk.nsets);
+  }
+  // ---- step 10
+  for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_Y] = t_squeeze(ps[b], F);
+  upload_consts();
+  desc_off = 0;
+  // ---- steps 11-12: h(X)
+  {
+    EvalArgs<FpP> a{};
+    a.code = (const uint32_t*)pk.q_code.p; a.n_instr = pk.q_ninstr; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot.p;
+    a.pbase = (const DFe*)w.coset.p; a.pstride = (uint64_t)pk.NS * en; a.sbase = (const DFe*)pk.shcoset.p;
+    a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
+    a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
+    static bool attr = false;
+    if (!attr) { BZ_CUDA(cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024)); attr = true; }
+    {
+      ProfScope prof(C, PROF_QUOTIENT);
+      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr * 4, st>>>(a);
+      C->kernel_launches++;
+    }
+    NttFusion fu; fu.post_mode = 3;
+    ntt_run(C, 0, w.hext.p, w.hcoef.p, pk.ext_k, true, B, fu);
+    std::vector<CommitReq> reqs;
+    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(pk.qdeg));
+    for (uint32_t i = 0; i < pk.qdeg; ++i) reqs.push_back({PolyRef{R_HCOEF, i}, false});
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t i = 0; i < pk.qdeg; ++i) bl[b][i] = rnd_host(ps[b], F, pk.r_hblind + i);
+    commit(reqs, bl, pts);
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t i = 0; i < pk.qdeg; ++i) t_write_point(ps[b], pts[b][i]);
+    // ---- step 13: x
+    for (uint32_t b = 0; b < B; ++b) {
+      HFe x = t_squeeze(ps[b], F);
+      ps[b].consts[pk.C_X] = x;
+      HFe xn = x; for (uint32_t i = 0; i < k; ++i) xn = F.sqr(xn);
+      ps[b].consts[pk.C_XN] = xn;
+      for (int r : pk.rots) {
+        HFe pt = r >= 0 ? F.mul(x, F.pow_u64(pk.omega, (uint64_t)r)) : F.mul(x, F.pow_u64(pk.omega_inv, (uint64_t)(-r)));
+        ps[b].consts[pk.rot_const.at(r)] = pt;
+      }
+      // h blind: fold from the last piece
+      HFe hb = F.zero();
+      for (int i = (int)pk.qdeg - 1; i >= 0; --i) hb = F.add(F.mul(hb, xn), bl[b][i]);
+      ps[b].blinds[pk.nblinds - 2] = hb;
+    }
+    upload_consts();
+    // h_poly = sum pieces_i xn^i (Horner from the last piece)
+    std::vector<PolyRef> refs;
+    for (int i = (int)pk.qdeg - 1; i >= 0; --i) refs.push_back(PolyRef{R_HCOEF, (uint32_t)i});
+    std::vector<LinCombDesc> ld{LinCombDesc{PolyRef{R_MISC, pk.m_hpoly}, pk.C_XN, pk.qdeg, 0}};
+    lincomb(ld, refs);
+  }
+  // ---- steps 14-18: evaluations
+  {
+    std::vector<std::vector<HFe>> ev;
+    evaluate((const EvalQuery*)pk.d_evals.p, (uint32_t)pk.evals.size(), ev);
+    for (uint32_t b = 0; b < B; ++b) for (const HFe& e : ev[b]) t_write_scalar(ps[b], F, e);
+  }
+  // ---- step 20: multiopen
+  const uint32_t nps = (uint32_t)pk.point_sets.size();
+  std::vector<std::vector<HFe>> q_blinds(B, std::vector<HFe>(nps));
+  {
+    for (uint32_t b = 0; b < B; ++b) { ps[b].consts[pk.C_X1] = t_squeeze(ps[b], F); ps[b].consts[pk.C_X2] = t_squeeze(ps[b], F); }
+    upload_consts();
+    desc_off = 0;
+    std::vector<LinCombDesc> ld;
+    std::vector<PolyRef> refs;
+    for (uint32_t s = 0; s < nps; ++s) {
+      uint32_t first = (uint32_t)refs.size(), cnt = 0;
+      for (auto& ci : pk.cmap) if (ci.set == (int)s) { refs.push_back(ci.poly); ++cnt; }
+      ld.push_back(LinCombDesc{PolyRef{R_MISC, pk.m_qset0 + s}, pk.C_X1, cnt, first});
+    }
+    lincomb(ld, refs);
+    for (uint32_t b = 0; b < B; ++b) {
+      const HFe x1 = ps[b].consts[pk.C_X1];
+      for (uint32_t s = 0; s < nps; ++s) q_blinds[b][s] = F.zero();
+      for (auto& ci : pk.cmap) {
+        HFe bl = ci.blind_kind == 0 ? F.one() : ps[b].blinds[ci.blind_idx];
+        q_blinds[b][ci.set] = F.add(F.mul(q_blinds[b][ci.set], x1), bl);
+      }
+    }
+    // successive synthetic divisions; round r divides every set that has > r points
+    size_t maxpts = 0;
+    for (auto& s : pk.point_sets) maxpts = std::max(maxpts, s.size());
+    std::vector<PolyRef> cur(nps);
+    for (uint32_t s = 0; s < nps; ++s) cur[s] = PolyRef{R_MISC, pk.m_qset0 + s};
+    for (size_t r = 0; r < maxpts; ++r) {
+      std::vector<KateDesc> kd;
+      for (uint32_t s = 0; s < nps; ++s)
+        if (pk.point_sets[s].size() > r) {
+          PolyRef outp{R_MISC, pk.m_qtmp0 + 2 * s + (uint32_t)(r & 1)};
+          kd.push_back(KateDesc{cur[s], outp, pk.rot_const.at(pk.point_sets[s][r])});
+          cur[s] = outp;
+        }
+      KateDesc* dk = upload_desc(kd);
+      ProfScope prof(C, PROF_POLY);
+      kate_division_kernel<FpP><<<dim3((unsigned)kd.size(), B), KATE_THREADS, 0, st>>>(reg, n, dk, (const DFe*)w.consts.p, pk.cstride);
+      C->kernel_launches++;
+    }
+    std::vector<LinCombDesc> l2{LinCombDesc{PolyRef{R_MISC, pk.m_qprime}, pk.C_X2, nps, 0}};
+    lincomb(l2, cur);
+    std::vector<CommitReq> rq{{PolyRef{R_MISC, pk.m_qprime}, false}};
+    std::vector<std::vector<HFe>> qb(B, std::vector<HFe>(1));
+    for (uint32_t b = 0; b < B; ++b) qb[b][0] = rnd_host(ps[b], F, pk.r_qprime);
+    commit(rq, qb, pts);
+    for (uint32_t b = 0; b < B; ++b) t_write_point(ps[b], pts[b][0]);
+    for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_X3] = t_squeeze(ps[b], F);
+    upload_consts();
+    std::vector<EvalQuery> eq;
+    for (uint32_t s = 0; s < nps; ++s) eq.push_back(EvalQuery{PolyRef{R_MISC, pk.m_qset0 + s}, pk.C_X3});
+    EvalQuery* deq = upload_desc(eq);
+    std::vector<std::vector<HFe>> ev;
+    evaluate(deq, nps, ev);
+    for (uint32_t b = 0; b < B; ++b) for (const HFe& e : ev[b]) t_write_scalar(ps[b], F, e);
+    for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_X4] = t_squeeze(ps[b], F);
+    upload_consts();
+    std::vector<PolyRef> prefs{PolyRef{R_MISC, pk.m_qprime}};
+    for (uint32_t s = 0; s < nps; ++s) prefs.push_back(PolyRef{R_MISC, pk.m_qset0 + s});
+    std::vector<LinCombDesc> l3{LinCombDesc{PolyRef{R_MISC, pk.m_ppoly}, pk.C_X4, nps + 1, 0}};
+    lincomb(l3, prefs);
+    for (uint32_t b = 0; b < B; ++b) {
+      HFe pb = qb[b][0], x4 = ps[b].consts[pk.C_X4];
+      for (uint32_t s = 0; s < nps; ++s) pb = F.add(F.mul(pb, x4), q_blinds[b][s]);
+      q_blinds[b].push_back(pb);        // stash p_blind at index nps
+    }
+  }
+  // ---- step 21: inner product argument
+  {
+    desc_off = 0;
+    // S(X): random coefficients with S(x3) = 0
+    std::vector<EvalQuery> eq{EvalQuery{PolyRef{R_SPOLY, 0}, pk.C_X3}};
+    EvalQuery* deq = upload_desc(eq);
+    {
+      ProfScope prof(C, PROF_EVAL);
+      eval_queries_kernel<FpP><<<dim3(1, B), EVALQ_THREADS, 0, st>>>(reg, n, deq, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, 1);
+      tweak_element_kernel<FpP><<<(B + 63) / 64, 64, 0, st>>>(reg, n, PolyRef{R_SPOLY, 0}, 0, (const DFe*)w.evalout.p, 1, 0, 0, B);
+      C->kernel_launches += 2;
+    }
+    std::vector<CommitReq> rq{{PolyRef{R_SPOLY, 0}, false}};
+    std::vector<std::vector<HFe>> sb(B, std::vector<HFe>(1));
+    for (uint32_t b = 0; b < B; ++b) sb[b][0] = rnd_host(ps[b], F, pk.r_sblind);
+    commit(rq, sb, pts);
+    std::vector<HFe> fblind(B);
+    for (uint32_t b = 0; b < B; ++b) {
+      t_write_point(ps[b], pts[b][0]);
+      HFe xi = t_squeeze(ps[b], F), z = t_squeeze(ps[b], F);
+      ps[b].consts[pk.C_XI] = xi; ps[b].consts[pk.C_Z] = z;
+      fblind[b] = F.add(F.mul(sb[b][0], xi), q_blinds[b][nps]);
+    }
+    upload_consts();
+    // p' = S * xi + P ; p'[0] -= p'(x3) ; b = powers of x3 ; coef = 1
+    std::vector<PolyRef> refs{PolyRef{R_SPOLY, 0}, PolyRef{R_MISC, pk.m_ppoly}};
+    std::vector<LinCombDesc> ld{LinCombDesc{PolyRef{R_MISC, pk.m_pprime}, pk.C_XI, 2, 0}};
+    lincomb(ld, refs);
+    std::vector<EvalQuery> eq2{EvalQuery{PolyRef{R_MISC, pk.m_pprime}, pk.C_X3}};
+    EvalQuery* deq2 = upload_desc(eq2);
+    {
+      ProfScope prof(C, PROF_IPA);
+      eval_queries_kernel<FpP><<<dim3(1, B), EVALQ_THREADS, 0, st>>>(reg, n, deq2, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, 1);
+      tweak_element_kernel<FpP><<<(B + 63) / 64, 64, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_pprime}, 0, (const DFe*)w.evalout.p, 1, 0, 0, B);
+      powers_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_b}, (const DFe*)w.consts.p, pk.cstride, pk.C_X3);
+      fill_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_coef}, n, dfe(F.one()));
+      C->kernel_launches += 4;
+    }
+    // rounds
+    const FixedBase& fb = pk.params->fb_g;
+    std::vector<void*> mainp((size_t)B * 2), extrap((size_t)B * 2);
+    for (uint32_t b = 0; b < B; ++b) {
+      mainp[2 * b] = misc(b, pk.m_scl); mainp[2 * b + 1] = misc(b, pk.m_scr);
+      extrap[2 * b] = (DFe*)w.extras.p + (size_t)b * 4; extrap[2 * b + 1] = (DFe*)w.extras.p + (size_t)b * 4 + 2;
+    }
+    BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), mainp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + (size_t)B * 2, extrap.data(), extrap.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    const uint32_t n_msm = 2 * B;
+    const uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / n_msm)));
+    pts.assign(B, std::vector<HostPoint>(2));
+    for (uint32_t j = 0; j < k; ++j) {
+      const uint32_t half = 1u << (k - j - 1);
+      {
+        ProfScope prof(C, PROF_IPA);
+        ipa_scalars_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_coef},
+                                                                        PolyRef{R_MISC, pk.m_scl}, PolyRef{R_MISC, pk.m_scr});
+        ipa_inner_kernel<FpP><<<B, IPA_THREADS, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, (const DFe*)w.consts.p, pk.cstride,
+                                                        pk.C_Z, (const DFe*)w.rnd.p, pk.R, pk.r_ipa + 2 * j, pk.r_ipa + 2 * j + 1, (DFe*)w.extras.p);
+        C->kernel_launches += 2;
+      }
+      fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + (size_t)B * 2), n_msm, chunks, w.commits.p);
+      read_points(n_msm, 2, pts);
+      for (uint32_t b = 0; b < B; ++b) {
+        t_write_point(ps[b], pts[b][0]);
+        t_write_point(ps[b], pts[b][1]);
+        HFe u = t_squeeze(ps[b], F), uinv = F.inv(u);
+        ps[b].consts[pk.C_U] = u; ps[b].consts[pk.C_UINV] = uinv;
+        HFe lr = rnd_host(ps[b], F, pk.r_ipa + 2 * j), rr = rnd_host(ps[b], F, pk.r_ipa + 2 * j + 1);
+        fblind[b] = F.add(fblind[b], F.add(F.mul(lr, uinv), F.mul(rr, u)));
+      }
+      upload_consts();
+      ProfScope prof(C, PROF_IPA);
+      ipa_fold_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, PolyRef{R_MISC, pk.m_coef},
+                                                                   (const DFe*)w.consts.p, pk.cstride, pk.C_U, pk.C_UINV);
+      C->kernel_launches++;
+    }
+    // c = p'[0], f
+    for (uint32_t b = 0; b < B; ++b) BZ_CUDA(cudaMemcpyAsync((char*)w.h_pinned + (size_t)b * 32, misc(b, pk.m_pprime), 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    for (uint32_t b = 0; b < B; ++b) {
+      HFe c; memcpy(c.l, (char*)w.h_pinned + (size_t)b * 32, 32);
+      t_write_scalar(ps[b], F, c);
+      t_write_scalar(ps[b], F, fblind[b]);
+      BZ_CHECK(ps[b].pos == pk.proof_size, "internal: proof size mismatch");
+    }
+  }
+  BZ_CUDA(cudaGetLastError());
+}
+
+}  // namespace bz
+
+extern "C" API int bz_create_proofs(bz_ctx* ctx, bz_pk* pkh, uint32_t batch, const void* instances, const uint32_t* instance_lens,
+                                    uint32_t instance_stride, const void* advice, const void* rand_wide, void* proofs) {
+  PV_TRY(ctx, {
+    BZ_CHECK(pkh && advice && rand_wide && proofs && batch >= 1, "null argument");
+    PkImpl& pk = pkh->p;
+    BZ_CHECK(pk.cs.I == 0 || (instances && instance_lens), "instances missing");
+    ensure_work(C, pk, batch);
+    Prover pr(C, pk, batch);
+    pr.run(instances, instance_lens, instance_stride, advice, rand_wide, (uint8_t*)proofs);
+  });
+}

@@ -1,0 +1,228 @@
+"""Host glue for the prover C ABI (include/bzhalo2.h): what the Rust shim does with `Params`, `ProvingKey` and
+`create_proof` (reference call sites /root/reference/benches/shot.rs:58-71), expressed over ctypes.
+
+Params / ProvingKey hold opaque device handles; create_proof returns exactly the bytes `transcript.finalize()`
+yields in halo2_proofs 0.2.0."""
+import ctypes
+import numpy as np
+from ..binding import _np_ptr, BzError
+
+FP = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+_FP_ROOT = 0x2bce74deac30ebda362120830561f81aea322bf2b7bb7584bdad6fabd87ea32f
+_FP_DELTA = 0x0a757d0f0006ab6cbd455b7112a5049df5e4f3f13eee56366a6ccd20dd7b9ba2
+
+
+def mont(values, p=FP):
+    """canonical ints -> (n,4) uint64 Montgomery limbs (pasta in-memory form)."""
+    buf = b"".join(((int(v) << 256) % p).to_bytes(32, "little") for v in values)
+    return np.frombuffer(buf, dtype=np.uint64).reshape(-1, 4).copy()
+
+
+class bz_token(ctypes.Structure):
+    _fields_ = [("op", ctypes.c_uint32), ("a", ctypes.c_uint32), ("b", ctypes.c_int32)]
+
+
+class bz_circuit(ctypes.Structure):
+    _fields_ = [
+        ("k", ctypes.c_uint32), ("num_advice", ctypes.c_uint32), ("num_fixed", ctypes.c_uint32),
+        ("num_instance", ctypes.c_uint32), ("degree", ctypes.c_uint32), ("blinding_factors", ctypes.c_uint32),
+        ("n_advice_queries", ctypes.c_uint32), ("advice_queries", ctypes.c_void_p),
+        ("n_fixed_queries", ctypes.c_uint32), ("fixed_queries", ctypes.c_void_p),
+        ("n_instance_queries", ctypes.c_uint32), ("instance_queries", ctypes.c_void_p),
+        ("n_perm_columns", ctypes.c_uint32), ("perm_columns", ctypes.c_void_p),
+        ("n_constants", ctypes.c_uint32), ("constants", ctypes.c_void_p),
+        ("n_tokens", ctypes.c_uint32), ("tokens", ctypes.c_void_p),
+        ("n_gate_polys", ctypes.c_uint32), ("gate_poly_offsets", ctypes.c_void_p),
+        ("n_lookups", ctypes.c_uint32), ("lookup_input_counts", ctypes.c_void_p), ("lookup_table_counts", ctypes.c_void_p),
+        ("lookup_expr_offsets", ctypes.c_void_p),
+        ("vk_transcript_repr", ctypes.c_uint8 * 32),
+    ]
+
+
+_KIND = {"advice": 0, "fixed": 1, "instance": 2}
+
+
+def _bind(lib):
+    vp, u32, i32 = ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int
+    if getattr(lib, "_prover_bound", False):
+        return
+    lib.bz_params_create.restype = i32
+    lib.bz_params_create.argtypes = [vp, u32, i32, vp, vp, vp, vp, i32, ctypes.POINTER(vp)]
+    lib.bz_params_destroy.restype = None
+    lib.bz_params_destroy.argtypes = [vp]
+    lib.bz_params_commit.restype = i32
+    lib.bz_params_commit.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.bz_pk_create.restype = i32
+    lib.bz_pk_create.argtypes = [vp, vp, ctypes.POINTER(bz_circuit), vp, vp, ctypes.POINTER(vp)]
+    lib.bz_pk_destroy.restype = None
+    lib.bz_pk_destroy.argtypes = [vp]
+    lib.bz_pk_num_random.restype = u32
+    lib.bz_pk_num_random.argtypes = [vp]
+    lib.bz_pk_proof_size.restype = u32
+    lib.bz_pk_proof_size.argtypes = [vp]
+    lib.bz_create_proofs.restype = i32
+    lib.bz_create_proofs.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp, vp]
+    lib._prover_bound = True
+
+
+class Params:
+    """`Params<vesta::Affine>` image on the device.  g, g_lagrange: (n,8) uint64 Montgomery affine; w, u: (8,)."""
+
+    def __init__(self, ctx, k, g, g_lagrange, w, u, curve=0, window_bits=0):
+        _bind(ctx.lib)
+        self.ctx, self.k, self.n = ctx, k, 1 << k
+        g = np.ascontiguousarray(g, dtype=np.uint64); gl = np.ascontiguousarray(g_lagrange, dtype=np.uint64)
+        w = np.ascontiguousarray(w, dtype=np.uint64); u = np.ascontiguousarray(u, dtype=np.uint64)
+        assert g.shape == (self.n, 8) and gl.shape == (self.n, 8)
+        h = ctypes.c_void_p()
+        ctx._check(ctx.lib.bz_params_create(ctx.h, k, curve, _np_ptr(g), _np_ptr(gl), _np_ptr(w), _np_ptr(u), window_bits, ctypes.byref(h)))
+        self.h = h
+
+    def commit(self, poly, blind, lagrange=False):
+        """Params::commit / commit_lagrange followed by to_affine(): returns (8,) uint64 affine."""
+        poly = np.ascontiguousarray(poly, dtype=np.uint64).reshape(self.n, 4)
+        blind = np.ascontiguousarray(blind, dtype=np.uint64).reshape(4)
+        out = np.zeros(8, dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.bz_params_commit(self.ctx.h, self.h, 1 if lagrange else 0, _np_ptr(poly), _np_ptr(blind), _np_ptr(out)))
+        return out
+
+    def commit_lagrange(self, poly, blind):
+        return self.commit(poly, blind, lagrange=True)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.bz_params_destroy(self.h)
+            self.h = None
+
+
+def flatten_circuit(ir, k, vk_repr):
+    """ConstraintSystem IR (plonk/circuit.py `to_ir`) -> bz_circuit + the numpy arrays that back its pointers."""
+    p = ir["modulus"]
+    consts, const_index = [], {}
+
+    def cidx(v):
+        v %= p
+        if v not in const_index:
+            const_index[v] = len(consts)
+            consts.append(v)
+        return const_index[v]
+
+    tokens = []
+
+    def emit(e):
+        kind = e[0]
+        if kind == "const":
+            tokens.append((0, cidx(e[1]), 0))
+        elif kind in ("advice", "fixed", "instance"):
+            tokens.append(({"advice": 1, "fixed": 2, "instance": 3}[kind], e[1], e[2]))
+        elif kind == "neg":
+            emit(e[1]); tokens.append((4, 0, 0))
+        elif kind == "sum":
+            emit(e[1]); emit(e[2]); tokens.append((5, 0, 0))
+        elif kind == "product":
+            emit(e[1]); emit(e[2]); tokens.append((6, 0, 0))
+        elif kind == "scaled":
+            emit(e[1]); tokens.append((7, cidx(e[2]), 0))
+        else:
+            raise ValueError(kind)
+
+    gate_off = [0]
+    for gate in ir["gates"]:
+        for poly in gate["polys"]:
+            emit(poly)
+            gate_off.append(len(tokens))
+    lk_off, lk_in, lk_tab = [len(tokens)], [], []
+    for lk in ir["lookups"]:
+        lk_in.append(len(lk["input"])); lk_tab.append(len(lk["table"]))
+        for e in lk["input"] + lk["table"]:
+            emit(e)
+            lk_off.append(len(tokens))
+    keep = {}
+    keep["aq"] = np.array(ir["advice_queries"], dtype=np.int32).reshape(-1, 2)
+    keep["fq"] = np.array(ir["fixed_queries"], dtype=np.int32).reshape(-1, 2)
+    keep["iq"] = np.array(ir["instance_queries"], dtype=np.int32).reshape(-1, 2)
+    keep["perm"] = np.array([[_KIND[c[0]], c[1]] for c in ir["permutation"]], dtype=np.uint32).reshape(-1, 2)
+    keep["consts"] = mont(consts, p) if consts else np.zeros((1, 4), np.uint64)
+    tk = (bz_token * max(1, len(tokens)))()
+    for i, (op, a, b) in enumerate(tokens):
+        tk[i].op, tk[i].a, tk[i].b = op, a, b
+    keep["tokens"] = tk
+    keep["gate_off"] = np.array(gate_off, dtype=np.uint32)
+    keep["lk_in"] = np.array(lk_in or [0], dtype=np.uint32)
+    keep["lk_tab"] = np.array(lk_tab or [0], dtype=np.uint32)
+    keep["lk_off"] = np.array(lk_off, dtype=np.uint32)
+    c = bz_circuit()
+    c.k, c.num_advice, c.num_fixed, c.num_instance = k, ir["num_advice"], ir["num_fixed"], ir["num_instance"]
+    c.degree, c.blinding_factors = ir["degree"], ir["blinding_factors"]
+    c.n_advice_queries, c.advice_queries = len(keep["aq"]), keep["aq"].ctypes.data
+    c.n_fixed_queries, c.fixed_queries = len(keep["fq"]), keep["fq"].ctypes.data
+    c.n_instance_queries, c.instance_queries = len(keep["iq"]), keep["iq"].ctypes.data
+    c.n_perm_columns, c.perm_columns = len(keep["perm"]), keep["perm"].ctypes.data
+    c.n_constants, c.constants = len(consts), keep["consts"].ctypes.data
+    c.n_tokens, c.tokens = len(tokens), ctypes.addressof(tk)
+    c.n_gate_polys, c.gate_poly_offsets = len(gate_off) - 1, keep["gate_off"].ctypes.data
+    c.n_lookups = len(ir["lookups"])
+    c.lookup_input_counts, c.lookup_table_counts = keep["lk_in"].ctypes.data, keep["lk_tab"].ctypes.data
+    c.lookup_expr_offsets = keep["lk_off"].ctypes.data
+    c.vk_transcript_repr[:] = list((vk_repr % p).to_bytes(32, "little"))
+    return c, keep
+
+
+def sigma_values(ir, k, mapping, p=FP):
+    """pk.permutation.permutations: sigma_col[row] = delta^col' * omega^row' (U: permutation/keygen.rs build_pk)."""
+    n = 1 << k
+    omega = pow(_FP_ROOT, 1 << (32 - k), p)
+    om = [1] * n
+    for i in range(1, n):
+        om[i] = om[i - 1] * omega % p
+    m = len(ir["permutation"])
+    dl = [pow(_FP_DELTA, i, p) for i in range(m)]
+    return [[dl[c] * om[r] % p for (c, r) in mapping[i]] for i in range(m)]
+
+
+class ProvingKey:
+    """keygen_pk's device image for one circuit."""
+
+    def __init__(self, ctx, params, ir, fixed_values, mapping, vk_repr):
+        _bind(ctx.lib)
+        self.ctx, self.params, self.ir = ctx, params, ir
+        self.k, self.n = params.k, params.n
+        circ, keep = flatten_circuit(ir, params.k, vk_repr)
+        fixed = mont([v for col in fixed_values for v in col]) if fixed_values else np.zeros((1, 4), np.uint64)
+        sig = sigma_values(ir, params.k, mapping)
+        sigma = mont([v for col in sig for v in col]) if sig else np.zeros((1, 4), np.uint64)
+        h = ctypes.c_void_p()
+        ctx._check(ctx.lib.bz_pk_create(ctx.h, params.h, ctypes.byref(circ), _np_ptr(fixed), _np_ptr(sigma), ctypes.byref(h)))
+        self.h = h
+        self.num_random = ctx.lib.bz_pk_num_random(h)
+        self.proof_size = ctx.lib.bz_pk_proof_size(h)
+
+    def close(self):
+        if self.h:
+            self.ctx.lib.bz_pk_destroy(self.h)
+            self.h = None
+
+
+def create_proofs(pk, instances, advice, rand_wide):
+    """create_proof for a batch.  instances: (B, num_instance, stride, 4) uint64 + implied lens, or list of lists of
+    int lists; advice: (B, num_advice, n, 4) uint64 Montgomery; rand_wide: (B, num_random, 8) uint64.
+    Returns list of B proof byte strings."""
+    ctx = pk.ctx
+    advice = np.ascontiguousarray(advice, dtype=np.uint64)
+    B = advice.shape[0]
+    assert advice.shape == (B, pk.ir["num_advice"], pk.n, 4)
+    rand_wide = np.ascontiguousarray(rand_wide, dtype=np.uint64)
+    assert rand_wide.shape == (B, pk.num_random, 8), (rand_wide.shape, pk.num_random)
+    ni = pk.ir["num_instance"]
+    lens = np.array([len(instances[0][i]) for i in range(ni)] or [0], dtype=np.uint32)
+    stride = max(1, int(lens.max()))
+    inst = np.zeros((B, max(1, ni), stride, 4), dtype=np.uint64)
+    for b in range(B):
+        assert len(instances[b]) == ni, "Error::InvalidInstances"
+        for i in range(ni):
+            assert len(instances[b][i]) == lens[i]
+            if lens[i]:
+                inst[b, i, :lens[i]] = mont(instances[b][i])
+    out = np.zeros((B, pk.proof_size), dtype=np.uint8)
+    ctx._check(ctx.lib.bz_create_proofs(ctx.h, pk.h, B, _np_ptr(inst), _np_ptr(lens), stride, _np_ptr(advice), _np_ptr(rand_wide), _np_ptr(out)))
+    return [bytes(out[b]) for b in range(B)]

@@ -103,6 +103,66 @@ int bz_lagrange_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t k);
 int bz_coeff_to_extended(bz_ctx* ctx, int field, const void* coeffs, void* out_extended, uint32_t k, uint32_t extended_k);
 int bz_extended_to_coeff(bz_ctx* ctx, int field, void* a, uint32_t extended_k);
 
+/* ==================================================================================================
+ * The prover: Params / ProvingKey images on the device and `create_proof`
+ * (U: halo2_proofs 0.2.0 src/poly/commitment.rs `Params`, src/plonk.rs `ProvingKey`, src/plonk/prover.rs
+ *  `create_proof`; reference call sites /root/reference/benches/shot.rs:58-71).
+ * ================================================================================================== */
+typedef struct bz_params bz_params;
+typedef struct bz_pk bz_pk;
+
+/* Params<C>: g, g_lagrange (n affine points each), w, u -- exactly the fields of halo2's `Params` (host memory).
+ * Builds the device image incl. the fixed-base window tables used by every commitment.
+ * window_bits: signed-digit window of the tables (0 = default). */
+int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, const void* g_lagrange, const void* w,
+                     const void* u, int window_bits, bz_params** out);
+void bz_params_destroy(bz_params* params);
+/* Params::commit (lagrange_basis = 0) / Params::commit_lagrange (1): poly = n scalars (host), blind = 1 scalar;
+ * result already normalised: 64 B affine (what `.to_affine()` / batch_normalize yields). */
+int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* poly, const void* blind,
+                     void* out_affine);
+
+/* The constraint system `pk.vk.cs` flattened.  Expressions are postfix token streams. */
+typedef struct {
+  uint32_t op; /* 0 Constant(a = constant index) 1 Advice(a = column, b = rotation) 2 Fixed 3 Instance 4 Negated 5 Sum
+                  6 Product 7 Scaled(a = constant index) */
+  uint32_t a;
+  int32_t b;
+} bz_token;
+
+typedef struct {
+  uint32_t k, num_advice, num_fixed, num_instance, degree, blinding_factors;
+  uint32_t n_advice_queries;   const int32_t* advice_queries;   /* (column, rotation) pairs in registration order */
+  uint32_t n_fixed_queries;    const int32_t* fixed_queries;
+  uint32_t n_instance_queries; const int32_t* instance_queries;
+  uint32_t n_perm_columns;     const uint32_t* perm_columns;    /* (kind, index) pairs; kind 0 advice 1 fixed 2 instance */
+  uint32_t n_constants;        const void* constants;           /* 32 B Montgomery each */
+  uint32_t n_tokens;           const bz_token* tokens;
+  uint32_t n_gate_polys;       const uint32_t* gate_poly_offsets;  /* n_gate_polys + 1 offsets into tokens, gate order */
+  uint32_t n_lookups;          const uint32_t* lookup_input_counts; const uint32_t* lookup_table_counts;
+  const uint32_t* lookup_expr_offsets; /* offsets (total + 1) into tokens; per lookup: its inputs, then its tables */
+  uint8_t vk_transcript_repr[32];      /* canonical LE scalar that vk.hash_into absorbs (opaque) */
+} bz_circuit;
+
+/* keygen_pk's device image: fixed_values = num_fixed x n scalars (Lagrange), sigma_values = n_perm_columns x n scalars
+ * (pk.permutation.permutations), both host memory.  Polys, extended cosets, l0 / l_blind / l_last and the compiled
+ * quotient program are derived on the device. */
+int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cs, const void* fixed_values,
+                 const void* sigma_values, bz_pk** out);
+void bz_pk_destroy(bz_pk* pk);
+uint32_t bz_pk_num_random(const bz_pk* pk); /* Scalar::random draws one create_proof makes (protocol order) */
+uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yields */
+
+/* create_proof for `batch` independent proofs of the same circuit, in lockstep on the device.
+ *   instances : batch x num_instance x instance_stride scalars; instance_lens[num_instance] values are used
+ *   advice    : batch x num_advice x n scalars (rows >= n - (blinding_factors + 1) are ignored: blinded)
+ *   rand_wide : batch x bz_pk_num_random x 64 B -- the raw outputs `Scalar::random(&mut rng)` would consume, in
+ *               the exact order create_proof draws them (the shim pre-draws: the count is shape-only)
+ *   proofs    : batch x bz_pk_proof_size bytes, identical to what Blake2bWrite::finalize() returns
+ * Errors: BZ_ERR_SYNTHESIS when a lookup input is missing from its table (Error::ConstraintSystemFailure). */
+int bz_create_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instances, const uint32_t* instance_lens,
+                     uint32_t instance_stride, const void* advice, const void* rand_wide, void* proofs);
+
 #ifdef __cplusplus
 }
 #endif

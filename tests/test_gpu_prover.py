@@ -1,0 +1,83 @@
+"""GPU parity for create_proof through the C ABI: proof bytes identical to the oracle's under the same RNG words, and
+every GPU proof accepted by the restated reference verifier (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+from tests.util_prover import Job, tiny_circuit, first_diff
+
+pytestmark = pytest.mark.gpu
+
+
+def _prove(job, pk, indices):
+    from battlezips_halo2_b200.plonk import prover as PR
+    B = len(indices)
+    advice = np.stack([job.advice] * B)
+    wide = np.stack([job.wide(i) for i in indices])
+    return PR.create_proofs(pk, [job.instances] * B, advice, wide)
+
+
+def test_params_commit_parity(ctx, oracle_c):
+    co = oracle_c
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx)
+    rng = np.random.default_rng(0)
+    poly = co.from_u512(0, rng.integers(0, 2**63, size=(32, 8), dtype=np.uint64))
+    blind = co.from_u512(0, rng.integers(0, 2**63, size=(1, 8), dtype=np.uint64))[0]
+    V = job.V
+    for lag in (False, True):
+        got = params.commit(poly, blind, lagrange=lag)
+        exp = (job.oparams.commit_lagrange if lag else job.oparams.commit)(poly, V.int1(blind))
+        assert np.array_equal(got, co.to_affine(0, exp)[0])
+    pk.close(); params.close()
+
+
+@pytest.mark.parametrize("window_bits", [4, 9])
+def test_tiny_proof_bytes_match_oracle(ctx, window_bits):
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=window_bits)
+    proofs = _prove(job, pk, [0, 1, 2])
+    for i, proof in enumerate(proofs):
+        exp = job.oracle_proof(index=i)
+        assert first_diff(proof, exp) is None, first_diff(proof, exp)
+        assert job.verify(proof)
+    pk.close(); params.close()
+
+
+def test_lookup_failure_maps_to_synthesis_error(ctx):
+    import battlezips_halo2_b200 as bz
+    from battlezips_halo2_b200.plonk import prover as PR
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=4)
+    adv = job.advice.copy()
+    adv[0, 0] = job.V.m(1000)
+    with pytest.raises(bz.BzError) as e:
+        PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])
+    assert e.value.code == -4
+    pk.close(); params.close()
+
+
+def test_shot_proof_bytes_match_oracle(ctx):
+    """BASELINE config 1/3 shape: Shot k=11, batch of 2 proofs with different RNG streams."""
+    from battlezips_halo2_b200.circuits import shot_circuit
+    cs, cfg, asg = shot_circuit(0)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    assert pk.proof_size == 4672 and pk.num_random == 4238
+    proofs = _prove(job, pk, [0, 7])
+    for idx, proof in zip([0, 7], proofs):
+        exp = job.oracle_proof(index=idx)
+        assert first_diff(proof, exp) is None, first_diff(proof, exp)
+        assert job.verify(proof)
+    pk.close(); params.close()
+
+
+def test_board_proof_bytes_match_oracle(ctx):
+    """BASELINE config 2: Board k=12 single proof, bit-exact bytes, accepted by the restated verifier."""
+    from battlezips_halo2_b200.circuits import board_circuit
+    cs, cfg, asg = board_circuit(0)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    proof = _prove(job, pk, [0])[0]
+    exp = job.oracle_proof(index=0)
+    assert first_diff(proof, exp) is None, first_diff(proof, exp)
+    assert job.verify(proof)
+    pk.close(); params.close()
