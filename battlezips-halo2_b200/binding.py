@@ -61,6 +61,8 @@ def load_library():
         "bz_version": (ctypes.c_char_p, []),
         "bz_profile_enable": (i32, [vp, i32]),
         "bz_profile_read": (i32, [vp, i32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(u64)]),
+        "bz_profile_counter": (i32, [vp, i32, ctypes.POINTER(u64), i32]),
+        "bz_imad_peak": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
         "bz_dev_alloc": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
         "bz_dev_free": (i32, [vp, vp]),
         "bz_h2d": (i32, [vp, vp, vp, ctypes.c_size_t]),
@@ -167,6 +169,16 @@ class Context:
             if cnt.value:
                 out[name] = (ms.value, cnt.value)
         return out
+
+    def profile_counter(self, which=0, reset=True):
+        v = ctypes.c_uint64()
+        self._check(self.lib.bz_profile_counter(self.h, which, ctypes.byref(v), 1 if reset else 0))
+        return v.value
+
+    def imad_peak(self):
+        v = ctypes.c_double()
+        self._check(self.lib.bz_imad_peak(self.h, ctypes.byref(v)))
+        return v.value
 
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)

@@ -113,6 +113,57 @@ __attribute__((visibility("default"))) int bz_profile_read(bz_ctx* ctx, int tag,
   });
 }
 
+__attribute__((visibility("default"))) int bz_profile_counter(bz_ctx* ctx, int which, uint64_t* value, int reset) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(which >= 0 && which < 8 && value, "bad counter");
+    *value = 0;
+    if (ctx->c.counters.p) {
+      BZ_CUDA(cudaMemcpyAsync(value, (uint64_t*)ctx->c.counters.p + which, 8, cudaMemcpyDeviceToHost, ctx->c.stream));
+      BZ_CUDA(cudaStreamSynchronize(ctx->c.stream));
+      if (reset) BZ_CUDA(cudaMemsetAsync((uint64_t*)ctx->c.counters.p + which, 0, 8, ctx->c.stream));
+    }
+  });
+}
+
+// Integer-pipe peak: independent 32-bit multiply-add chains on every SM; returns IMAD/s (the denominator for
+// the MSM / quotient integer roofline; SURVEY §8d "must be measured").
+__global__ void imad_peak_kernel(uint32_t* out, uint32_t iters) {
+  uint32_t a0 = threadIdx.x + 1, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+  const uint32_t m = blockIdx.x * 2 + 1, c = 0x9e3779b9u;
+  for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a0 = a0 * m + c; a1 = a1 * m + c; a2 = a2 * m + c; a3 = a3 * m + c;
+      a4 = a4 * m + c; a5 = a5 * m + c; a6 = a6 * m + c; a7 = a7 * m + c;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+__attribute__((visibility("default"))) int bz_imad_peak(bz_ctx* ctx, double* imad_per_sec) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(imad_per_sec, "null out");
+    const int blocks = ctx->c.sm_count * 8, threads = 256;
+    const uint32_t iters = 4096;
+    bz::DevBuf out; out.alloc((size_t)blocks * threads * 4);
+    cudaStream_t st = ctx->c.stream;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    imad_peak_kernel<<<blocks, threads, 0, st>>>(out.as<uint32_t>(), 64);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0, st);
+      imad_peak_kernel<<<blocks, threads, 0, st>>>(out.as<uint32_t>(), iters);
+      cudaEventRecord(e1, st);
+      BZ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      double ops = (double)blocks * threads * iters * 64.0;
+      best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->c.kernel_launches += 4;
+    *imad_per_sec = best;
+  });
+}
+
 // ---- element-wise field / point ops on host slices ------------------------------------------------
 __attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
   BZ_TRY(ctx, {

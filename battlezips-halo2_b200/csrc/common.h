@@ -76,6 +76,7 @@ struct Ctx {
   DevBuf scratch[4];       // general reusable scratch (msm, staging)
   uint64_t kernel_launches = 0;   // counted by every launch site (bench.py's gpu_launches)
   bool profiling = false;
+  DevBuf counters;        // [0] = mixed additions done by fixed_msm_kernel while profiling
   std::vector<ProfRec> prof;
   double prof_ms[PROF_NTAGS] = {0};
   uint64_t prof_count[PROF_NTAGS] = {0};

@@ -109,8 +109,9 @@ constexpr int FB_THREADS = 128;
 template <class BP, class SP>
 __global__ void __launch_bounds__(FB_THREADS) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
                                  const Fe<SP>* const* __restrict__ main, uint32_t n_main, const Fe<SP>* const* __restrict__ extra,
-                                 Xyzz<BP>* __restrict__ partial) {
+                                 Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
   __shared__ Xyzz<BP> sh[FB_THREADS];
+  uint32_t my_adds = 0;
   const uint32_t m = blockIdx.y, chunks = gridDim.x;
   const Fe<SP>* sm = main[m];
   const Fe<SP>* se = extra ? extra[m] : nullptr;
@@ -139,8 +140,13 @@ __global__ void __launch_bounds__(FB_THREADS) fixed_msm_kernel(const Affine<BP>*
       if (d) {
         Affine<BP> pt = aff_load(table + ((size_t)w * nbk + (d - 1)) * npts + i);
         xyzz_add_mixed_signed(acc, pt, neg);
+        ++my_adds;
       }
     }
+  }
+  if (add_counter) {       // profiling only: exact number of mixed additions this launch performed
+    uint32_t tot = __reduce_add_sync(0xffffffffu, my_adds);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(add_counter, (unsigned long long)tot);
   }
   sh[threadIdx.x] = acc;
   __syncthreads();
@@ -173,13 +179,14 @@ template <class BP, class SP>
 static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_main, uint32_t n_main, const void* const* d_extra,
                             uint32_t n_msm, uint32_t chunks, void* d_out_affine) {
   cudaStream_t st = ctx->stream;
+  if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
   ctx->scratch[3].ensure((size_t)n_msm * chunks * sizeof(Xyzz<BP>));
   Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
   {
     ProfScope p(ctx, PROF_FIXED_MSM);
     fixed_msm_kernel<BP, SP><<<dim3(chunks, n_msm), FB_THREADS, 0, st>>>(
         fb.table.as<Affine<BP>>(), fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main,
-        (const Fe<SP>* const*)d_extra, partial);
+        (const Fe<SP>* const*)d_extra, partial, ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr);
   }
   fixed_msm_finish_kernel<BP><<<(n_msm + 31) / 32, 32, 0, st>>>(partial, chunks, n_msm, (Affine<BP>*)d_out_affine);
   ctx->kernel_launches += 2;

@@ -778,8 +778,20 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     ps[b].consts[pk.C_ONE] = F.one();
     t_common_scalar(ps[b], F, cs.vk_repr);                                     // step 0
   }
-  // ---- upload: randomness (reduced on device), advice, instances
-  BZ_CUDA(cudaMemcpyAsync(w.wide.p, rand_wide, (size_t)B * pk.R * 64, cudaMemcpyHostToDevice, st));
+  // ---- upload: randomness (reduced on device), advice, instances.  Inputs may live in host or device memory
+  // (cudaMemcpyDefault); blinds are re-derived on the host from the same RNG words, so a device-resident stream
+  // is mirrored to the host once.
+  std::vector<uint8_t> wide_host;
+  {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, rand_wide) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
+      wide_host.resize((size_t)B * pk.R * 64);
+      BZ_CUDA(cudaMemcpyAsync(wide_host.data(), rand_wide, wide_host.size(), cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(cudaStreamSynchronize(st));
+      for (uint32_t b = 0; b < B; ++b) ps[b].wide = wide_host.data() + (size_t)b * pk.R * 64;
+    } else cudaGetLastError();
+  }
+  BZ_CUDA(cudaMemcpyAsync(w.wide.p, rand_wide, (size_t)B * pk.R * 64, cudaMemcpyDefault, st));
   {
     uint64_t tot = (uint64_t)B * pk.R;
     from_u512_kernel<FpP><<<(unsigned)((tot + 127) / 128), 128, 0, st>>>((const uint32_t*)w.wide.p, (DFe*)w.rnd.p, tot);
@@ -787,11 +799,11 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   }
   BZ_CUDA(cudaMemsetAsync(w.val.p, 0, (size_t)B * pk.NS * n * 32, st));
   for (uint32_t b = 0; b < B; ++b) {
-    BZ_CUDA(cudaMemcpyAsync(val(b, 0), (const char*)advice + (size_t)b * G * n * 32, (size_t)G * n * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(val(b, 0), (const char*)advice + (size_t)b * G * n * 32, (size_t)G * n * 32, cudaMemcpyDefault, st));
     for (uint32_t i = 0; i < I; ++i)
       if (instance_lens[i])
         BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_inst(i)), (const char*)instances + ((size_t)b * I + i) * instance_stride * 32,
-                                (size_t)instance_lens[i] * 32, cudaMemcpyHostToDevice, st));
+                                (size_t)instance_lens[i] * 32, cudaMemcpyDefault, st));
   }
   desc_off = 0;
   // ---- step 1: instance commitments (blind 1), absorbed

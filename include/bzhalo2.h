@@ -58,6 +58,10 @@ const char* bz_version(void);
  *       7 quotient, 8 scan, 9 eval, 10 poly, 11 ipa, 12 other */
 int bz_profile_enable(bz_ctx* ctx, int on);
 int bz_profile_read(bz_ctx* ctx, int tag, double* total_ms, uint64_t* count);
+/* counters collected while profiling: 0 = mixed point additions executed by the fixed-base MSM kernel */
+int bz_profile_counter(bz_ctx* ctx, int which, uint64_t* value, int reset);
+/* measured integer multiply-add peak of this GPU (IMAD/s), the roofline denominator of the integer-bound kernels */
+int bz_imad_peak(bz_ctx* ctx, double* imad_per_sec);
 
 /* ---- device memory (library-owned, freed by bz_dev_free or with the context) ------------------- */
 int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr);
@@ -158,7 +162,8 @@ uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yie
  *   advice    : batch x num_advice x n scalars (rows >= n - (blinding_factors + 1) are ignored: blinded)
  *   rand_wide : batch x bz_pk_num_random x 64 B -- the raw outputs `Scalar::random(&mut rng)` would consume, in
  *               the exact order create_proof draws them (the shim pre-draws: the count is shape-only)
- *   proofs    : batch x bz_pk_proof_size bytes, identical to what Blake2bWrite::finalize() returns
+ *   (instances / advice / rand_wide may be host pointers or device pointers from bz_dev_alloc)
+ *   proofs    : batch x bz_pk_proof_size bytes (host), identical to what Blake2bWrite::finalize() returns
  * Errors: BZ_ERR_SYNTHESIS when a lookup input is missing from its table (Error::ConstraintSystemFailure). */
 int bz_create_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instances, const uint32_t* instance_lens,
                      uint32_t instance_stride, const void* advice, const void* rand_wide, void* proofs);
