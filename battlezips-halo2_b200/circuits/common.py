@@ -182,6 +182,7 @@ def ecc_shape_synthesize(lay, h, scalar_a, scalar_b, rng):
     :104-134 `[v]V + [r]R`), the 10-bit running-sum range check of one scalar, one incomplete and one complete
     addition.  Returns the (x, y) cells of the "commitment" (advice[0], advice[1] of the last row used)."""
     a, adv, fx, q = lay.asg, h["advice"], h["fixed"], h["q"]
+    frng = random.Random(0x5EED)    # fixed columns (window tables, z) are circuit constants: witness independent
     G = (P - 1, 2)              # a Pallas point: (-1)^3 + 5 = 2^2
     out_cell = None
     acc = G
@@ -194,11 +195,11 @@ def ecc_shape_synthesize(lay, h, scalar_a, scalar_b, rng):
             a.assign_advice(adv[4], row, z)                 # running sum z_i
             if i < 85:
                 w = windows[i]
-                coeffs = [rng.randrange(P) for _ in range(8)]
+                coeffs = [frng.randrange(P) for _ in range(8)]
                 for j in range(8):
                     a.assign_fixed(fx[j], row, coeffs[j])
                 x = sum(c * pow(w, j, P) for j, c in enumerate(coeffs)) % P
-                zf = rng.randrange(1 << 20)
+                zf = frng.randrange(1 << 20)
                 u = rng.randrange(P)
                 y = (u * u - zf) % P
                 a.assign_fixed(h["fixed_z"], row, zf)
