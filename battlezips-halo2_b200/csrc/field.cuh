@@ -9,6 +9,7 @@
 #pragma once
 #include <cstdint>
 #include <cuda_runtime.h>
+#include "montmul.cuh"
 
 namespace bz {
 
@@ -118,7 +119,7 @@ template <class P> __device__ __forceinline__ Fe<P> fe_dbl(const Fe<P>& a) { ret
 // Montgomery product a*b/R mod m.  Operand scanning, one reduction row per multiplier limb;
 // the reduction multiplier is q = -t0 (since -m^-1 = -1 mod 2^32) and only limbs 1..3 and 7 of the
 // modulus are non-trivial.  b < m required; a may be any value < 2^256 (used by from_u512).
-template <class P> __device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+template <class P> __device__ __forceinline__ Fe<P> fe_mul_c(const Fe<P>& a, const Fe<P>& b) {
   uint32_t t[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) t[i] = 0;
@@ -155,6 +156,15 @@ template <class P> __device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const
   Fe<P> r;
 #pragma unroll
   for (int i = 0; i < 8; ++i) r.l[i] = t[i];
+  return r;
+}
+
+// The shipped multiplication: explicit mad.lo.cc / madc.hi.cc carry chains (montmul.cuh).  Requires a + m < 2^256
+// and b < m, which every reduced operand satisfies.
+template <class P> __device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  Fe<P> r;
+  mm::mont_mul_wide<P::M1, P::M2, P::M3>(r.l, a.l, b.l);
+  fe_final_sub<P>(r.l);
   return r;
 }
 
@@ -222,7 +232,7 @@ template <class P> __device__ __forceinline__ Fe<P> fe_from_u512(const uint32_t 
   for (int i = 0; i < 8; ++i) { lo.l[i] = w[i]; hi.l[i] = w[8 + i]; }
   Fe<P> r2 = fe_r2<P>();
   Fe<P> r3 = fe_mul<P>(r2, r2);
-  return fe_add<P>(fe_mul<P>(lo, r2), fe_mul<P>(hi, r3));
+  return fe_add<P>(fe_mul_c<P>(lo, r2), fe_mul_c<P>(hi, r3));     // lo / hi are arbitrary 256-bit values
 }
 
 using Fp = Fe<FpP>;

@@ -95,7 +95,8 @@ static void fb_build_t(Ctx* ctx, FixedBase& fb, const void* bases_dev) {
 }
 
 void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev, uint32_t npts, uint32_t c) {
-  BZ_CHECK(c >= 2 && c <= 16, "fixed-base window out of range");
+  BZ_CHECK(c >= 4 && c <= 16, "fixed-base window out of range");
+  BZ_CHECK((uint64_t)((256 + c - 1) / c) * (1ull << (c - 1)) * npts < (1ull << 31), "fixed-base table too large for 31-bit entry indices");
   fb.curve = curve; fb.npts = npts; fb.c = c; fb.W = (256 + c - 1) / c; fb.nbk = 1u << (c - 1);
   if (curve == 0) fb_build_t<FqP>(ctx, fb, bases_dev); else fb_build_t<FpP>(ctx, fb, bases_dev);
 }
@@ -104,57 +105,107 @@ void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev,
 // grid = (chunks, n_msm), block = FB_THREADS.  MSM m sums over points [0, npts): scalars of points
 // i < n_main come from main[m] (a polynomial, Montgomery form), the trailing npts - n_main points
 // (w, u: blinds / IPA cross terms) from extra[m] (may be null = zero).
+//
+// Work compaction: witness columns are mostly 0 / 1, so "one thread = one point" leaves 2/3 of every warp idle
+// (ncu r1: 11-13 active threads per warp-instruction).  Each round the CTA decodes FB_THREADS scalars into
+// signed digits, packs the non-zero ones as table indices into a shared-memory work list (block-wide exclusive
+// scan of the per-thread counts, no atomics, deterministic order) and then ALL threads pull entries from the
+// list round-robin: every warp runs full until the list is drained.
 constexpr int FB_THREADS = 128;
+constexpr int FB_MAX_W = 64;       // windows per scalar (c >= 4)
 
 template <class BP, class SP>
-__global__ void __launch_bounds__(FB_THREADS) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
+__global__ void __launch_bounds__(FB_THREADS, 4) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
                                  const Fe<SP>* const* __restrict__ main, uint32_t n_main, const Fe<SP>* const* __restrict__ extra,
                                  Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
-  __shared__ Xyzz<BP> sh[FB_THREADS];
+  extern __shared__ uint32_t fb_smem[];
+  uint32_t* list = fb_smem;                                  // FB_THREADS * W entries
+  __shared__ uint32_t warp_cnt[FB_THREADS / 32];
   uint32_t my_adds = 0;
-  const uint32_t m = blockIdx.y, chunks = gridDim.x;
+  const uint32_t m = blockIdx.y, chunks = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Fe<SP>* sm = main[m];
   const Fe<SP>* se = extra ? extra[m] : nullptr;
   Xyzz<BP> acc = xyzz_identity<BP>();
   const uint32_t half = 1u << (c - 1), full = 1u << c;
-  for (uint32_t i = blockIdx.x * FB_THREADS + threadIdx.x; i < npts; i += chunks * FB_THREADS) {
-    Fe<SP> s;
-    if (i < n_main) s = fe_load(sm + i);
-    else if (se) s = fe_load(se + (i - n_main));
-    else continue;
-    if (fe_is_zero(s)) continue;
-    s = fe_from_mont(s);
-    uint32_t carry = 0;
-    for (uint32_t w = 0; w < W; ++w) {
-      uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
-      uint32_t raw = 0;
-      if (limb < 8) {
-        raw = s.l[limb] >> sh_;
-        if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
-        raw &= full - 1;
+  // this CTA's contiguous point range
+  const uint32_t per = (npts + chunks - 1) / chunks;
+  const uint32_t p_lo = blockIdx.x * per, p_hi = min(p_lo + per, npts);
+  for (uint32_t base = p_lo; base < p_hi; base += FB_THREADS) {
+    const uint32_t i = base + tid;
+    // ---- decode this thread's scalar into packed entries (kept in registers as a bitmap + digits recomputed) ----
+    Fe<SP> s = fe_zero<SP>();
+    bool have = false;
+    if (i < p_hi) {
+      if (i < n_main) { s = fe_load(sm + i); have = true; }
+      else if (se) { s = fe_load(se + (i - n_main)); have = true; }
+    }
+    uint32_t cnt = 0;
+    if (have && !fe_is_zero(s)) {
+      s = fe_from_mont(s);
+      uint32_t carry = 0;
+      for (uint32_t w = 0; w < W; ++w) {
+        uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
+        uint32_t raw = 0;
+        if (limb < 8) {
+          raw = s.l[limb] >> sh_;
+          if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
+          raw &= full - 1;
+        }
+        uint32_t v = raw + carry;
+        carry = v > half ? 1u : 0u;
+        cnt += (v != 0 && v != full) ? 1u : 0u;      // v == full cannot happen (raw <= full-1, carry makes v<=full; v==full -> d=0)
       }
-      uint32_t v = raw + carry;
-      bool neg = v > half;
-      uint32_t d = neg ? full - v : v;
-      carry = neg ? 1u : 0u;
-      if (d) {
-        Affine<BP> pt = aff_load(table + ((size_t)w * nbk + (d - 1)) * npts + i);
-        xyzz_add_mixed_signed(acc, pt, neg);
-        ++my_adds;
+    } else have = false;
+    // ---- block-wide exclusive scan of cnt ----
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    if (lane == 31) warp_cnt[wid] = incl;
+    __syncthreads();
+    uint32_t off = incl - cnt, total = 0;
+#pragma unroll
+    for (int w2 = 0; w2 < FB_THREADS / 32; ++w2) { uint32_t t = warp_cnt[w2]; if (w2 < (int)wid) off += t; total += t; }
+    // ---- write entries ----
+    if (have) {
+      uint32_t carry = 0;
+      for (uint32_t w = 0; w < W; ++w) {
+        uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
+        uint32_t raw = 0;
+        if (limb < 8) {
+          raw = s.l[limb] >> sh_;
+          if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
+          raw &= full - 1;
+        }
+        uint32_t v = raw + carry;
+        bool neg = v > half;
+        uint32_t d = neg ? full - v : v;
+        carry = neg ? 1u : 0u;
+        if (d) list[off++] = (uint32_t)(((size_t)w * nbk + (d - 1)) * npts + i) | (neg ? 0x80000000u : 0u);
       }
     }
+    __syncthreads();
+    // ---- drain the list: all threads busy ----
+    for (uint32_t e = tid; e < total; e += FB_THREADS) {
+      uint32_t ent = list[e];
+      Affine<BP> pt = aff_load(table + (ent & 0x7fffffffu));
+      xyzz_add_mixed_signed(acc, pt, (ent >> 31) != 0);
+      ++my_adds;
+    }
+    __syncthreads();
   }
   if (add_counter) {       // profiling only: exact number of mixed additions this launch performed
     uint32_t tot = __reduce_add_sync(0xffffffffu, my_adds);
-    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(add_counter, (unsigned long long)tot);
+    if (lane == 0 && tot) atomicAdd(add_counter, (unsigned long long)tot);
   }
-  sh[threadIdx.x] = acc;
+  // ---- CTA tree reduction (the list buffer is reused as XYZZ scratch: FB_THREADS * 128 B) ----
+  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(fb_smem);
+  sh[tid] = acc;
   __syncthreads();
   for (uint32_t d = FB_THREADS >> 1; d > 0; d >>= 1) {
-    if (threadIdx.x < d) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + d]);
+    if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
     __syncthreads();
   }
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     Xyzz<BP>* o = partial + (size_t)m * chunks + blockIdx.x;
     fe_store(&o->x, sh[0].x); fe_store(&o->y, sh[0].y); fe_store(&o->zz, sh[0].zz); fe_store(&o->zzz, sh[0].zzz);
   }
@@ -184,7 +235,8 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
   Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
   {
     ProfScope p(ctx, PROF_FIXED_MSM);
-    fixed_msm_kernel<BP, SP><<<dim3(chunks, n_msm), FB_THREADS, 0, st>>>(
+    const size_t smem = std::max<size_t>((size_t)FB_THREADS * fb.W * 4, (size_t)FB_THREADS * sizeof(Xyzz<BP>));
+    fixed_msm_kernel<BP, SP><<<dim3(chunks, n_msm), FB_THREADS, smem, st>>>(
         fb.table.as<Affine<BP>>(), fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main,
         (const Fe<SP>* const*)d_extra, partial, ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr);
   }

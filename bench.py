@@ -29,6 +29,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "shot"))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("BZ_BATCH", "64")), help="proofs per step per GPU (shot / board)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "3")),
+                    help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board)")
     ap.add_argument("--log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
@@ -36,6 +38,11 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------------
+# FMA-pipe (IMAD / IMAD.WIDE / IMAD.HI / IMAD.X) instructions per field multiplication in the shipped SASS
+# (cuobjdump -sass count of pow_table_kernel / 2)
+FMA_PER_MUL = 125
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -240,10 +247,10 @@ class ProofWorkload:
     DISTINCT = 8
 
     def __init__(self, args, which):
-        self.which, self.B = which, args.batch
+        self.which, self.B, self.T = which, args.batch, max(1, args.inflight)
         self.k = 11 if which == "shot" else 12
-        self.name = (f"batched {'Shot' if which == 'shot' else 'Board'} proofs (k={self.k}, IPA/Pasta), {self.B} independent proofs per "
-                     f"GPU per step, synthetic witnesses (BASELINE config {'3' if which == 'shot' else '2'})")
+        self.name = (f"batched {'Shot' if which == 'shot' else 'Board'} proofs (k={self.k}, IPA/Pasta), {self.T} lanes x {self.B} independent "
+                     f"proofs per GPU per step, synthetic witnesses (BASELINE config {'3' if which == 'shot' else '2'})")
 
     def _jobs(self, rank):
         from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
@@ -280,48 +287,75 @@ class ProofWorkload:
         return out
 
     def setup(self, ctx, rank):
-        import torch
+        import torch, ctypes
+        import battlezips_halo2_b200 as bz
         from battlezips_halo2_b200.plonk import prover as PR
+        from concurrent.futures import ThreadPoolExecutor
         self.ctx, self.PR = ctx, PR
         adv_d = self._jobs(rank)
         fx = np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
-        self.params = PR.Params(ctx, self.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])
+        self.params = PR.Params(ctx, self.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])     # window tables: shared by all lanes
         self.fx = fx
-        self.pk = PR.ProvingKey(ctx, self.params, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), 0x1234567890ABCDEF1234567890ABCDEF)
-        B = self.B
-        sel = [i % self.DISTINCT for i in range(B)]
-        self.advice = np.ascontiguousarray(adv_d[sel])                        # (B, G, n, 4)
-        self.wide = self._wide(rank, B)
+        B, T = self.B, self.T
         ni = self.ir["num_instance"]
         self.lens = np.array([len(self.instances_d[0][i]) for i in range(ni)], dtype=np.uint32)
-        stride = int(self.lens.max())
-        inst = np.zeros((B, ni, stride, 4), dtype=np.uint64)
-        for b in range(B):
-            for i in range(ni):
-                inst[b, i, :self.lens[i]] = PR.mont(self.instances_d[sel[b]][i])
-        self.inst, self.stride = inst, stride
-        self.proofs = np.zeros((B, self.pk.proof_size), dtype=np.uint8)
-        # pinned host copies (e2e) and device-resident copies (value)
-        self.h_adv = torch.from_numpy(self.advice.view(np.int64)).pin_memory()
-        self.h_wide = torch.from_numpy(self.wide.view(np.int64)).pin_memory()
-        self.h_inst = torch.from_numpy(self.inst.view(np.int64)).pin_memory()
-        self.d_adv, self.d_wide, self.d_inst = ctx.to_device(self.advice), ctx.to_device(self.wide), ctx.to_device(self.inst)
-        self.h2d = self.advice.nbytes + self.wide.nbytes + self.inst.nbytes
-        self.d2h = self.proofs.nbytes
+        self.stride = int(self.lens.max())
+        mapping = self.asg0.permutation_mapping()
+        self.lanes = []
+        wide_all = self._wide(rank, B * T)
+        for t in range(T):
+            lane = {}
+            lane["stream"] = torch.cuda.current_stream() if t == 0 else torch.cuda.Stream()
+            lane["ctx"] = ctx if t == 0 else bz.Context(ctx.device, stream=lane["stream"].cuda_stream)
+            lane["pk"] = PR.ProvingKey(lane["ctx"], self.params, self.ir, self.asg0.fixed, mapping, 0x1234567890ABCDEF1234567890ABCDEF)
+            sel = [(t * B + i) % self.DISTINCT for i in range(B)]
+            lane["sel"] = sel
+            advice = np.ascontiguousarray(adv_d[sel])                        # (B, G, n, 4)
+            wide = np.ascontiguousarray(wide_all[t * B:(t + 1) * B])
+            inst = np.zeros((B, ni, self.stride, 4), dtype=np.uint64)
+            for b in range(B):
+                for i in range(ni):
+                    inst[b, i, :self.lens[i]] = PR.mont(self.instances_d[sel[b]][i])
+            lane["proofs"] = np.zeros((B, lane["pk"].proof_size), dtype=np.uint8)
+            lane["h"] = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in (inst, advice, wide)]
+            lane["d"] = [lane["ctx"].to_device(x) for x in (inst, advice, wide)]
+            lane["bytes"] = advice.nbytes + wide.nbytes + inst.nbytes
+            self.lanes.append(lane)
+        self.advice, self.wide = np.ascontiguousarray(adv_d[:1]), wide_all[:2]
+        self.pk = self.lanes[0]["pk"]
+        self.h2d = sum(l["bytes"] for l in self.lanes)
+        self.d2h = sum(l["proofs"].nbytes for l in self.lanes)
+        self.pool = ThreadPoolExecutor(T)
 
-    def _run(self, inst_ptr, adv_ptr, wide_ptr):
+    def _lane_run(self, lane, ptrs):
         import ctypes
-        c = self.ctx
-        c._check(c.lib.bz_create_proofs(c.h, self.pk.h, self.B, inst_ptr, self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
-                                        adv_ptr, wide_ptr, self.proofs.ctypes.data_as(ctypes.c_void_p)))
-        return self.B
+        c = lane["ctx"]
+        c._check(c.lib.bz_create_proofs(c.h, lane["pk"].h, self.B, ptrs[0], self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
+                                        ptrs[1], ptrs[2], lane["proofs"].ctypes.data_as(ctypes.c_void_p)))
+
+    def _run(self, device):
+        import ctypes
+        futs = []
+        for lane in self.lanes:
+            ptrs = [d.ptr for d in lane["d"]] if device else [ctypes.c_void_p(h.data_ptr()) for h in lane["h"]]
+            futs.append(self.pool.submit(self._lane_run, lane, ptrs))
+        for f in futs:
+            f.result()
+        return self.B * self.T
 
     def step_device(self):
-        return self._run(self.d_inst.ptr, self.d_adv.ptr, self.d_wide.ptr)
+        return self._run(True)
 
     def step_e2e(self):
-        import ctypes
-        return self._run(ctypes.c_void_p(self.h_inst.data_ptr()), ctypes.c_void_p(self.h_adv.data_ptr()), ctypes.c_void_p(self.h_wide.data_ptr()))
+        return self._run(False)
+
+    def step_profile(self):
+        lane = self.lanes[0]
+        self._lane_run(lane, [d.ptr for d in lane["d"]])
+        return self.B
+
+    def all_contexts(self):
+        return [l["ctx"] for l in self.lanes]
 
     def dominant(self):
         # fixed-base MSM: algorithmic bytes = one 64 B table point per mixed addition + 32 B per scalar read
@@ -332,10 +366,10 @@ class ProofWorkload:
         from oracle import halo2 as H
         op = H.Params(self.k, 0, self.fx["g"], self.fx["g_lagrange"], self.fx["w"], self.fx["u"])
         opk = H.keygen(op, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), vk_repr=0x1234567890ABCDEF1234567890ABCDEF)
-        sel = [i % self.DISTINCT for i in range(self.B)]
-        for b in sorted({0, self.B - 1}):
-            if not H.verify_proof(op, opk, self.instances_d[sel[b]], bytes(self.proofs[b])):
-                return False
+        for lane in (self.lanes[0], self.lanes[-1]):
+            for b in sorted({0, self.B - 1}):
+                if not H.verify_proof(op, opk, self.instances_d[lane["sel"][b]], bytes(lane["proofs"][b])):
+                    return False
         self._oracle = (H, op, opk)
         return True
 
@@ -425,8 +459,8 @@ def main():
     for _ in range(args.warmup):
         wl.step_device()
     barrier()
-    launches0 = ctx.kernel_launches()
-    ctx.profile_enable(True)
+    ctxs = wl.all_contexts() if hasattr(wl, "all_contexts") else [ctx]
+    launches0 = sum(c.kernel_launches() for c in ctxs)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -443,8 +477,21 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     clocks = sampler.stop() if rank == 0 else None
-    launches = ctx.kernel_launches() - launches0
-    prof = ctx.profile_read()
+    launches = sum(c.kernel_launches() for c in ctxs) - launches0
+    # ---- per-kernel pass: the same steps on ONE lane with the library's CUDA-event scopes on, so every kernel is
+    # timed alone on the GPU (with several lanes in flight, kernels of different lanes overlap and a per-kernel
+    # duration would measure the time-slicing, not the kernel).  The roofline / int_pipe objects come from here.
+    ctx.profile_enable(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(args.steps):
+        (wl.step_profile if hasattr(wl, "step_profile") else wl.step_device)()
+    p1.record(stream)
+    barrier()
+    prof_ms = p0.elapsed_time(p1)
+    prof = dict(ctx.profile_read())
+    adds_total = ctx.profile_counter(0)
     ctx.profile_enable(False)
 
     # ---- end-to-end through the host-buffer ABI (H2D + D2H inside the timed region) ----
@@ -476,22 +523,22 @@ def main():
     roof = None
     int_pipe = None
     if tag == "fixed_msm" and tag in prof:
-        adds = ctx.profile_counter(0)
+        adds = adds_total
         tot_ms, cnt = prof[tag]
         alg_bytes = adds * 64.0 / cnt + 32.0 * (wl.B * (1 << wl.k)) * 0      # per launch: one 64 B table entry per mixed addition
         imad_peak = ctx.imad_peak()
         # 10 field multiplications (8M + 2S) per mixed addition; I = IMAD-pipe instructions per multiplication in the
         # shipped SASS (cuobjdump count): IMAD.WIDE + IMAD.X + IMAD.MOV/SHL/U32
         fmul_per_s = adds * 10.0 / (tot_ms / 1e3)
-        int_pipe = {"kernel": tag, "mixed_adds_per_step": adds / args.steps, "field_mul_per_s": fmul_per_s, "imad_per_field_mul_sass": 220,
-                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * 220 / imad_peak}
+        int_pipe = {"kernel": tag, "mixed_adds_per_step": adds / args.steps, "field_mul_per_s": fmul_per_s, "fma_pipe_instr_per_field_mul_sass": FMA_PER_MUL,
+                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * FMA_PER_MUL / imad_peak}
     if tag in prof:
         tot_ms, cnt = prof[tag]
         avg_s = tot_ms / cnt / 1e3
         ach = alg_bytes / avg_s / 1e9
         roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
-                "share_of_step": tot_ms / ms,
+                "share_of_step": tot_ms / prof_ms, "measured": "single-lane pass of the same steps, CUDA-event scopes in the library",
                 "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
     cpu = None
     if world == 1 or rank == 0:
