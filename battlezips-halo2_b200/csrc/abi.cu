@@ -139,6 +139,46 @@ __global__ void imad_peak_kernel(uint32_t* out, uint32_t iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
+// same, with 32x32+64 -> 64 multiply-adds (IMAD.WIDE.U32), the instruction the Montgomery multiplication is made of
+__global__ void imad_wide_peak_kernel(unsigned long long* out, uint32_t iters) {
+  unsigned long long a0 = threadIdx.x + 1, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+  const uint32_t m = blockIdx.x * 2 + 1;
+  for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      a0 = (unsigned long long)(uint32_t)a0 * m + a0; a1 = (unsigned long long)(uint32_t)a1 * m + a1;
+      a2 = (unsigned long long)(uint32_t)a2 * m + a2; a3 = (unsigned long long)(uint32_t)a3 * m + a3;
+      a4 = (unsigned long long)(uint32_t)a4 * m + a4; a5 = (unsigned long long)(uint32_t)a5 * m + a5;
+      a6 = (unsigned long long)(uint32_t)a6 * m + a6; a7 = (unsigned long long)(uint32_t)a7 * m + a7;
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+}
+__attribute__((visibility("default"))) int bz_imad_wide_peak(bz_ctx* ctx, double* imad_wide_per_sec) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(imad_wide_per_sec, "null out");
+    const int blocks = ctx->c.sm_count * 8, threads = 256;
+    const uint32_t iters = 4096;
+    bz::DevBuf out; out.alloc((size_t)blocks * threads * 8);
+    cudaStream_t st = ctx->c.stream;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    imad_wide_peak_kernel<<<blocks, threads, 0, st>>>(out.as<unsigned long long>(), 64);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0, st);
+      imad_wide_peak_kernel<<<blocks, threads, 0, st>>>(out.as<unsigned long long>(), iters);
+      cudaEventRecord(e1, st);
+      BZ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      double ops = (double)blocks * threads * iters * 64.0;
+      best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->c.kernel_launches += 4;
+    *imad_wide_per_sec = best;
+  });
+}
+
 __attribute__((visibility("default"))) int bz_imad_peak(bz_ctx* ctx, double* imad_per_sec) {
   BZ_TRY(ctx, {
     BZ_CHECK(imad_per_sec, "null out");

@@ -161,10 +161,31 @@ template <class P> __device__ __forceinline__ Fe<P> fe_mul_c(const Fe<P>& a, con
 
 // The shipped multiplication: explicit mad.lo.cc / madc.hi.cc carry chains (montmul.cuh).  Requires a + m < 2^256
 // and b < m, which every reduced operand satisfies.
+// Out of line on purpose: fully inlined, the mixed-addition loop of the MSM kernel is ~180 KB of SASS and thrashes
+// the 32 KB L1.5 instruction cache (ncu r1b: `no_instruction` stalls, no gain from occupancy).  One shared copy of the
+// ~250-instruction multiplication keeps every hot loop inside the instruction cache.
+#ifndef BZ_MUL_INLINE
+#define BZ_MUL_ATTR __noinline__
+#else
+#define BZ_MUL_ATTR __forceinline__
+#endif
+struct MulRet { uint4 lo, hi; };      // returned in registers by the device ABI
+template <class P> __device__ BZ_MUL_ATTR MulRet fe_mul_raw(uint4 a0, uint4 a1, uint4 b0, uint4 b1) {
+  uint32_t a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  uint32_t b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  uint32_t r[8];
+  mm::mont_mul_wide<P::M1, P::M2, P::M3>(r, a, b);
+  fe_final_sub<P>(r);
+  MulRet o;
+  o.lo = make_uint4(r[0], r[1], r[2], r[3]); o.hi = make_uint4(r[4], r[5], r[6], r[7]);
+  return o;
+}
 template <class P> __device__ __forceinline__ Fe<P> fe_mul(const Fe<P>& a, const Fe<P>& b) {
+  MulRet o = fe_mul_raw<P>(make_uint4(a.l[0], a.l[1], a.l[2], a.l[3]), make_uint4(a.l[4], a.l[5], a.l[6], a.l[7]),
+                           make_uint4(b.l[0], b.l[1], b.l[2], b.l[3]), make_uint4(b.l[4], b.l[5], b.l[6], b.l[7]));
   Fe<P> r;
-  mm::mont_mul_wide<P::M1, P::M2, P::M3>(r.l, a.l, b.l);
-  fe_final_sub<P>(r.l);
+  r.l[0] = o.lo.x; r.l[1] = o.lo.y; r.l[2] = o.lo.z; r.l[3] = o.lo.w;
+  r.l[4] = o.hi.x; r.l[5] = o.hi.y; r.l[6] = o.hi.z; r.l[7] = o.hi.w;
   return r;
 }
 

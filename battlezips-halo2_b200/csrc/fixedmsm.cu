@@ -11,6 +11,7 @@
 #include "common.h"
 #include "curve.cuh"
 #include "fixedmsm.h"
+#include <cstdlib>
 
 namespace bz {
 
@@ -114,8 +115,8 @@ void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev,
 constexpr int FB_THREADS = 128;
 constexpr int FB_MAX_W = 64;       // windows per scalar (c >= 4)
 
-template <class BP, class SP>
-__global__ void __launch_bounds__(FB_THREADS, 4) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
+template <class BP, class SP, int MINB>
+__global__ void __launch_bounds__(FB_THREADS, MINB) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
                                  const Fe<SP>* const* __restrict__ main, uint32_t n_main, const Fe<SP>* const* __restrict__ extra,
                                  Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
   extern __shared__ uint32_t fb_smem[];
@@ -236,9 +237,15 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
   {
     ProfScope p(ctx, PROF_FIXED_MSM);
     const size_t smem = std::max<size_t>((size_t)FB_THREADS * fb.W * 4, (size_t)FB_THREADS * sizeof(Xyzz<BP>));
-    fixed_msm_kernel<BP, SP><<<dim3(chunks, n_msm), FB_THREADS, smem, st>>>(
-        fb.table.as<Affine<BP>>(), fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main,
-        (const Fe<SP>* const*)d_extra, partial, ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr);
+    static int occ = -1;
+    if (occ < 0) { const char* e = getenv("BZ_MSM_OCC"); occ = e ? atoi(e) : 4; }   // measured on B200 (profiles/README.md): 4 CTAs/SM is fastest; IMAD.WIDE chains saturate the fma-heavy pipe
+    unsigned long long* cnt = ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr;
+#define BZ_FB_LAUNCH(MINB)                                                                                       \
+    fixed_msm_kernel<BP, SP, MINB><<<dim3(chunks, n_msm), FB_THREADS, smem, st>>>(                                 \
+        fb.table.as<Affine<BP>>(), fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main,             \
+        (const Fe<SP>* const*)d_extra, partial, cnt)
+    if (occ >= 8) BZ_FB_LAUNCH(8); else if (occ >= 6) BZ_FB_LAUNCH(6); else if (occ == 5) BZ_FB_LAUNCH(5); else BZ_FB_LAUNCH(4);
+#undef BZ_FB_LAUNCH
   }
   fixed_msm_finish_kernel<BP><<<(n_msm + 31) / 32, 32, 0, st>>>(partial, chunks, n_msm, (Affine<BP>*)d_out_affine);
   ctx->kernel_launches += 2;

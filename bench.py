@@ -38,9 +38,10 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------------------------
-# FMA-pipe (IMAD / IMAD.WIDE / IMAD.HI / IMAD.X) instructions per field multiplication in the shipped SASS
-# (cuobjdump -sass count of pow_table_kernel / 2)
-FMA_PER_MUL = 125
+# fma-heavy pipe cost of one field multiplication in the shipped SASS, in IMAD-equivalents (issue slots of the pipe):
+# 71 IMAD.WIDE.U32(.X) at HALF rate (measured: bz_imad_wide_peak = 0.455 x bz_imad_peak) = 142, plus 25 IMAD.HI + 11 IMAD +
+# 18 IMAD.X at full rate = 54  ->  196  (cuobjdump -sass of fe_mul_raw)
+FMA_PER_MUL = 196
 
 
 def peaks():

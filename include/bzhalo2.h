@@ -62,6 +62,8 @@ int bz_profile_read(bz_ctx* ctx, int tag, double* total_ms, uint64_t* count);
 int bz_profile_counter(bz_ctx* ctx, int which, uint64_t* value, int reset);
 /* measured integer multiply-add peak of this GPU (IMAD/s), the roofline denominator of the integer-bound kernels */
 int bz_imad_peak(bz_ctx* ctx, double* imad_per_sec);
+/* same for the 32x32+64->64 form (IMAD.WIDE.U32), which is what the field multiplication is built from */
+int bz_imad_wide_peak(bz_ctx* ctx, double* imad_wide_per_sec);
 
 /* ---- device memory (library-owned, freed by bz_dev_free or with the context) ------------------- */
 int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr);
