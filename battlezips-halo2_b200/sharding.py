@@ -27,3 +27,30 @@ def gather_proofs(local_proofs, lo, total, group=None):
         merged.update(part)
     assert sorted(merged) == list(range(total)), "shards do not cover the job range exactly once"
     return [merged[i] for i in range(total)]
+
+
+def allgather_point_sum(local_jac, normalize, add, device=None, group=None):
+    """The one real exchange on this path: a large MSM is split by POINT RANGE, every rank reduces its
+    range to one Jacobian partial (96 B) and the partials are all-gathered (NCCL has no elliptic-curve reduction op)
+    and summed locally: G - 1 point additions.
+
+    local_jac : numpy (12,) uint64 Jacobian partial of this rank
+    normalize : callable (G,12) uint64 Jacobian -> (G,8) uint64 affine       (GPU: bz_batch_normalize_dev)
+    add       : callable ((8,), (8,)) affine -> (8,) affine                   (GPU: bz_curve_op add)
+    device    : torch device of the exchange tensors ("cuda" for NCCL, "cpu" for gloo)
+    Returns the affine sum (8,) uint64 on every rank."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    t = torch.from_numpy(np.ascontiguousarray(local_jac, dtype=np.uint64).view(np.int64).copy())
+    if device is not None:
+        t = t.to(device)
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    jac = np.stack([p.cpu().numpy().view(np.uint64) for p in parts])
+    aff = normalize(jac)
+    acc = aff[0]
+    for i in range(1, world):
+        acc = add(acc, aff[i])
+    return acc

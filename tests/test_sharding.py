@@ -44,3 +44,38 @@ def test_two_rank_sharded_proving(tmp_path):
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(2, _free_port(), 5, out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def _msm_worker(rank, world, port, out_path):
+    import numpy as np
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from oracle import c_oracle as co
+    from battlezips_halo2_b200.sharding import allgather_point_sum
+    import ctypes
+    rng = np.random.default_rng(5)
+    n = 300
+    C = co.CURVES[0][0]
+    h = C.hash_to_curve("Halo2-Parameters")
+    bases = co.points_to_mont(0, [h(b"\x00" + i.to_bytes(4, "little")) for i in range(n)])
+    scalars = co.from_u512(0, rng.integers(0, 2**63, size=(n, 8), dtype=np.uint64))
+    lo, hi = shard_range(n, rank, world)
+    partial = co.best_multiexp(0, scalars[lo:hi], bases[lo:hi])
+
+    def add(a, b):
+        out = np.zeros(8, dtype=np.uint64)
+        co.lib().orc_point_add(0, co._p(np.ascontiguousarray(a)), co._p(np.ascontiguousarray(b)), co._p(out))
+        return out
+    total = allgather_point_sum(partial, lambda j: co.to_affine(0, j), add, device="cpu")
+    full = co.to_affine(0, co.best_multiexp(0, scalars, bases))[0]
+    if rank == 0:
+        open(out_path, "w").write("ok" if np.array_equal(total, full) else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_point_range_split_msm_allgather(tmp_path):
+    """Large-MSM split by point range + all-gather of 96 B partials + local sum == unsplit MSM."""
+    out = str(tmp_path / "msm.txt")
+    mp.spawn(_msm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
