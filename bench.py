@@ -198,7 +198,6 @@ class MsmWorkload:
         c._check(c.lib.bz_best_multiexp(c.h, self.curve, ctypes.c_void_p(self.h_scalars.data_ptr()),
                                         ctypes.c_void_p(self.h_bases.data_ptr()), self.n, out.ctypes.data_as(ctypes.c_void_p)))
         if self.world > 1:
-            c.to_device(out).ptr and None
             self.d_out.upload(out)
             self._combine()
             return self.n_total / self.world
