@@ -31,7 +31,7 @@ def parse():
     ap.add_argument("--batch", type=int, default=int(os.environ.get("BZ_BATCH", "64")), help="proofs per step per GPU (shot / board)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "3")),
                     help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board)")
-    ap.add_argument("--log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
+    ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
     return ap.parse_args()
