@@ -4,4 +4,4 @@ gate-for-gate; the 19 halo2_gadgets ECC / range-check gates that `PedersenCommit
 (R:src/chips/pedersen.rs:49-62) are SHAPE-EQUIVALENT stand-ins (same count, degrees up to 9, rotations, one
 degree-3 lookup against the 1024-row table) -- see SURVEY App. C and DESIGN.md "Circuits"."""
 from .shot import shot_circuit
-from .board import board_circuit
+from .board import board_circuit, board_circuit_scaled

@@ -59,13 +59,29 @@ def configure():
                 "num2bits": num2bits, "bits2num": bits2num, "placement": placement, "q_transpose": q_t, "ecc": ecc}
 
 
-def synthesize(cs, cfg, pattern, trapdoor, seed=0):
+def synthesize(cs, cfg, pattern, trapdoor, seed=0, k=K, copies=1):
     """R:src/chips/board.rs:331-363: 10 ship commitments (H, V per ship) -> bits -> placement -> transpose ->
-    board state -> Pedersen commitment; public = commitment (x, y)."""
+    board state -> Pedersen commitment; public = commitment (x, y).
+    copies > 1 tiles the whole board region pattern down the rows (BASELINE config 5: "Board circuit replicated ...
+    many boards per proof"); the public inputs are those of the first board."""
     rng = random.Random(seed)
-    lay = Layout(cs, K)
-    a, adv, fx = lay.asg, cfg["advice"], cfg["fixed"]
+    lay = Layout(cs, k)
+    a = lay.asg
     ecc_shape_load_table(lay, cfg["ecc"])
+    first = None
+    for c in range(copies):
+        pat = pattern if c % 2 == 0 else (PATTERN_2 if pattern is PATTERN_1 else PATTERN_1)
+        cells = _synthesize_board(lay, cs, cfg, pat, (trapdoor + c) % (1 << 254), rng)
+        first = first or cells
+    cx, cy, commit = first
+    a.set_instance(cfg["instance"], [commit[0], commit[1]])          # R:src/chips/board.rs:359-360
+    a.copy(cx, ("instance", cfg["instance"], 0))
+    a.copy(cy, ("instance", cfg["instance"], 1))
+    return a
+
+
+def _synthesize_board(lay, cs, cfg, pattern, trapdoor, rng):
+    a, adv, fx = lay.asg, cfg["advice"], cfg["fixed"]
     # ship commitments: horizontal / vertical bitfields, one of each pair is zero
     ships = []
     for (x, y, vertical), length in zip(pattern, SHIP_LENGTHS):
@@ -135,11 +151,18 @@ def synthesize(cs, cfg, pattern, trapdoor, seed=0):
     b2n = num2bits_synthesize(lay, cfg["bits2num"], fx[0], state_cell, board_bits)
     for t in range(BOARD_SIZE):
         a.copy(b2n[t], ("advice", adv[10], rt + t))
-    cx, cy, commit = ecc_shape_synthesize(lay, cfg["ecc"], board_state, trapdoor, rng)
-    a.set_instance(cfg["instance"], [commit[0], commit[1]])          # R:src/chips/board.rs:359-360
-    a.copy(cx, ("instance", cfg["instance"], 0))
-    a.copy(cy, ("instance", cfg["instance"], 1))
-    return a
+    return ecc_shape_synthesize(lay, cfg["ecc"], board_state, trapdoor, rng)
+
+
+def board_circuit_scaled(k, copies=None, seed=0):
+    """BASELINE config 5: the Board circuit replicated down the rows of a 2^k-row table (copies=None: as many boards as
+    fit).  Same constraint system as the k=12 circuit; only the number of used rows and k change."""
+    cs, cfg = configure()
+    rows_per_board = 2100
+    if copies is None:
+        copies = max(1, ((1 << k) - 1200) // rows_per_board)
+    asg = synthesize(cs, cfg, PATTERN_1, random.Random(3000 + seed).randrange(1 << 254), seed=seed, k=k, copies=copies)
+    return cs, cfg, asg
 
 
 def board_circuit(index=0, seed=0):

@@ -20,6 +20,9 @@ typedef bzh::Fe HFe;
 
 namespace bz {
 
+void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
+void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+
 typedef ::bz::Fe<FpP> DFe;      // device element type of the prover's scalar field (Vesta scalars = Fp)
 
 // ------------------------------------------------------------------------------------------------------
@@ -29,6 +32,7 @@ struct ParamsImpl {
   DevBuf g_w_u;         // n + 2 affine points: g || w || u
   DevBuf gl_w;          // n + 1 affine points: g_lagrange || w
   FixedBase fb_g, fb_gl;
+  bool use_tables = true;   // small n: fixed-base window tables; large n (k >= 15): bucket MSM over the raw bases
 };
 
 struct Token { uint32_t op, a; int32_t b; };
@@ -92,7 +96,7 @@ struct PkImpl {
   // workspace cache
   struct Work {
     uint32_t batch = 0;
-    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in;
+    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
   } work;
   ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); }
@@ -365,8 +369,14 @@ API int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, cons
         }
       }
     }
-    fixed_base_build(C, p.fb_g, curve, p.g_w_u.p, (uint32_t)n + 2, c);
-    fixed_base_build(C, p.fb_gl, curve, p.gl_w.p, (uint32_t)n + 1, c);
+    const char* fg = getenv("BZ_FORCE_GENERAL_MSM");
+    p.use_tables = k <= 14 && !(fg && atoi(fg));
+    if (p.use_tables) {
+      fixed_base_build(C, p.fb_g, curve, p.g_w_u.p, (uint32_t)n + 2, c);
+      fixed_base_build(C, p.fb_gl, curve, p.gl_w.p, (uint32_t)n + 1, c);
+    } else {
+      p.fb_g.curve = p.fb_gl.curve = curve; p.fb_g.npts = (uint32_t)n + 2; p.fb_gl.npts = (uint32_t)n + 1;
+    }
     *out = h.release();
   });
 }
@@ -386,7 +396,15 @@ API int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, con
     void* ptrs[2] = {d_poly.p, d_extra.p};
     BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
     const FixedBase& fb = lagrange_basis ? p.fb_gl : p.fb_g;
-    fixed_msm_run(C, fb, (const void* const*)d_ptrs.p, p.n, (const void* const*)((void**)d_ptrs.p + 1), 1, 16, d_out.p);
+    if (p.use_tables) fixed_msm_run(C, fb, (const void* const*)d_ptrs.p, p.n, (const void* const*)((void**)d_ptrs.p + 1), 1, 16, d_out.p);
+    else {
+      DevBuf d_in, d_jac; d_in.alloc((size_t)fb.npts * 32); d_jac.alloc(96);
+      BZ_CUDA(cudaMemcpyAsync(d_in.p, d_poly.p, (size_t)p.n * 32, cudaMemcpyDeviceToDevice, st));
+      BZ_CUDA(cudaMemcpyAsync((char*)d_in.p + (size_t)p.n * 32, d_extra.p, (size_t)(fb.npts - p.n) * 32, cudaMemcpyDeviceToDevice, st));
+      msm_run(C, p.curve, d_in.p, lagrange_basis ? p.gl_w.p : p.g_w_u.p, fb.npts, d_jac.p, 0);
+      jac_to_affine_run(C, p.curve, d_jac.p, d_out.p, 1);
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
     BZ_CUDA(cudaMemcpyAsync(out_affine, d_out.p, 64, cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
   });
@@ -693,7 +711,6 @@ struct Prover {
     pts.assign(B, std::vector<HostPoint>(nr));
     // all requests of one call share the basis
     bool lag = reqs[0].lagrange;
-    const FixedBase& fb = lag ? pk.params->fb_gl : pk.params->fb_g;
     std::vector<void*> mainp((size_t)B * nr), extrap((size_t)B * nr);
     std::vector<HFe> ex((size_t)B * nr * 2, F.zero());
     BZ_CHECK((size_t)B * nr * 2 * 32 <= w.extras.bytes && (size_t)B * nr * 2 * sizeof(void*) <= w.ptrs.bytes && (size_t)B * nr * 64 <= w.commits.bytes,
@@ -709,12 +726,30 @@ struct Prover {
         else ex[j * 2] = blinds[b][i];
       }
     BZ_CUDA(cudaMemcpyAsync(w.extras.p, ex.data(), ex.size() * 32, cudaMemcpyHostToDevice, st));
-    BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), mainp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-    BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + (size_t)B * nr, extrap.data(), extrap.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
     uint32_t n_msm = B * nr;
-    uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / std::max(1u, n_msm))));
-    fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + (size_t)B * nr), n_msm, chunks, w.commits.p);
+    run_msms(lag, mainp, extrap, n_msm);
     read_points(n_msm, nr, pts);
+  }
+  // one batch of commitments: fixed-base tables when available, otherwise the bucket MSM per polynomial
+  void run_msms(bool lagrange, const std::vector<void*>& mainp, const std::vector<void*>& extrap, uint32_t n_msm) {
+    const FixedBase& fb = lagrange ? pk.params->fb_gl : pk.params->fb_g;
+    if (pk.params->use_tables) {
+      BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+      BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + n_msm, extrap.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+      uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / std::max(1u, n_msm))));
+      fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + n_msm), n_msm, chunks, w.commits.p);
+      return;
+    }
+    const uint32_t npts = fb.npts, nextra = npts - n;
+    const void* bases = lagrange ? pk.params->gl_w.p : pk.params->g_w_u.p;
+    w.msm_in.ensure((size_t)npts * 32);
+    w.msm_jac.ensure((size_t)n_msm * 96);
+    for (uint32_t j = 0; j < n_msm; ++j) {
+      BZ_CUDA(cudaMemcpyAsync(w.msm_in.p, mainp[j], (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+      BZ_CUDA(cudaMemcpyAsync((char*)w.msm_in.p + (size_t)n * 32, extrap[j], (size_t)nextra * 32, cudaMemcpyDeviceToDevice, st));
+      msm_run(C, pk.params->curve, w.msm_in.p, bases, npts, (char*)w.msm_jac.p + (size_t)j * 96, 0);
+    }
+    jac_to_affine_run(C, pk.params->curve, w.msm_jac.p, w.commits.p, n_msm);
   }
   void read_points(uint32_t n_msm, uint32_t nr, std::vector<std::vector<HostPoint>>& pts) {
     BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.commits.p, (size_t)n_msm * 64, cudaMemcpyDeviceToHost, st));
@@ -1131,17 +1166,12 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       C->kernel_launches += 4;
     }
     // rounds
-    const FixedBase& fb = pk.params->fb_g;
     std::vector<void*> mainp((size_t)B * 2), extrap((size_t)B * 2);
     for (uint32_t b = 0; b < B; ++b) {
       mainp[2 * b] = misc(b, pk.m_scl); mainp[2 * b + 1] = misc(b, pk.m_scr);
       extrap[2 * b] = (DFe*)w.extras.p + (size_t)b * 4; extrap[2 * b + 1] = (DFe*)w.extras.p + (size_t)b * 4 + 2;
     }
-    BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), mainp.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-    BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + (size_t)B * 2, extrap.data(), extrap.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
-    BZ_CUDA(cudaStreamSynchronize(st));
     const uint32_t n_msm = 2 * B;
-    const uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / n_msm)));
     pts.assign(B, std::vector<HostPoint>(2));
     for (uint32_t j = 0; j < k; ++j) {
       const uint32_t half = 1u << (k - j - 1);
@@ -1153,7 +1183,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
                                                         pk.C_Z, (const DFe*)w.rnd.p, pk.R, pk.r_ipa + 2 * j, pk.r_ipa + 2 * j + 1, (DFe*)w.extras.p);
         C->kernel_launches += 2;
       }
-      fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + (size_t)B * 2), n_msm, chunks, w.commits.p);
+      run_msms(false, mainp, extrap, n_msm);
       read_points(n_msm, 2, pts);
       for (uint32_t b = 0; b < B; ++b) {
         t_write_point(ps[b], pts[b][0]);

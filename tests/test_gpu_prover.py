@@ -81,3 +81,20 @@ def test_board_proof_bytes_match_oracle(ctx):
     assert first_diff(proof, exp) is None, first_diff(proof, exp)
     assert job.verify(proof)
     pk.close(); params.close()
+
+
+@pytest.mark.parametrize("force_general", [False, True])
+def test_scaled_board_k13_both_commit_paths(ctx, force_general, monkeypatch):
+    """BASELINE config 5 in small: the Board circuit tiled down a 2^13-row table (3 boards per proof), proved once with
+    the fixed-base window tables and once with the large-n path (bucket MSM over the raw bases, what k >= 15 uses)."""
+    from battlezips_halo2_b200.circuits import board_circuit_scaled
+    if force_general:
+        monkeypatch.setenv("BZ_FORCE_GENERAL_MSM", "1")
+    cs, cfg, asg = board_circuit_scaled(13)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    proof = _prove(job, pk, [3])[0]
+    exp = job.oracle_proof(index=3)
+    assert first_diff(proof, exp) is None, first_diff(proof, exp)
+    assert job.verify(proof)
+    pk.close(); params.close()

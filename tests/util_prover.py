@@ -1,5 +1,6 @@
 """Shared helpers for the prover parity tests: build a job (circuit IR, keys, witness, RNG stream) for both the
 oracle (CPU restatement) and the product (libbzhalo2 via ctypes)."""
+import os
 import numpy as np
 from oracle import halo2 as H, c_oracle as co, pasta
 import battlezips_halo2_b200  # noqa: F401  (registers the package)
@@ -47,7 +48,12 @@ class Job:
     def __init__(self, cs, asg, seed=0xB200B200B200B200):
         self.cs, self.asg, self.k = cs, asg, asg.k
         self.ir = cs.to_ir()
-        self.oparams = H.Params.new(self.k, 0)
+        fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"params_vesta_k{self.k}.npz")
+        if os.path.exists(fixture):          # URS fixtures made by tests/golden/make_params.py (oracle Params::new)
+            d = np.load(fixture)
+            self.oparams = H.Params(self.k, 0, d["g"], d["g_lagrange"], d["w"], d["u"])
+        else:
+            self.oparams = H.Params.new(self.k, 0)
         self.mapping = asg.permutation_mapping()
         self.opk = H.keygen(self.oparams, self.ir, asg.fixed, self.mapping, vk_repr=VK_REPR)
         self.V = H.Vec(0)
