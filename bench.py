@@ -32,6 +32,7 @@ def parse():
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "3")),
                     help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board)")
     ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
+    ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
     return ap.parse_args()
@@ -282,6 +283,11 @@ class ProofWorkload:
     def __init__(self, args, which):
         self.which, self.B, self.T = which, args.batch, max(1, args.inflight)
         self.k = 11 if which == "shot" else 12
+        if which == "board_scaled":          # BASELINE config 5: Board replicated down a 2^k-row table
+            self.k, self.B, self.T, self.DISTINCT = args.k, 1, 1, 1
+        if which == "board_scaled":
+            self.name = f"Board circuit replicated to k={self.k} (many boards per proof), single proof, synthetic URS (BASELINE config 5)"
+            return
         self.name = (f"batched {'Shot' if which == 'shot' else 'Board'} proofs (k={self.k}, IPA/Pasta), {self.T} lanes x {self.B} independent "
                      f"proofs per GPU per step, synthetic witnesses (BASELINE config {'3' if which == 'shot' else '2'})")
 
@@ -289,7 +295,11 @@ class ProofWorkload:
         from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
         from battlezips_halo2_b200.plonk import prover as PR
         make = shot_circuit if self.which == "shot" else board_circuit
-        jobs = [make(rank * 1000 + i) for i in range(self.DISTINCT)]
+        if self.which == "board_scaled":
+            from battlezips_halo2_b200.circuits import board_circuit_scaled
+            jobs = [board_circuit_scaled(self.k, seed=rank)]
+        else:
+            jobs = [make(rank * 1000 + i) for i in range(self.DISTINCT)]
         cs, _, asg0 = jobs[0]
         self.ir = cs.to_ir()
         self.asg0 = asg0
@@ -326,7 +336,11 @@ class ProofWorkload:
         from concurrent.futures import ThreadPoolExecutor
         self.ctx, self.PR = ctx, PR
         adv_d = self._jobs(rank)
-        fx = np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
+        fxp = os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz")
+        if os.path.exists(fxp):
+            fx = np.load(fxp)
+        else:
+            fx = self._synthetic_urs(ctx)
         self.params = PR.Params(ctx, self.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])     # window tables: shared by all lanes
         self.fx = fx
         B, T = self.B, self.T
@@ -359,6 +373,19 @@ class ProofWorkload:
         self.h2d = sum(l["bytes"] for l in self.lanes)
         self.d2h = sum(l["proofs"].nbytes for l in self.lanes)
         self.pool = ThreadPoolExecutor(T)
+
+    def _synthetic_urs(self, ctx):
+        """k > 13: no hash-derived URS fixture (2^k hash-to-curves + an EC-FFT is host-minutes).  Valid, distinct points
+        [i+1]W and [i+1]U computed on the device; g_lagrange is NOT the Lagrange image of g, so these proofs exercise the
+        prover at full cost but are not verifiable -- stated in the JSON line."""
+        from battlezips_halo2_b200 import arithmetic as ar
+        small = np.load(os.path.join(ROOT, "tests", "golden", "params_vesta_k5.npz"))
+        n = 1 << self.k
+        ks = np.zeros((n, 8), dtype=np.uint64); ks[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
+        g = ar.curve_op(ctx, 0, "mul_u32", np.repeat(small["w"][None, :], n, axis=0), ks)
+        gl = ar.curve_op(ctx, 0, "mul_u32", np.repeat(small["u"][None, :], n, axis=0), ks)
+        self.synthetic_urs = True
+        return {"g": g, "g_lagrange": gl, "w": small["g"][0], "u": small["g"][1]}
 
     def _lane_run(self, lane, ptrs):
         import ctypes
@@ -396,6 +423,8 @@ class ProofWorkload:
 
     def check(self):
         """every proof of the last step is accepted by the restated reference verifier (sampled: first, last)"""
+        if getattr(self, "synthetic_urs", False):
+            return None
         from oracle import halo2 as H
         op = H.Params(self.k, 0, self.fx["g"], self.fx["g_lagrange"], self.fx["w"], self.fx["u"])
         opk = H.keygen(op, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), vk_repr=0x1234567890ABCDEF1234567890ABCDEF)
@@ -410,7 +439,7 @@ class ProofWorkload:
         """restated halo2_proofs prover (oracle: Python protocol order over the C rayon-style arithmetic)"""
         from oracle import halo2 as H, c_oracle as co
         if not hasattr(self, "_oracle"):
-            fx = np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
+            fx = self.fx if hasattr(self, "fx") else np.load(os.path.join(ROOT, "tests", "golden", f"params_vesta_k{self.k}.npz"))
             op = H.Params(self.k, 0, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])
             opk = H.keygen(op, self.ir, self.asg0.fixed, self.asg0.permutation_mapping(), vk_repr=0x1234567890ABCDEF1234567890ABCDEF)
             self._oracle = (H, op, opk)
@@ -425,7 +454,8 @@ class ProofWorkload:
                           f"{co.get_threads()} threads)"), co.get_threads(), dt
 
 
-WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload, "shot": lambda a: ProofWorkload(a, "shot"), "board": lambda a: ProofWorkload(a, "board")}
+WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload, "shot": lambda a: ProofWorkload(a, "shot"), "board": lambda a: ProofWorkload(a, "board"),
+             "board_scaled": lambda a: ProofWorkload(a, "board_scaled")}
 
 
 # ------------------------------------------------------------------------------------------------------
