@@ -362,15 +362,16 @@ API int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, cons
     if (!c) {
       const char* e = getenv("BZ_FIXED_WINDOW");
       c = e ? (uint32_t)atoi(e) : 0;
-      if (!c) {   // largest window whose two tables stay under ~24 GB
+      if (!c) {   // largest window whose two tables stay under ~24 GB (k <= 13) / ~80 GB (larger k) and under 2^31 entries
+        const double cap = k <= 13 ? 24e9 : 80e9;
         for (c = 13; c > 4; --c) {
-          double bytes = 2.0 * ((256 + c - 1) / c) * (double)(1u << (c - 1)) * (double)(n + 2) * 64.0;
-          if (bytes <= 24e9) break;
+          double entries = (double)((256 + c - 1) / c) * (double)(1u << (c - 1)) * (double)(n + 2);
+          if (2.0 * entries * 64.0 <= cap && entries < 2147483648.0) break;
         }
       }
     }
     const char* fg = getenv("BZ_FORCE_GENERAL_MSM");
-    p.use_tables = k <= 14 && !(fg && atoi(fg));
+    p.use_tables = k <= 17 && !(fg && atoi(fg));   // k >= 18: tables would need c <= 6 (3x the additions of a bucket MSM)
     if (p.use_tables) {
       fixed_base_build(C, p.fb_g, curve, p.g_w_u.p, (uint32_t)n + 2, c);
       fixed_base_build(C, p.fb_gl, curve, p.gl_w.p, (uint32_t)n + 1, c);

@@ -582,6 +582,9 @@ def main():
     value = units * world / (ms / 1e3)
     e2e_value = units_e * world / (ms_e / 1e3)
     tag, alg_bytes = wl.dominant()
+    if tag not in prof and prof:                     # e.g. k >= 18: commitments go through the bucket MSM
+        tag = max(prof, key=lambda t: prof[t][0])
+        alg_bytes = 0.0
     peak, peak_kind = peaks()
     roof = None
     int_pipe = None
