@@ -9,13 +9,15 @@
 // only HBM traffic is 32 B/scalar + 64 B/point gathers.
 #include "common.h"
 #include "curve.cuh"
+#include <cub/device/device_radix_sort.cuh>
 
 namespace bz {
 
-// ---- 1. signed-digit decomposition + histogram ------------------------------------------------
+// ---- 1. signed-digit decomposition: key = window * nb + (|digit| - 1) (W * nb for a zero digit), value = point
+// index | sign << 31 ---------------------------------------------------------------------------------------------
 template <class SP>
 __global__ void msm_digits_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                                  uint32_t nb, uint32_t* __restrict__ keys, uint32_t* __restrict__ counts) {
+                                  uint32_t nb, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fe<SP> s = fe_from_mont(fe_load(scalars + i));
@@ -29,13 +31,27 @@ __global__ void msm_digits_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n
       if (sh + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh);
       raw &= full - 1;
     }
-    uint32_t v = raw + carry, key = 0;
-    if (v > half) { key = (full - v) | 0x80000000u; carry = 1; }
-    else { key = v; carry = 0; }
-    keys[(size_t)w * n + i] = key;
-    uint32_t b = key & 0x7fffffffu;
-    if (b) atomicAdd(&counts[w * nb + b - 1], 1u);
+    uint32_t v = raw + carry;
+    bool neg = v > half;
+    uint32_t d = neg ? full - v : v;
+    carry = neg ? 1u : 0u;
+    keys[(size_t)w * n + i] = d ? (w * nb + d - 1) : W * nb;    // zero digits: sentinel key = #buckets, sinks to the end
+    vals[(size_t)w * n + i] = i | (neg ? 0x80000000u : 0u);
   }
+}
+
+// bucket boundaries in the sorted key array: offsets[b] = lower_bound(b), counts[b] = lower_bound(b + 1) - offsets[b]
+__global__ void msm_bounds_kernel(const uint32_t* __restrict__ sorted_keys, uint32_t items, uint32_t total_buckets,
+                                  uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= total_buckets) return;
+  uint32_t lo = 0, hi = items;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < b) lo = mid + 1; else hi = mid; }
+  uint32_t start = lo;
+  hi = items;
+  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < b + 1) lo = mid + 1; else hi = mid; }
+  offsets[b] = start;
+  counts[b] = lo - start;
 }
 
 // ---- 2. exclusive scan of bucket counts over all windows (single CTA; W*nb <= 2^21) ------------
@@ -55,19 +71,6 @@ __global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* _
   }
   uint32_t run = part[tid] - sum;
   for (uint32_t j = lo; j < hi; ++j) { offsets[j] = run; cursor[j] = run; run += counts[j]; }
-}
-
-// ---- 3. scatter point indices into bucket order --------------------------------------------------
-__global__ void msm_scatter_kernel(const uint32_t* __restrict__ keys, uint32_t n, uint32_t W, uint32_t nb,
-                                   uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  uint32_t w = blockIdx.y;
-  if (i >= n) return;
-  uint32_t key = keys[(size_t)w * n + i];
-  uint32_t b = key & 0x7fffffffu;
-  if (!b) return;
-  uint32_t pos = atomicAdd(&cursor[w * nb + b - 1], 1u);
-  sorted[pos] = i | (key & 0x80000000u);
 }
 
 // ---- 4. bucket accumulation, skew-proof: every bucket's entry list is cut into segments of <= SEG
@@ -134,15 +137,17 @@ template <class BP> __device__ __forceinline__ void xyzz_store(Xyzz<BP>* p, cons
 }
 
 // ---- 5. per-window reduction  R_w = sum_b (b+1) * bucket[w][b] ------------------------------------
-// CTA per window; thread t owns a contiguous chunk of buckets: running sums give
-// acc_t = sum (b - lo_t + 1) B_b and S_t = sum B_b; contribution = acc_t + lo_t * S_t (lo_t 0-based).
+// grid = (W, S): CTA (w, s) owns buckets [s*nb/S, (s+1)*nb/S) of window w; thread t owns a contiguous chunk:
+// running sums give acc_t = sum (b - lo_t + 1) B_b and S_t = sum B_b; contribution = acc_t + lo_t * S_t.
+// The S partials of a window are summed by the combine step.
 template <class BP>
-__global__ void __launch_bounds__(256) msm_reduce_kernel(const Xyzz<BP>* __restrict__ buckets, uint32_t nb, Xyzz<BP>* __restrict__ window_sums) {
+__global__ void __launch_bounds__(256) msm_reduce_kernel(const Xyzz<BP>* __restrict__ buckets, uint32_t nb, uint32_t splits, Xyzz<BP>* __restrict__ window_partials) {
   extern __shared__ unsigned char smem_raw[];
   Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(smem_raw);
-  uint32_t w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-  uint32_t per = (nb + nt - 1) / nt;
-  uint32_t lo = tid * per, hi = min(lo + per, nb);
+  uint32_t w = blockIdx.x, sidx = blockIdx.y, tid = threadIdx.x, nt = blockDim.x;
+  uint32_t span = nb / splits, base = sidx * span;
+  uint32_t per = (span + nt - 1) / nt;
+  uint32_t lo = base + min(tid * per, span), hi = min(lo + per, base + span);
   Xyzz<BP> run = xyzz_identity<BP>(), acc = xyzz_identity<BP>();
   for (uint32_t b = hi; b > lo; --b) {
     Xyzz<BP> bk = xyzz_load(buckets + (size_t)w * nb + (b - 1));
@@ -156,7 +161,17 @@ __global__ void __launch_bounds__(256) msm_reduce_kernel(const Xyzz<BP>* __restr
     if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
     __syncthreads();
   }
-  if (tid == 0) xyzz_store(window_sums + w, sh[0]);
+  if (tid == 0) xyzz_store(window_partials + (size_t)w * splits + sidx, sh[0]);
+}
+
+// sum the S partials of every window (one thread per window)
+template <class BP>
+__global__ void msm_window_sum_kernel(const Xyzz<BP>* __restrict__ window_partials, uint32_t W, uint32_t splits, Xyzz<BP>* __restrict__ window_sums) {
+  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = 0; j < splits; ++j) acc = xyzz_add(acc, xyzz_load(window_partials + (size_t)w * splits + j));
+  xyzz_store(window_sums + w, acc);
 }
 
 // ---- 6. Horner over windows: R = sum_w 2^(c w) R_w ; writes Jacobian (x,y,z) -----------------------
@@ -200,9 +215,10 @@ static uint32_t pick_window(uint32_t n) {
 template <class BP, class SP>
 static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, uint32_t n, Jac<BP>* out, int c_override) {
   cudaStream_t st = ctx->stream;
+  const bzh::Field& BF = ctx->field(BP::ID);
   if (n == 0) {
     Jac<BP> id{}; memset(&id, 0, sizeof(id));
-    bzh::Fe one = ctx->field(BP::ID).one(); memcpy(id.y.l, one.l, 32);
+    bzh::Fe one = BF.one(); memcpy(id.y.l, one.l, 32);
     BZ_CUDA(cudaMemcpyAsync(out, &id, sizeof(id), cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaStreamSynchronize(st));
     return;
@@ -210,45 +226,71 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   uint32_t c = c_override > 0 ? (uint32_t)c_override : pick_window(n);
   uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1), total = W * nb;
   BZ_CHECK(total <= (1u << 21), "msm: too many buckets");
+  const uint64_t items64 = (uint64_t)W * n;
+  BZ_CHECK(items64 < (1ull << 31), "msm: n * windows too large");
+  const uint32_t items = (uint32_t)items64;
+  uint32_t splits = nb >= 4096 ? nb / 2048 : 1;                  // CTAs per window in the reduction
   // scratch layout
-  size_t keys_b = (size_t)W * n * 4, sorted_b = keys_b, cnt_b = (size_t)total * 4;
-  ctx->scratch[0].ensure(keys_b);
-  ctx->scratch[1].ensure(sorted_b);
-  uint32_t max_segs = (uint32_t)(((uint64_t)W * n) / SEG + total);
-  ctx->scratch[2].ensure(cnt_b * 5 + (size_t)max_segs * 4);
-  ctx->scratch[3].ensure((size_t)(total + W + max_segs) * sizeof(Xyzz<BP>));
+  size_t temp_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)items, 0, 32, st);
+  uint32_t max_segs = (uint32_t)(items64 / SEG + total);
+  ctx->scratch[0].ensure((size_t)items * 4 * 2);                  // keys, vals
+  ctx->scratch[1].ensure((size_t)items * 4 * 2 + temp_bytes + 256);   // sorted keys, sorted vals, cub temp
+  ctx->scratch[2].ensure((size_t)total * 4 * 4 + (size_t)max_segs * 4);
+  ctx->scratch[3].ensure((size_t)(total + W * splits + W + max_segs) * sizeof(Xyzz<BP>));
   uint32_t* keys = ctx->scratch[0].as<uint32_t>();
-  uint32_t* sorted = ctx->scratch[1].as<uint32_t>();
+  uint32_t* vals = keys + items;
+  uint32_t* skeys = ctx->scratch[1].as<uint32_t>();
+  uint32_t* sorted = skeys + items;
+  void* cub_temp = (void*)(((uintptr_t)(sorted + items) + 255) & ~(uintptr_t)255);
   uint32_t* counts = ctx->scratch[2].as<uint32_t>();
   uint32_t* offsets = counts + total;
-  uint32_t* cursor = offsets + total;
-  uint32_t* nseg = cursor + total;
+  uint32_t* nseg = offsets + total;
   uint32_t* segoff = nseg + total;
   uint32_t* seg_bucket = segoff + total;
   Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
-  Xyzz<BP>* wsums = buckets + total;
+  Xyzz<BP>* wparts = buckets + total;
+  Xyzz<BP>* wsums = wparts + (size_t)W * splits;
   Xyzz<BP>* partial = wsums + W;
 
-  BZ_CUDA(cudaMemsetAsync(counts, 0, cnt_b, st));
   { ProfScope p(ctx, PROF_MSM_DIGITS);
-    msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, counts); }
+    msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, vals); }
   { ProfScope p(ctx, PROF_MSM_SORT);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
-    msm_scatter_kernel<<<dim3((n + 255) / 256, W), 256, 0, st>>>(keys, n, W, nb, cursor, sorted); }
-  { ProfScope p(ctx, PROF_MSM_SORT);
+    // radix sort of (bucket key, point) pairs over just the bits a key can have
+    int end_bit = 1; while ((1u << end_bit) <= total) ++end_bit;
+    cub::DeviceRadixSort::SortPairs(cub_temp, temp_bytes, (const uint32_t*)keys, skeys, (const uint32_t*)vals, sorted, (int)items, 0, end_bit, st);
+    msm_bounds_kernel<<<(total + 255) / 256, 256, 0, st>>>(skeys, items, total, offsets, counts);
     msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*unused cursor copy, overwritten below*/, total);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*scratch copy, overwritten below*/, total);
     msm_segmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket); }
   { ProfScope p(ctx, PROF_MSM_BUCKET);
     msm_segment_kernel<BP><<<(max_segs + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, nseg, segoff, seg_bucket, total, max_segs, partial);
     msm_bucket_fold_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(partial, nseg, segoff, total, buckets); }
-  uint32_t rthreads = nb >= 256 ? 256 : (nb >= 32 ? nb : 32);
+  uint32_t span = nb / splits;
+  uint32_t rthreads = span >= 256 ? 256 : (span >= 32 ? span : 32);
   { ProfScope p(ctx, PROF_MSM_REDUCE);
-    msm_reduce_kernel<BP><<<W, rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, wsums); }
-  { ProfScope p(ctx, PROF_MSM_COMBINE);
-    msm_combine_kernel<BP><<<1, 32, 0, st>>>(wsums, W, c, out); }
-  ctx->kernel_launches += 10;
+    msm_reduce_kernel<BP><<<dim3(W, splits), rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, splits, wparts);
+    msm_window_sum_kernel<BP><<<(W + 31) / 32, 32, 0, st>>>(wparts, W, splits, wsums); }
+  ctx->kernel_launches += 12;
   BZ_CUDA(cudaGetLastError());
+  // ---- Horner over the W window sums on the host: 255 sequential doublings cost ~1.1 ms on one GPU thread and
+  // ~0.1 ms on a CPU core; the data is W * 128 B.
+  {
+    ProfScope p(ctx, PROF_MSM_COMBINE);
+    std::vector<bzh::HXyzz> hw(W);
+    BZ_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)W * sizeof(bzh::HXyzz), cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    bzh::HXyzz acc = bzh::hx_identity();
+    for (int w = (int)W - 1; w >= 0; --w) {
+      for (uint32_t j = 0; j < c; ++j) acc = bzh::hx_dbl(BF, acc);
+      acc = bzh::hx_add(BF, acc, hw[w]);
+    }
+    bzh::Fe jac[3];
+    bzh::hx_to_jac(BF, acc, jac);
+    BZ_CUDA(cudaMemcpyAsync(out, jac, 96, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  }
 }
 
 // curve: 0 = Vesta (scalars Fp, coordinates Fq), 1 = Pallas (scalars Fq, coordinates Fp).  All pointers device.
