@@ -79,9 +79,14 @@ __global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* _
 // segment partials.
 constexpr uint32_t SEG = 32;
 
-__global__ void msm_segcount_kernel(const uint32_t* __restrict__ counts, uint32_t total_buckets, uint32_t* __restrict__ nseg) {
+constexpr uint32_t FOLD_SERIAL_MAX = 32;     // buckets with more segment partials than this are folded by a whole CTA
+__global__ void msm_segcount_kernel(const uint32_t* __restrict__ counts, uint32_t total_buckets, uint32_t* __restrict__ nseg,
+                                    uint32_t* __restrict__ large_count, uint32_t* __restrict__ large_list, uint32_t max_large) {
   uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
-  if (gb < total_buckets) nseg[gb] = (counts[gb] + SEG - 1) / SEG;
+  if (gb >= total_buckets) return;
+  uint32_t m = (counts[gb] + SEG - 1) / SEG;
+  nseg[gb] = m;
+  if (m > FOLD_SERIAL_MAX) { uint32_t idx = atomicAdd(large_count, 1u); if (idx < max_large) large_list[idx] = gb; }
 }
 __global__ void msm_segmap_kernel(const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff, uint32_t total_buckets,
                                   uint32_t* __restrict__ seg_bucket) {
@@ -119,6 +124,7 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const Xyzz<BP>* __
   uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb >= total_buckets) return;
   uint32_t o = segoff[gb], m = nseg[gb];
+  if (m > FOLD_SERIAL_MAX) return;            // handled by msm_bucket_fold_large_kernel
   Xyzz<BP> acc = xyzz_identity<BP>();
   for (uint32_t j = 0; j < m; ++j) {
     const Xyzz<BP>* q = partial + o + j;
@@ -127,6 +133,36 @@ __global__ void __launch_bounds__(128) msm_bucket_fold_kernel(const Xyzz<BP>* __
   }
   Xyzz<BP>* ob = buckets + gb;
   fe_store(&ob->x, acc.x); fe_store(&ob->y, acc.y); fe_store(&ob->zz, acc.zz); fe_store(&ob->zzz, acc.zzz);
+}
+
+// One CTA per oversized bucket (skewed scalars, few-bit top window): strided accumulation of its segment partials,
+// then a shared-memory tree.
+template <class BP>
+__global__ void __launch_bounds__(256) msm_bucket_fold_large_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ nseg,
+                                  const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ large_count,
+                                  const uint32_t* __restrict__ large_list, uint32_t max_large, Xyzz<BP>* __restrict__ buckets) {
+  __shared__ Xyzz<BP> sh[256];
+  uint32_t nl = min(*large_count, max_large);
+  for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
+    uint32_t gb = large_list[li], o = segoff[gb], m = nseg[gb];
+    Xyzz<BP> acc = xyzz_identity<BP>();
+    for (uint32_t j = threadIdx.x; j < m; j += 256) {
+      const Xyzz<BP>* q = partial + o + j;
+      Xyzz<BP> v; v.x = fe_load(&q->x); v.y = fe_load(&q->y); v.zz = fe_load(&q->zz); v.zzz = fe_load(&q->zzz);
+      acc = xyzz_add(acc, v);
+    }
+    sh[threadIdx.x] = acc;
+    __syncthreads();
+    for (uint32_t d = 128; d > 0; d >>= 1) {
+      if (threadIdx.x < d) sh[threadIdx.x] = xyzz_add(sh[threadIdx.x], sh[threadIdx.x + d]);
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+      Xyzz<BP>* ob = buckets + gb;
+      fe_store(&ob->x, sh[0].x); fe_store(&ob->y, sh[0].y); fe_store(&ob->zz, sh[0].zz); fe_store(&ob->zzz, sh[0].zzz);
+    }
+    __syncthreads();
+  }
 }
 
 template <class BP> __device__ __forceinline__ Xyzz<BP> xyzz_load(const Xyzz<BP>* p) {
@@ -206,9 +242,13 @@ __global__ void jac_to_affine_kernel(const Jac<BP>* __restrict__ in, Affine<BP>*
 static uint32_t pick_window(uint32_t n) {
   uint32_t lg = 0;
   while ((1ull << (lg + 1)) <= n) ++lg;
-  int c = (int)lg - 2;          // ~n/4 points per... tuned on B200 later (profiles/)
+  int c = (int)lg - 2;
   if (c < 4) c = 4;
   if (c > 16) c = 16;
+  // avoid windows whose top digit has only a few significant bits of the 255-bit scalar (all points would pile into
+  // a handful of buckets): require the last window to hold >= c/2 real bits or none
+  auto top_bits = [](int cc) { int W = (256 + cc - 1) / cc; return 255 - (W - 1) * cc; };
+  while (c > 4) { int tb = top_bits(c); if (tb <= 0 || tb >= c / 2) break; --c; }
   return (uint32_t)c;
 }
 
@@ -237,7 +277,8 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   uint32_t max_segs = (uint32_t)(items64 / SEG + total);
   ctx->scratch[0].ensure((size_t)items * 4 * 2);                  // keys, vals
   ctx->scratch[1].ensure((size_t)items * 4 * 2 + temp_bytes + 256);   // sorted keys, sorted vals, cub temp
-  ctx->scratch[2].ensure((size_t)total * 4 * 4 + (size_t)max_segs * 4);
+  const uint32_t max_large = (uint32_t)(items64 / (SEG * FOLD_SERIAL_MAX) + 1);
+  ctx->scratch[2].ensure((size_t)total * 4 * 4 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4);
   ctx->scratch[3].ensure((size_t)(total + W * splits + W + max_segs) * sizeof(Xyzz<BP>));
   uint32_t* keys = ctx->scratch[0].as<uint32_t>();
   uint32_t* vals = keys + items;
@@ -249,6 +290,8 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   uint32_t* nseg = offsets + total;
   uint32_t* segoff = nseg + total;
   uint32_t* seg_bucket = segoff + total;
+  uint32_t* large_count = seg_bucket + max_segs;
+  uint32_t* large_list = large_count + 4;
   Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
   Xyzz<BP>* wparts = buckets + total;
   Xyzz<BP>* wsums = wparts + (size_t)W * splits;
@@ -261,12 +304,14 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
     int end_bit = 1; while ((1u << end_bit) <= total) ++end_bit;
     cub::DeviceRadixSort::SortPairs(cub_temp, temp_bytes, (const uint32_t*)keys, skeys, (const uint32_t*)vals, sorted, (int)items, 0, end_bit, st);
     msm_bounds_kernel<<<(total + 255) / 256, 256, 0, st>>>(skeys, items, total, offsets, counts);
-    msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg);
+    BZ_CUDA(cudaMemsetAsync(large_count, 0, 16, st));
+    msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg, large_count, large_list, max_large);
     msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*scratch copy, overwritten below*/, total);
     msm_segmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket); }
   { ProfScope p(ctx, PROF_MSM_BUCKET);
     msm_segment_kernel<BP><<<(max_segs + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, nseg, segoff, seg_bucket, total, max_segs, partial);
-    msm_bucket_fold_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(partial, nseg, segoff, total, buckets); }
+    msm_bucket_fold_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(partial, nseg, segoff, total, buckets);
+    msm_bucket_fold_large_kernel<BP><<<std::min<uint32_t>(max_large, 4 * 148), 256, 0, st>>>(partial, nseg, segoff, large_count, large_list, max_large, buckets); }
   uint32_t span = nb / splits;
   uint32_t rthreads = span >= 256 ? 256 : (span >= 32 ? span : 32);
   { ProfScope p(ctx, PROF_MSM_REDUCE);

@@ -176,3 +176,23 @@ def test_large_ntt_roundtrip_property(ctx, oracle_c):
     back = d_b.download((n, 4))
     assert np.array_equal(back, a)
     d_a.free(); d_b.free()
+
+
+def test_best_multiexp_large_skewed(ctx, oracle_c):
+    """2^15 points with witness-like scalars (70% zero, 20% one, ...): one bucket holds ~20% of all points, which the
+    bucket kernel must spread over many threads (segments + CTA-wide fold), and the result must still be bit-exact."""
+    co = oracle_c
+    curve, n = 1, 1 << 15
+    C, sf, bf = co.CURVES[curve]
+    rnd = random.Random(77)
+    base = co.points_to_mont(curve, _bases(co, curve, 512))
+    bm = np.tile(base, (n // 512, 1))
+    r = C.scalar.p
+    sc = []
+    for _ in range(n):
+        u = rnd.random()
+        sc.append(0 if u < 0.7 else 1 if u < 0.9 else rnd.randrange(2, 1 << 10) if u < 0.95 else rnd.randrange(r))
+    sm = co.to_mont(sf, sc)
+    got = ar.best_multiexp(ctx, curve, sm, bm)
+    exp = co.best_multiexp(curve, sm, bm)
+    assert np.array_equal(co.to_affine(curve, got), co.to_affine(curve, exp))
