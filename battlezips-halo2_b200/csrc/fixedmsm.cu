@@ -102,153 +102,151 @@ void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev,
   if (curve == 0) fb_build_t<FqP>(ctx, fb, bases_dev); else fb_build_t<FpP>(ctx, fb, bases_dev);
 }
 
-// ---- the commitment kernel -----------------------------------------------------------------------
-// grid = (chunks, n_msm), block = FB_THREADS.  MSM m sums over points [0, npts): scalars of points
-// i < n_main come from main[m] (a polynomial, Montgomery form), the trailing npts - n_main points
-// (w, u: blinds / IPA cross terms) from extra[m] (may be null = zero).
+// ---- the commitment pipeline ------------------------------------------------------------------------
+// MSM m sums over points [0, npts): scalars of points i < n_main come from main[m] (a polynomial, Montgomery form),
+// the trailing npts - n_main points (w, u: blinds / IPA cross terms) from extra[m] (may be null = zero).
 //
-// Work compaction: witness columns are mostly 0 / 1, so "one thread = one point" leaves 2/3 of every warp idle
-// (ncu r1: 11-13 active threads per warp-instruction).  Each round the CTA decodes FB_THREADS scalars into
-// signed digits, packs the non-zero ones as table indices into a shared-memory work list (block-wide exclusive
-// scan of the per-thread counts, no atomics, deterministic order) and then ALL threads pull entries from the
-// list round-robin: every warp runs full until the list is drained.
+//   1. fb_decode_kernel   one thread per (msm, point): signed digits -> packed table indices, appended to the MSM's
+//                         entry list (warp-aggregated atomic reservation; zero digits vanish here, so witness columns
+//                         -- mostly 0/1 -- cost only what they contain)
+//   2. fb_accumulate_kernel   one thread per 32 consecutive list entries: gather + mixed additions, no shared memory,
+//                         no barriers, every warp full (r1 ncu: the one-thread-per-point kernel ran 11-13 of 32 lanes)
+//   3. fb_fold_kernel     one CTA per MSM: strided sum of its segment partials, shared-memory tree, affine output
 constexpr int FB_THREADS = 128;
-constexpr int FB_MAX_W = 64;       // windows per scalar (c >= 4)
+constexpr uint32_t FB_SEG = 32;
+constexpr int FB_FOLD_THREADS = 128;
 
-template <class BP, class SP, int MINB>
-__global__ void __launch_bounds__(FB_THREADS, MINB) fixed_msm_kernel(const Affine<BP>* __restrict__ table, uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
+template <class SP>
+__global__ void __launch_bounds__(FB_THREADS) fb_decode_kernel(uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
                                  const Fe<SP>* const* __restrict__ main, uint32_t n_main, const Fe<SP>* const* __restrict__ extra,
-                                 Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
-  extern __shared__ uint32_t fb_smem[];
-  uint32_t* list = fb_smem;                                  // FB_THREADS * W entries
-  __shared__ uint32_t warp_cnt[FB_THREADS / 32];
-  uint32_t my_adds = 0;
-  const uint32_t m = blockIdx.y, chunks = gridDim.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const Fe<SP>* sm = main[m];
-  const Fe<SP>* se = extra ? extra[m] : nullptr;
-  Xyzz<BP> acc = xyzz_identity<BP>();
+                                 uint32_t* __restrict__ lists, uint32_t list_stride, uint32_t* __restrict__ list_count) {
+  const uint32_t m = blockIdx.y, i = blockIdx.x * FB_THREADS + threadIdx.x, lane = threadIdx.x & 31;
   const uint32_t half = 1u << (c - 1), full = 1u << c;
-  // this CTA's contiguous point range
-  const uint32_t per = (npts + chunks - 1) / chunks;
-  const uint32_t p_lo = blockIdx.x * per, p_hi = min(p_lo + per, npts);
-  for (uint32_t base = p_lo; base < p_hi; base += FB_THREADS) {
-    const uint32_t i = base + tid;
-    // ---- decode this thread's scalar into packed entries (kept in registers as a bitmap + digits recomputed) ----
-    Fe<SP> s = fe_zero<SP>();
-    bool have = false;
-    if (i < p_hi) {
-      if (i < n_main) { s = fe_load(sm + i); have = true; }
-      else if (se) { s = fe_load(se + (i - n_main)); have = true; }
-    }
-    uint32_t cnt = 0;
-    if (have && !fe_is_zero(s)) {
-      s = fe_from_mont(s);
-      uint32_t carry = 0;
-      for (uint32_t w = 0; w < W; ++w) {
-        uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
-        uint32_t raw = 0;
-        if (limb < 8) {
-          raw = s.l[limb] >> sh_;
-          if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
-          raw &= full - 1;
-        }
-        uint32_t v = raw + carry;
-        carry = v > half ? 1u : 0u;
-        cnt += (v != 0 && v != full) ? 1u : 0u;      // v == full cannot happen (raw <= full-1, carry makes v<=full; v==full -> d=0)
+  Fe<SP> s = fe_zero<SP>();
+  bool have = false;
+  if (i < npts) {
+    const Fe<SP>* se = extra ? extra[m] : nullptr;
+    if (i < n_main) { s = fe_load(main[m] + i); have = true; }
+    else if (se) { s = fe_load(se + (i - n_main)); have = true; }
+  }
+  uint32_t cnt = 0;
+  if (have && !fe_is_zero(s)) {
+    s = fe_from_mont(s);
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < W; ++w) {
+      uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
+      uint32_t raw = 0;
+      if (limb < 8) {
+        raw = s.l[limb] >> sh_;
+        if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
+        raw &= full - 1;
       }
-    } else have = false;
-    // ---- block-wide exclusive scan of cnt ----
-    uint32_t incl = cnt;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
-    if (lane == 31) warp_cnt[wid] = incl;
-    __syncthreads();
-    uint32_t off = incl - cnt, total = 0;
-#pragma unroll
-    for (int w2 = 0; w2 < FB_THREADS / 32; ++w2) { uint32_t t = warp_cnt[w2]; if (w2 < (int)wid) off += t; total += t; }
-    // ---- write entries ----
-    if (have) {
-      uint32_t carry = 0;
-      for (uint32_t w = 0; w < W; ++w) {
-        uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
-        uint32_t raw = 0;
-        if (limb < 8) {
-          raw = s.l[limb] >> sh_;
-          if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
-          raw &= full - 1;
-        }
-        uint32_t v = raw + carry;
-        bool neg = v > half;
-        uint32_t d = neg ? full - v : v;
-        carry = neg ? 1u : 0u;
-        if (d) list[off++] = (uint32_t)(((size_t)w * nbk + (d - 1)) * npts + i) | (neg ? 0x80000000u : 0u);
-      }
+      uint32_t v = raw + carry;
+      carry = v > half ? 1u : 0u;
+      cnt += (v != 0 && v != full) ? 1u : 0u;
     }
-    __syncthreads();
-    // ---- drain the list: all threads busy ----
-    for (uint32_t e = tid; e < total; e += FB_THREADS) {
-      uint32_t ent = list[e];
+  } else have = false;
+  // warp-aggregated reservation in this MSM's list
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+  uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31), base = 0;
+  if (lane == 31 && warp_total) base = atomicAdd(&list_count[m], warp_total);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  if (!have) return;
+  uint32_t* list = lists + (size_t)m * list_stride;
+  uint32_t off = base + incl - cnt, carry = 0;
+  for (uint32_t w = 0; w < W; ++w) {
+    uint32_t bit = w * c, limb = bit >> 5, sh_ = bit & 31;
+    uint32_t raw = 0;
+    if (limb < 8) {
+      raw = s.l[limb] >> sh_;
+      if (sh_ + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh_);
+      raw &= full - 1;
+    }
+    uint32_t v = raw + carry;
+    bool neg = v > half;
+    uint32_t d = neg ? full - v : v;
+    carry = neg ? 1u : 0u;
+    if (d) list[off++] = (uint32_t)(((size_t)w * nbk + (d - 1)) * npts + i) | (neg ? 0x80000000u : 0u);
+  }
+}
+
+template <class BP>
+__global__ void __launch_bounds__(FB_THREADS) fb_accumulate_kernel(const Affine<BP>* __restrict__ table, const uint32_t* __restrict__ lists,
+                                 uint32_t list_stride, const uint32_t* __restrict__ list_count, uint32_t segs_per_msm,
+                                 Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
+  const uint32_t m = blockIdx.y, sidx = blockIdx.x * FB_THREADS + threadIdx.x;
+  const uint32_t cnt = list_count[m];
+  uint32_t my_adds = 0;
+  if (sidx < segs_per_msm && sidx * FB_SEG < cnt) {
+    const uint32_t* list = lists + (size_t)m * list_stride + sidx * FB_SEG;
+    const uint32_t k = min(FB_SEG, cnt - sidx * FB_SEG);
+    Xyzz<BP> acc = xyzz_identity<BP>();
+    for (uint32_t j = 0; j < k; ++j) {
+      uint32_t ent = list[j];
       Affine<BP> pt = aff_load(table + (ent & 0x7fffffffu));
       xyzz_add_mixed_signed(acc, pt, (ent >> 31) != 0);
-      ++my_adds;
     }
-    __syncthreads();
+    my_adds = k;
+    Xyzz<BP>* o = partial + (size_t)m * segs_per_msm + sidx;
+    fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
   }
   if (add_counter) {       // profiling only: exact number of mixed additions this launch performed
     uint32_t tot = __reduce_add_sync(0xffffffffu, my_adds);
-    if (lane == 0 && tot) atomicAdd(add_counter, (unsigned long long)tot);
+    if ((threadIdx.x & 31) == 0 && tot) atomicAdd(add_counter, (unsigned long long)tot);
   }
-  // ---- CTA tree reduction (the list buffer is reused as XYZZ scratch: FB_THREADS * 128 B) ----
-  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(fb_smem);
+}
+
+// fold the segment partials of each MSM and normalise: one CTA per MSM -> affine (64 B), identity = zeros
+template <class BP>
+__global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
+                                 uint32_t segs_per_msm, Affine<BP>* __restrict__ out) {
+  __shared__ Xyzz<BP> sh[FB_FOLD_THREADS];
+  const uint32_t m = blockIdx.x, tid = threadIdx.x;
+  const uint32_t nseg = (list_count[m] + FB_SEG - 1) / FB_SEG;
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = tid; j < nseg; j += FB_FOLD_THREADS) {
+    const Xyzz<BP>* q = partial + (size_t)m * segs_per_msm + j;
+    Xyzz<BP> v; v.x = fe_load(&q->x); v.y = fe_load(&q->y); v.zz = fe_load(&q->zz); v.zzz = fe_load(&q->zzz);
+    acc = xyzz_add(acc, v);
+  }
   sh[tid] = acc;
   __syncthreads();
-  for (uint32_t d = FB_THREADS >> 1; d > 0; d >>= 1) {
+  for (uint32_t d = FB_FOLD_THREADS >> 1; d > 0; d >>= 1) {
     if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
     __syncthreads();
   }
   if (tid == 0) {
-    Xyzz<BP>* o = partial + (size_t)m * chunks + blockIdx.x;
-    fe_store(&o->x, sh[0].x); fe_store(&o->y, sh[0].y); fe_store(&o->zz, sh[0].zz); fe_store(&o->zzz, sh[0].zzz);
+    Affine<BP> r = xyzz_to_affine(sh[0]);
+    fe_store(&out[m].x, r.x); fe_store(&out[m].y, r.y);
   }
-}
-
-// fold the chunk partials of each MSM and normalise: one thread per MSM -> affine (64 B), identity = zeros
-template <class BP>
-__global__ void fixed_msm_finish_kernel(const Xyzz<BP>* __restrict__ partial, uint32_t chunks, uint32_t n_msm, Affine<BP>* __restrict__ out) {
-  uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_msm) return;
-  Xyzz<BP> acc = xyzz_identity<BP>();
-  for (uint32_t j = 0; j < chunks; ++j) {
-    const Xyzz<BP>* q = partial + (size_t)m * chunks + j;
-    Xyzz<BP> v; v.x = fe_load(&q->x); v.y = fe_load(&q->y); v.zz = fe_load(&q->zz); v.zzz = fe_load(&q->zzz);
-    acc = xyzz_add(acc, v);
-  }
-  Affine<BP> r = xyzz_to_affine(acc);
-  fe_store(&out[m].x, r.x); fe_store(&out[m].y, r.y);
 }
 
 template <class BP, class SP>
 static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_main, uint32_t n_main, const void* const* d_extra,
-                            uint32_t n_msm, uint32_t chunks, void* d_out_affine) {
+                            uint32_t n_msm, uint32_t /*chunks*/, void* d_out_affine) {
   cudaStream_t st = ctx->stream;
   if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
-  ctx->scratch[3].ensure((size_t)n_msm * chunks * sizeof(Xyzz<BP>));
+  const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
+  const uint32_t segs = (list_stride + FB_SEG - 1) / FB_SEG;
+  ctx->scratch[0].ensure((size_t)n_msm * list_stride * 4);
+  ctx->scratch[1].ensure((size_t)n_msm * 4 + 64);
+  ctx->scratch[3].ensure((size_t)n_msm * segs * sizeof(Xyzz<BP>));
+  uint32_t* lists = ctx->scratch[0].as<uint32_t>();
+  uint32_t* counts = ctx->scratch[1].as<uint32_t>();
   Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
+  BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_msm * 4, st));
+  unsigned long long* cnt = ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr;
   {
     ProfScope p(ctx, PROF_FIXED_MSM);
-    const size_t smem = std::max<size_t>((size_t)FB_THREADS * fb.W * 4, (size_t)FB_THREADS * sizeof(Xyzz<BP>));
-    static int occ = -1;
-    if (occ < 0) { const char* e = getenv("BZ_MSM_OCC"); occ = e ? atoi(e) : 4; }   // measured on B200 (profiles/README.md): 4 CTAs/SM is fastest; IMAD.WIDE chains saturate the fma-heavy pipe
-    unsigned long long* cnt = ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr;
-#define BZ_FB_LAUNCH(MINB)                                                                                       \
-    fixed_msm_kernel<BP, SP, MINB><<<dim3(chunks, n_msm), FB_THREADS, smem, st>>>(                                 \
-        fb.table.as<Affine<BP>>(), fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main,             \
-        (const Fe<SP>* const*)d_extra, partial, cnt)
-    if (occ >= 8) BZ_FB_LAUNCH(8); else if (occ >= 6) BZ_FB_LAUNCH(6); else if (occ == 5) BZ_FB_LAUNCH(5); else BZ_FB_LAUNCH(4);
-#undef BZ_FB_LAUNCH
+    fb_decode_kernel<SP><<<dim3((fb.npts + FB_THREADS - 1) / FB_THREADS, n_msm), FB_THREADS, 0, st>>>(
+        fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main, (const Fe<SP>* const*)d_extra, lists, list_stride, counts);
+    fb_accumulate_kernel<BP><<<dim3((segs + FB_THREADS - 1) / FB_THREADS, n_msm), FB_THREADS, 0, st>>>(
+        fb.table.as<Affine<BP>>(), lists, list_stride, counts, segs, partial, cnt);
   }
-  fixed_msm_finish_kernel<BP><<<(n_msm + 31) / 32, 32, 0, st>>>(partial, chunks, n_msm, (Affine<BP>*)d_out_affine);
-  ctx->kernel_launches += 2;
+  fb_fold_kernel<BP><<<n_msm, FB_FOLD_THREADS, 0, st>>>(partial, counts, segs, (Affine<BP>*)d_out_affine);
+  ctx->kernel_launches += 3;
   BZ_CUDA(cudaGetLastError());
 }
 
