@@ -249,8 +249,8 @@ __attribute__((visibility("default"))) int bz_best_multiexp(bz_ctx* ctx, int cur
   BZ_TRY(ctx, {
     BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
     BZ_CHECK(n < (1ull << 31), "msm: n too large");
-    bz::DevBuf ds, db, dout;
-    ds.alloc(n * 32 + 32); db.alloc(n * 64 + 64); dout.alloc(96);
+    bz::DevBuf &ds = ctx->c.stage[0], &db = ctx->c.stage[1], &dout = ctx->c.stage[2];
+    ds.ensure(n * 32 + 32); db.ensure(n * 64 + 64); dout.ensure(96);
     cudaStream_t st = ctx->c.stream;
     BZ_CUDA(cudaMemcpyAsync(ds.p, coeffs, n * 32, cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaMemcpyAsync(db.p, bases, n * 64, cudaMemcpyHostToDevice, st));
@@ -301,8 +301,8 @@ __attribute__((visibility("default"))) int bz_extended_to_coeff_dev(bz_ctx* ctx,
 static int host_ntt(bz_ctx* ctx, int field, const void* in, size_t n_in, void* out, size_t n_out, int logN, bool inverse, const bz::NttFusion& fu) {
   BZ_TRY(ctx, {
     BZ_CHECK(field == 0 || field == 1, "bad field id");
-    bz::DevBuf din, dout;
-    din.alloc(n_in * 32); dout.alloc(n_out * 32);
+    bz::DevBuf &din = ctx->c.stage[0], &dout = ctx->c.stage[1];
+    din.ensure(n_in * 32); dout.ensure(n_out * 32);
     cudaStream_t st = ctx->c.stream;
     BZ_CUDA(cudaMemcpyAsync(din.p, in, n_in * 32, cudaMemcpyHostToDevice, st));
     bz::ntt_run(&ctx->c, field, din.p, dout.p, logN, inverse, 1, fu);

@@ -102,6 +102,152 @@ __global__ void copy_rows_kernel(Regions reg, uint64_t len, const CopyDesc* __re
   for (uint32_t j = threadIdx.x; j < d.count; j += blockDim.x) fe_store(dst + j, fe_load(s + j));
 }
 
+// ---- lookup permutation (U: halo2_proofs 0.2.0 src/plonk/lookup/prover.rs::permute_expression_pair) -------------
+// One CTA per (lookup, proof).  The reference sorts the compressed input expression over the usable rows (Ord = the
+// canonical integer), keeps a BTreeMap multiset of the table expression, writes the table value next to the FIRST row of
+// every run of equal inputs and fills the remaining ("repeated") rows, last row first, with the left-over table values
+// in ascending order.  Here: two shared-memory bitonic sorts of 256-bit canonical keys, one binary search per distinct
+// input value, two block scans and a gather -- results are the same canonical values, hence bit-identical columns.
+struct LookupPermDesc { PolyRef cin, ctab, aout, sout; };
+constexpr int LKP_THREADS = 1024;
+constexpr uint32_t LKP_MAX_N = 4096;         // 44 B of shared memory per row
+inline size_t lookup_permute_smem(uint32_t n) { return (size_t)n * 32 + (size_t)3 * n * 4; }
+
+__device__ __forceinline__ bool key_less(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  sub_cc(a0.x, b0.x); subc_cc(a0.y, b0.y); subc_cc(a0.z, b0.z); subc_cc(a0.w, b0.w);
+  subc_cc(a1.x, b1.x); subc_cc(a1.y, b1.y); subc_cc(a1.z, b1.z); subc_cc(a1.w, b1.w);
+  return subc(0u, 0u) != 0u;             // borrow out  <=>  a < b
+}
+__device__ __forceinline__ bool key_eq(const uint4& a0, const uint4& a1, const uint4& b0, const uint4& b1) {
+  return ((a0.x ^ b0.x) | (a0.y ^ b0.y) | (a0.z ^ b0.z) | (a0.w ^ b0.w) | (a1.x ^ b1.x) | (a1.y ^ b1.y) | (a1.z ^ b1.z) | (a1.w ^ b1.w)) == 0u;
+}
+// ascending bitonic sort of npad (power of two) keys in shared memory, K[2i], K[2i+1] = low / high half of key i
+__device__ __forceinline__ void bitonic_sort_keys(uint4* K, uint32_t npad) {
+  for (uint32_t k = 2; k <= npad; k <<= 1)
+    for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+      for (uint32_t t = threadIdx.x; t < (npad >> 1); t += blockDim.x) {
+        const uint32_t i = ((t & ~(j - 1)) << 1) | (t & (j - 1)), p = i | j;
+        const uint4 a0 = K[2 * i], a1 = K[2 * i + 1], b0 = K[2 * p], b1 = K[2 * p + 1];
+        const bool up = (i & k) == 0;
+        const bool sw = up ? key_less(b0, b1, a0, a1) : key_less(a0, a1, b0, b1);
+        if (sw) { K[2 * i] = b0; K[2 * i + 1] = b1; K[2 * p] = a0; K[2 * p + 1] = a1; }
+      }
+      __syncthreads();
+    }
+}
+// in-place exclusive prefix sum of arr[0..len) by the whole CTA; returns the total.  wsum: 33 words of shared memory
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t* arr, uint32_t len, uint32_t* wsum) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const uint32_t per = (len + blockDim.x - 1) / blockDim.x, lo = min(tid * per, len), hi = min(lo + per, len);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; ++i) s += arr[i];
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t v = lane < nw ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, iv, d); if (lane >= (uint32_t)d) iv += o; }
+    if (lane < nw) wsum[lane] = iv - v;
+    if (lane == 31) wsum[32] = iv;
+  }
+  __syncthreads();
+  uint32_t run = wsum[wid] + incl - s;
+  for (uint32_t i = lo; i < hi; ++i) { uint32_t v = arr[i]; arr[i] = run; run += v; }
+  const uint32_t total = wsum[32];
+  __syncthreads();
+  return total;
+}
+
+template <class P>
+__global__ void __launch_bounds__(LKP_THREADS) lookup_permute_kernel(Regions reg, uint32_t n, uint32_t usable, const LookupPermDesc* __restrict__ descs,
+                                      Fe<P>* __restrict__ tsorted /* [proof][lookup][n] canonical */, uint32_t* __restrict__ err) {
+  extern __shared__ uint4 lkp_smem[];
+  __shared__ uint32_t wsum[33];
+  uint4* K = lkp_smem;
+  uint32_t* removed = reinterpret_cast<uint32_t*>(lkp_smem + 2 * (size_t)n);     // -> rank among the left-over table rows
+  uint32_t* repeat = removed + n;                                                // -> rank among the repeated input rows
+  uint32_t* left = repeat + n;                                                   // left-over table rows, ascending
+  const uint32_t l = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+  const LookupPermDesc d = descs[l];
+  Fe<P>* T = tsorted + ((uint64_t)b * gridDim.x + l) * n;
+  const uint4 ff = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+  auto load_keys = [&](PolyRef src) {
+    const Fe<P>* s = region_ptr<P>(reg, src, b, n);
+    for (uint32_t i = tid; i < n; i += LKP_THREADS) {
+      if (i < usable) {
+        Fe<P> v = fe_from_mont(fe_load(s + i));
+        K[2 * i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]); K[2 * i + 1] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
+      } else { K[2 * i] = ff; K[2 * i + 1] = ff; }      // larger than every canonical value: stays behind the usable rows
+    }
+    __syncthreads();
+  };
+  // 1. table expression, sorted, canonical -> global scratch
+  load_keys(d.ctab);
+  bitonic_sort_keys(K, n);
+  for (uint32_t i = tid; i < usable; i += LKP_THREADS) {
+    uint4* o = reinterpret_cast<uint4*>(T + i);
+    o[0] = K[2 * i]; o[1] = K[2 * i + 1];
+  }
+  __syncthreads();
+  // 2. input expression, sorted: A'
+  load_keys(d.cin);
+  bitonic_sort_keys(K, n);
+  Fe<P>* aout = region_ptr<P>(reg, d.aout, b, n);
+  Fe<P>* sout = region_ptr<P>(reg, d.sout, b, n);
+  for (uint32_t i = tid; i < n; i += LKP_THREADS) {
+    removed[i] = 0;
+    bool rep = false;
+    if (i < usable) {
+      const uint4 a0 = K[2 * i], a1 = K[2 * i + 1];
+      Fe<P> v; v.l[0] = a0.x; v.l[1] = a0.y; v.l[2] = a0.z; v.l[3] = a0.w; v.l[4] = a1.x; v.l[5] = a1.y; v.l[6] = a1.z; v.l[7] = a1.w;
+      fe_store(aout + i, fe_to_mont(v));
+      rep = i > 0 && key_eq(a0, a1, K[2 * i - 2], K[2 * i - 1]);
+    }
+    repeat[i] = rep ? 1u : 0u;
+  }
+  __syncthreads();
+  // 3. every distinct input value takes one copy out of the table multiset
+  for (uint32_t i = tid; i < usable; i += LKP_THREADS) {
+    if (repeat[i]) continue;
+    const uint4 a0 = K[2 * i], a1 = K[2 * i + 1];
+    uint32_t lo = 0, hi = usable;                       // lower_bound
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      const uint4* q = reinterpret_cast<const uint4*>(T + mid);
+      if (key_less(q[0], q[1], a0, a1)) lo = mid + 1; else hi = mid;
+    }
+    bool ok = lo < usable;
+    if (ok) { const uint4* q = reinterpret_cast<const uint4*>(T + lo); ok = key_eq(q[0], q[1], a0, a1); }
+    if (ok) removed[lo] = 1; else atomicOr(err, 1u);    // Error::ConstraintSystemFailure: input not in the table
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += LKP_THREADS) removed[i] = (i < usable && !removed[i]) ? 1u : 0u;    // now: "kept"
+  __syncthreads();
+  const uint32_t n_left = block_exclusive_scan(removed, n, wsum);
+  for (uint32_t i = tid; i < usable; i += LKP_THREADS) {
+    const uint32_t nxt = (i + 1 < n) ? removed[i + 1] : n_left;
+    if (nxt != removed[i]) left[removed[i]] = i;
+  }
+  __syncthreads();
+  const uint32_t n_rep = block_exclusive_scan(repeat, n, wsum);
+  if (n_rep != n_left) { if (tid == 0) atomicOr(err, 2u); return; }
+  // 4. S'
+  for (uint32_t i = tid; i < usable; i += LKP_THREADS) {
+    const uint32_t nxt = (i + 1 < n) ? repeat[i + 1] : n_rep;
+    Fe<P> v;
+    if (nxt == repeat[i]) {
+      const uint4 a0 = K[2 * i], a1 = K[2 * i + 1];
+      v.l[0] = a0.x; v.l[1] = a0.y; v.l[2] = a0.z; v.l[3] = a0.w; v.l[4] = a1.x; v.l[5] = a1.y; v.l[6] = a1.z; v.l[7] = a1.w;
+    } else {
+      v = fe_load(T + left[n_left - 1 - repeat[i]]);
+    }
+    fe_store(sout + i, fe_to_mont(v));
+  }
+}
+
 // ---- grand products ----------------------------------------------------------------------------------
 // permutation fractions for one column set: num[i] = prod_j (v_j + (beta delta^j) w^i + gamma),
 //                                            den[i] = prod_j (v_j + beta sigma_j + gamma)

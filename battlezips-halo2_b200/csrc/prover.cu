@@ -96,10 +96,11 @@ struct PkImpl {
   // workspace cache
   struct Work {
     uint32_t batch = 0;
-    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac;
+    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac, lk_sorted, lk_err;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+    uint32_t* h_err = nullptr;      // pinned: error word of the device lookup permutation
   } work;
-  ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); }
+  ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); if (work.h_err) cudaFreeHost(work.h_err); }
 };
 
 // ------------------------------------------------------------------------------------------------------
@@ -307,6 +308,9 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.ptrs.alloc(B * 64 * 2 * sizeof(void*));
   w.descs.alloc(64 * 1024);
   w.adv_in.alloc(1);
+  w.lk_sorted.alloc(std::max<size_t>(1, (size_t)B * pk.L * n * E));
+  w.lk_err.alloc(64);
+  if (!w.h_err) BZ_CUDA(cudaMallocHost(&w.h_err, 64));
   if (w.h_pinned) cudaFreeHost(w.h_pinned);
   w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(64 * 64, (pk.evals.size() + 16) * E)), 1 << 20);
   BZ_CUDA(cudaMallocHost(&w.h_pinned, w.h_pinned_bytes));
@@ -881,45 +885,64 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       eval_program_kernel<FpP><<<dim3((n + 127) / 128, B), 128, pk.lk_ninstr * 4, st>>>(a);
       C->kernel_launches++;
     }
-    // host: sort / permute (U: lookup/prover.rs::permute_expression_pair)
-    const size_t per = (size_t)2 * L * n * 32;
-    BZ_CHECK((size_t)B * per <= w.h_pinned_bytes, "pinned staging too small");
-    for (uint32_t b = 0; b < B; ++b) BZ_CUDA(cudaMemcpyAsync((char*)w.h_pinned + b * per, misc(b, pk.m_cin0), per, cudaMemcpyDeviceToHost, st));
-    BZ_CUDA(cudaStreamSynchronize(st));
-    std::vector<HFe> up((size_t)B * L * 2 * n, F.zero());
-    for (uint32_t b = 0; b < B; ++b)
-      for (uint32_t l = 0; l < L; ++l) {
-        const HFe* cinp = (const HFe*)((char*)w.h_pinned + b * per) + (size_t)(2 * l) * n;
-        const HFe* ctab = cinp + n;
-        struct Key { std::array<uint64_t, 4> v; uint32_t idx; };
-        auto canon = [&](const HFe& x) { std::array<uint64_t, 4> r; F.to_raw(x, r.data()); return r; };
-        auto less = [](const std::array<uint64_t, 4>& a, const std::array<uint64_t, 4>& c) { for (int i = 3; i >= 0; --i) { if (a[i] != c[i]) return a[i] < c[i]; } return false; };
-        std::vector<Key> a(usable);
-        for (uint32_t i = 0; i < usable; ++i) a[i] = Key{canon(cinp[i]), i};
-        std::stable_sort(a.begin(), a.end(), [&](const Key& x, const Key& y) { return less(x.v, y.v); });
-        std::map<std::array<uint64_t, 4>, std::pair<uint32_t, HFe>, decltype(less)> leftover(less);
-        for (uint32_t i = 0; i < usable; ++i) { auto key = canon(ctab[i]); auto it = leftover.find(key); if (it == leftover.end()) leftover.emplace(key, std::make_pair(1u, ctab[i])); else it->second.first++; }
-        HFe* ap = &up[((size_t)b * L + l) * 2 * n];
-        HFe* sp = ap + n;
-        std::vector<uint32_t> repeated;
-        for (uint32_t row = 0; row < usable; ++row) {
-          ap[row] = cinp[a[row].idx];
-          if (row == 0 || a[row].v != a[row - 1].v) {
-            sp[row] = ap[row];
-            auto it = leftover.find(a[row].v);
-            if (it == leftover.end() || it->second.first == 0) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure)");
-            it->second.first--;
-          } else repeated.push_back(row);
+    const bool device_permute = n <= LKP_MAX_N && !getenv("BZ_LOOKUP_HOST");
+    std::vector<HFe> up;
+    if (device_permute) {
+      // device: sort / permute (U: lookup/prover.rs::permute_expression_pair), one CTA per (lookup, proof)
+      static bool attr = false;
+      if (!attr) { BZ_CUDA(cudaFuncSetAttribute(lookup_permute_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lookup_permute_smem(LKP_MAX_N))); attr = true; }
+      std::vector<LookupPermDesc> pd;
+      for (uint32_t l = 0; l < L; ++l)
+        pd.push_back(LookupPermDesc{PolyRef{R_MISC, pk.m_cin0 + 2 * l}, PolyRef{R_MISC, pk.m_cin0 + 2 * l + 1}, PolyRef{R_VAL, pk.slot_lk(l, 0)}, PolyRef{R_VAL, pk.slot_lk(l, 1)}});
+      LookupPermDesc* dpd = upload_desc(pd);
+      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, 4, st));
+      {
+        ProfScope prof(C, PROF_SCAN);
+        lookup_permute_kernel<FpP><<<dim3(L, B), LKP_THREADS, lookup_permute_smem(n), st>>>(reg, n, usable, dpd, (DFe*)w.lk_sorted.p, (uint32_t*)w.lk_err.p);
+        C->kernel_launches++;
+      }
+      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, 4, cudaMemcpyDeviceToHost, st));     // read after the commitments' sync below
+    } else {
+      // host: sort / permute (U: lookup/prover.rs::permute_expression_pair)
+      const size_t per = (size_t)2 * L * n * 32;
+      BZ_CHECK((size_t)B * per <= w.h_pinned_bytes, "pinned staging too small");
+      for (uint32_t b = 0; b < B; ++b) BZ_CUDA(cudaMemcpyAsync((char*)w.h_pinned + b * per, misc(b, pk.m_cin0), per, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(cudaStreamSynchronize(st));
+      up.assign((size_t)B * L * 2 * n, F.zero());
+      for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t l = 0; l < L; ++l) {
+          const HFe* cinp = (const HFe*)((char*)w.h_pinned + b * per) + (size_t)(2 * l) * n;
+          const HFe* ctab = cinp + n;
+          struct Key { std::array<uint64_t, 4> v; uint32_t idx; };
+          auto canon = [&](const HFe& x) { std::array<uint64_t, 4> r; F.to_raw(x, r.data()); return r; };
+          auto less = [](const std::array<uint64_t, 4>& a, const std::array<uint64_t, 4>& c) { for (int i = 3; i >= 0; --i) { if (a[i] != c[i]) return a[i] < c[i]; } return false; };
+          std::vector<Key> a(usable);
+          for (uint32_t i = 0; i < usable; ++i) a[i] = Key{canon(cinp[i]), i};
+          std::stable_sort(a.begin(), a.end(), [&](const Key& x, const Key& y) { return less(x.v, y.v); });
+          std::map<std::array<uint64_t, 4>, std::pair<uint32_t, HFe>, decltype(less)> leftover(less);
+          for (uint32_t i = 0; i < usable; ++i) { auto key = canon(ctab[i]); auto it = leftover.find(key); if (it == leftover.end()) leftover.emplace(key, std::make_pair(1u, ctab[i])); else it->second.first++; }
+          HFe* ap = &up[((size_t)b * L + l) * 2 * n];
+          HFe* sp = ap + n;
+          std::vector<uint32_t> repeated;
+          for (uint32_t row = 0; row < usable; ++row) {
+            ap[row] = cinp[a[row].idx];
+            if (row == 0 || a[row].v != a[row - 1].v) {
+              sp[row] = ap[row];
+              auto it = leftover.find(a[row].v);
+              if (it == leftover.end() || it->second.first == 0) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure)");
+              it->second.first--;
+            } else repeated.push_back(row);
+          }
+          for (auto& kv : leftover)
+            for (uint32_t c = 0; c < kv.second.first; ++c) { BZ_CHECK(!repeated.empty(), "lookup permutation underflow"); sp[repeated.back()] = kv.second.second; repeated.pop_back(); }
+          BZ_CHECK(repeated.empty(), "lookup permutation leftover");
         }
-        for (auto& kv : leftover)
-          for (uint32_t c = 0; c < kv.second.first; ++c) { BZ_CHECK(!repeated.empty(), "lookup permutation underflow"); sp[repeated.back()] = kv.second.second; repeated.pop_back(); }
-        BZ_CHECK(repeated.empty(), "lookup permutation leftover");
-      }
-    for (uint32_t b = 0; b < B; ++b)
-      for (uint32_t l = 0; l < L; ++l) {
-        BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 0)), &up[((size_t)b * L + l) * 2 * n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
-        BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 1)), &up[((size_t)b * L + l) * 2 * n + n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
-      }
+      for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t l = 0; l < L; ++l) {
+          BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 0)), &up[((size_t)b * L + l) * 2 * n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
+          BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_lk(l, 1)), &up[((size_t)b * L + l) * 2 * n + n], (size_t)n * 32, cudaMemcpyHostToDevice, st));
+        }
+    }
     std::vector<CopyDesc> cd;
     std::vector<CommitReq> reqs;
     std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(2 * L));
@@ -936,8 +959,9 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       }
     }
     launch_copy(cd, n);
-    BZ_CUDA(cudaStreamSynchronize(st));      // `up` must outlive the async copies
+    if (!device_permute) BZ_CUDA(cudaStreamSynchronize(st));      // `up` must outlive the async copies
     commit(reqs, bl, pts);
+    if (device_permute && *w.h_err) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure)");
     for (uint32_t b = 0; b < B; ++b) for (uint32_t j = 0; j < 2 * L; ++j) t_write_point(ps[b], pts[b][j]);
   }
   // ---- step 6

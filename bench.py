@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
+    ap.add_argument("--no-extras", dest="extras", action="store_false",
+                    help="default (shot) run only: skip the compact Board / MSM / NTT sub-benchmarks reported under `extras`")
     return ap.parse_args()
 
 
@@ -208,6 +210,11 @@ class MsmWorkload:
         # MSM algorithmic bytes: 32 B scalar + 64 B base per point (96*N); dominant kernel = bucket accumulation
         return "msm_bucket", 96.0 * self.n
 
+    def close(self):
+        for d in (self.d_scalars, self.d_bases, self.d_out):
+            d.free()
+        self.h_scalars = self.h_bases = None
+
     def cpu(self, sample_log, steps=1):
         from oracle import c_oracle as co
         m = 1 << min(sample_log, self.log)
@@ -258,6 +265,13 @@ class NttWorkload:
     def dominant(self):
         npass = 1 if self.log <= 12 else (2 if self.log <= 20 else 3)
         return "ntt_pass", 64.0 * self.n / npass      # per launch: each pass reads+writes the array once
+
+    def field_muls(self):
+        return (self.n // 2) * self.log               # butterflies of one transform
+
+    def close(self):
+        self.d_a.free(); self.d_b.free()
+        self.h_a = None
 
     def cpu(self, sample_log, steps=1):
         from oracle import c_oracle as co
@@ -417,6 +431,17 @@ class ProofWorkload:
     def all_contexts(self):
         return [l["ctx"] for l in self.lanes]
 
+    def close(self):
+        self.pool.shutdown()
+        for lane in self.lanes:
+            for d in lane["d"]:
+                d.free()
+            lane["pk"].close()
+            if lane["ctx"] is not self.ctx:
+                lane["ctx"].close()
+        self.params.close()
+        self.lanes = []
+
     def dominant(self):
         # fixed-base MSM: algorithmic bytes = one 64 B table point per mixed addition + 32 B per scalar read
         return "fixed_msm", None
@@ -488,6 +513,123 @@ def run_reference(args, rank):
         "gpu_launches": 0}))
 
 
+def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps=None, warmup=None):
+    """One workload, three timed passes (device-resident, per-kernel profile, end-to-end with host buffers) -> dict."""
+    import torch
+    import torch.distributed as dist
+    steps = steps or args.steps
+    warmup = warmup or args.warmup
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing ----
+    for _ in range(warmup):
+        wl.step_device()
+    barrier()
+    ctxs = wl.all_contexts() if hasattr(wl, "all_contexts") else [ctx]
+    launches0 = sum(c.kernel_launches() for c in ctxs)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    units = 0.0
+    for _ in range(steps):
+        units += wl.step_device()
+    e1.record(stream)
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    clocks = sampler.stop() if rank == 0 else None
+    launches = sum(c.kernel_launches() for c in ctxs) - launches0
+    # ---- per-kernel pass: the same steps on ONE lane with the library's CUDA-event scopes on, so every kernel is
+    # timed alone on the GPU (with several lanes in flight, kernels of different lanes overlap and a per-kernel
+    # duration would measure the time-slicing, not the kernel).  The roofline / int_pipe objects come from here.
+    ctx.profile_enable(True)
+    barrier()
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record(stream)
+    for _ in range(steps):
+        (wl.step_profile if hasattr(wl, "step_profile") else wl.step_device)()
+    p1.record(stream)
+    barrier()
+    prof_ms = p0.elapsed_time(p1)
+    prof = dict(ctx.profile_read())
+    adds_total = ctx.profile_counter(0)
+    ctx.profile_enable(False)
+
+    # ---- end-to-end through the host-buffer ABI (H2D + D2H inside the timed region) ----
+    for _ in range(min(warmup, 2)):
+        wl.step_e2e()
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record(stream)
+    t0 = time.perf_counter()
+    units_e = 0.0
+    for _ in range(steps):
+        units_e += wl.step_e2e()
+    e3.record(stream)
+    barrier()
+    wall_e = time.perf_counter() - t0
+    ms_e = torch.tensor([max(e2.elapsed_time(e3), 1e3 * wall_e)], device="cuda")   # host-synchronous calls: wall clock bounds it
+    if world > 1:
+        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
+    ms_e = float(ms_e.item())
+    if rank != 0:
+        return None
+    value = units * world / (ms / 1e3)
+    e2e_value = units_e * world / (ms_e / 1e3)
+    tag, alg_bytes = wl.dominant()
+    if tag not in prof and prof:                     # e.g. k >= 18: commitments go through the bucket MSM
+        tag = max(prof, key=lambda t: prof[t][0])
+        alg_bytes = 0.0
+    peak, peak_kind = peaks()
+    roof = None
+    int_pipe = None
+    if tag == "fixed_msm" and tag in prof:
+        adds = adds_total
+        tot_ms, cnt = prof[tag]
+        alg_bytes = adds * 64.0 / cnt      # per launch: one 64 B table entry per mixed addition
+        imad_peak = ctx.imad_peak()
+        # 10 field multiplications (8M + 2S) per mixed addition; I = fma-pipe issue slots per multiplication in the
+        # shipped SASS (cuobjdump count, DESIGN.md)
+        fmul_per_s = adds * 10.0 / (tot_ms / 1e3)
+        int_pipe = {"kernel": tag, "mixed_adds_per_step": adds / steps, "field_mul_per_s": fmul_per_s, "fma_pipe_instr_per_field_mul_sass": FMA_PER_MUL,
+                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * FMA_PER_MUL / imad_peak}
+    elif hasattr(wl, "field_muls") and tag in prof:
+        tot_ms, cnt = prof[tag]
+        imad_peak = ctx.imad_peak()
+        fmul_per_s = wl.field_muls() * steps / (tot_ms / 1e3)
+        int_pipe = {"kernel": tag, "field_mul_per_s": fmul_per_s, "fma_pipe_instr_per_field_mul_sass": FMA_PER_MUL,
+                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * FMA_PER_MUL / imad_peak}
+    if tag in prof:
+        tot_ms, cnt = prof[tag]
+        avg_s = tot_ms / cnt / 1e3
+        ach = alg_bytes / avg_s / 1e9
+        roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
+                "share_of_step": tot_ms / prof_ms, "measured": "single-lane pass of the same steps, CUDA-event scopes in the library",
+                "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
+    cpu = None
+    if want_cpu:
+        v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
+        cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
+    return {
+        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": steps, "warmup": warmup,
+        "ms_per_step": ms / steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None,
+        "dtype": wl.dtype, "data": "synthetic",
+        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "per-step working set (tables + batch) larger than L2" if isinstance(wl, ProofWorkload) else "inputs < L2; not flushed"},
+        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
+        "verified": getattr(wl, "check", lambda: None)()}
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -512,114 +654,26 @@ def main():
     ctx = bz.Context(local_rank, stream=stream.cuda_stream)
     wl = WORKLOADS[args.workload](args)
     wl.setup(ctx, rank)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # ---- device-resident timing ----
-    for _ in range(args.warmup):
-        wl.step_device()
-    barrier()
-    ctxs = wl.all_contexts() if hasattr(wl, "all_contexts") else [ctx]
-    launches0 = sum(c.kernel_launches() for c in ctxs)
-    sampler = ClockSampler(local_rank)
+    line = measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=(rank == 0))
+    # ---- the other headline numbers of BASELINE.json's metric (Board proofs/s, MSM points/s, NTT GB/s) ride along in
+    # the same JSON line as compact sub-benchmarks, so that one default run reports all of them
+    extras = {}
+    if args.workload == "shot" and args.extras:
+        if hasattr(wl, "close"):
+            wl.close()
+        names = ["board", "msm", "ntt"] if world == 1 else ["msm"]
+        for name in names:
+            w2 = WORKLOADS[name](args)
+            w2.setup(ctx, rank)
+            r = measure(args, w2, ctx, stream, rank, world, local_rank, want_cpu=False, steps=min(args.steps, 3), warmup=3)
+            if hasattr(w2, "close"):
+                w2.close()
+            if r is not None:
+                extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "int_pipe", "verified")}
     if rank == 0:
-        sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    units = 0.0
-    for _ in range(args.steps):
-        units += wl.step_device()
-    e1.record(stream)
-    barrier()
-    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-    if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
-    clocks = sampler.stop() if rank == 0 else None
-    launches = sum(c.kernel_launches() for c in ctxs) - launches0
-    # ---- per-kernel pass: the same steps on ONE lane with the library's CUDA-event scopes on, so every kernel is
-    # timed alone on the GPU (with several lanes in flight, kernels of different lanes overlap and a per-kernel
-    # duration would measure the time-slicing, not the kernel).  The roofline / int_pipe objects come from here.
-    ctx.profile_enable(True)
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    p0.record(stream)
-    for _ in range(args.steps):
-        (wl.step_profile if hasattr(wl, "step_profile") else wl.step_device)()
-    p1.record(stream)
-    barrier()
-    prof_ms = p0.elapsed_time(p1)
-    prof = dict(ctx.profile_read())
-    adds_total = ctx.profile_counter(0)
-    ctx.profile_enable(False)
-
-    # ---- end-to-end through the host-buffer ABI (H2D + D2H inside the timed region) ----
-    for _ in range(min(args.warmup, 2)):
-        wl.step_e2e()
-    barrier()
-    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e2.record(stream)
-    t0 = time.perf_counter()
-    units_e = 0.0
-    for _ in range(args.steps):
-        units_e += wl.step_e2e()
-    e3.record(stream)
-    barrier()
-    wall_e = time.perf_counter() - t0
-    ms_e = torch.tensor([max(e2.elapsed_time(e3), 1e3 * wall_e)], device="cuda")   # host-synchronous calls: wall clock bounds it
-    if world > 1:
-        dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
-    ms_e = float(ms_e.item())
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
-    value = units * world / (ms / 1e3)
-    e2e_value = units_e * world / (ms_e / 1e3)
-    tag, alg_bytes = wl.dominant()
-    if tag not in prof and prof:                     # e.g. k >= 18: commitments go through the bucket MSM
-        tag = max(prof, key=lambda t: prof[t][0])
-        alg_bytes = 0.0
-    peak, peak_kind = peaks()
-    roof = None
-    int_pipe = None
-    if tag == "fixed_msm" and tag in prof:
-        adds = adds_total
-        tot_ms, cnt = prof[tag]
-        alg_bytes = adds * 64.0 / cnt + 32.0 * (wl.B * (1 << wl.k)) * 0      # per launch: one 64 B table entry per mixed addition
-        imad_peak = ctx.imad_peak()
-        # 10 field multiplications (8M + 2S) per mixed addition; I = IMAD-pipe instructions per multiplication in the
-        # shipped SASS (cuobjdump count): IMAD.WIDE + IMAD.X + IMAD.MOV/SHL/U32
-        fmul_per_s = adds * 10.0 / (tot_ms / 1e3)
-        int_pipe = {"kernel": tag, "mixed_adds_per_step": adds / args.steps, "field_mul_per_s": fmul_per_s, "fma_pipe_instr_per_field_mul_sass": FMA_PER_MUL,
-                    "imad_peak_measured_per_s": imad_peak, "frac_of_imad_peak": fmul_per_s * FMA_PER_MUL / imad_peak}
-    if tag in prof:
-        tot_ms, cnt = prof[tag]
-        avg_s = tot_ms / cnt / 1e3
-        ach = alg_bytes / avg_s / 1e9
-        roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
-                "share_of_step": tot_ms / prof_ms, "measured": "single-lane pass of the same steps, CUDA-event scopes in the library",
-                "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
-    cpu = None
-    if world == 1 or rank == 0:
-        v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
-        cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
-    if isinstance(wl, ProofWorkload):
-        wl.h2d_ = wl.h2d
-    print(json.dumps({
-        "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None,
-        "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "per-step working set (tables + batch) larger than L2" if isinstance(wl, ProofWorkload) else "inputs < L2; not flushed"},
-        "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
-        "verified": getattr(wl, "check", lambda: None)()}))
+        if extras:
+            line["extras"] = extras
+        print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
