@@ -74,3 +74,23 @@ def curve_op(ctx, curve, op, a, b):
     out = np.empty_like(a)
     ctx._check(ctx.lib.bz_curve_op(ctx.h, curve, _CURVE_OPS[op], _np_ptr(a), _np_ptr(b), _np_ptr(out), len(a)))
     return out
+
+
+def hash_to_curve(ctx, curve, domain_prefix, messages):
+    """pasta `C::hash_to_curve(domain_prefix)` over equal-length byte messages -> (count, 8) uint64 Montgomery affine."""
+    msgs = [bytes(m) for m in messages]
+    L = len(msgs[0]) if msgs else 0
+    assert all(len(m) == L for m in msgs)
+    buf = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8).copy()
+    out = np.zeros((len(msgs), 8), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_hash_to_curve(ctx.h, curve, domain_prefix.encode(), _np_ptr(buf), L, len(msgs), _np_ptr(out)))
+    return out
+
+
+def params_new(ctx, k, curve=0):
+    """`Params::new(k)` on the device -> dict(g, g_lagrange: (n, 8); w, u: (8,)) of Montgomery affine points."""
+    n = 1 << k
+    g, gl = np.zeros((n, 8), dtype=np.uint64), np.zeros((n, 8), dtype=np.uint64)
+    w, u = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+    ctx._check(ctx.lib.bz_params_new(ctx.h, k, curve, _np_ptr(g), _np_ptr(gl), _np_ptr(w), _np_ptr(u)))
+    return {"g": g, "g_lagrange": gl, "w": w, "u": u}

@@ -81,6 +81,8 @@ def load_library():
         "bz_lagrange_to_coeff": (i32, [vp, i32, vp, u32]),
         "bz_coeff_to_extended": (i32, [vp, i32, vp, vp, u32, u32]),
         "bz_extended_to_coeff": (i32, [vp, i32, vp, u32]),
+        "bz_params_new": (i32, [vp, u32, i32, vp, vp, vp, vp]),
+        "bz_hash_to_curve": (i32, [vp, i32, ctypes.c_char_p, vp, u32, u64, vp]),
     }
     declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",
                           "bz_pk_num_random", "bz_pk_proof_size", "bz_create_proofs"}     # bound in plonk/prover.py

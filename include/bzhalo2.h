@@ -123,6 +123,16 @@ typedef struct bz_pk bz_pk;
 int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, const void* g_lagrange, const void* w,
                      const void* u, int window_bits, bz_params** out);
 void bz_params_destroy(bz_params* params);
+/* Params::new(k) (U: halo2_proofs 0.2.0 src/poly/commitment.rs; reference call sites /root/reference/benches/shot.rs:58,
+ * benches/board.rs:51, src/circuits/shot.rs:915, src/circuits/board.rs:907): g[i] = hash_to_curve("Halo2-Parameters")
+ * (0x00 || i LE32), g_lagrange = group inverse FFT of g, w / u = hasher(0x01) / hasher(0x02) -- all computed on the
+ * device.  Outputs (host): g, g_lagrange = 2^k x 64 B affine; w, u = 64 B. */
+int bz_params_new(bz_ctx* ctx, uint32_t k, int curve, void* g, void* g_lagrange, void* w, void* u);
+/* pasta_curves `C::hash_to_curve(domain_prefix)(message)` for `count` messages of msg_len bytes each (host); 64 B affine
+ * out per message.  (U: pasta_curves 0.4.1 src/hashtocurve.rs; reference call site /root/reference/src/utils/pedersen.rs:20-22,
+ * KATs /root/reference/src/utils/constants/fixed_bases/board_commit_v.rs:5-14.) */
+int bz_hash_to_curve(bz_ctx* ctx, int curve, const char* domain_prefix, const void* messages, uint32_t msg_len,
+                     uint64_t count, void* out_affine);
 /* Params::commit (lagrange_basis = 0) / Params::commit_lagrange (1): poly = n scalars (host), blind = 1 scalar;
  * result already normalised: 64 B affine (what `.to_affine()` / batch_normalize yields). */
 int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* poly, const void* blind,
