@@ -109,11 +109,11 @@ void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev,
 //   1. fb_decode_kernel   one thread per (msm, point): signed digits -> packed table indices, appended to the MSM's
 //                         entry list (warp-aggregated atomic reservation; zero digits vanish here, so witness columns
 //                         -- mostly 0/1 -- cost only what they contain)
-//   2. fb_accumulate_kernel   one thread per 32 consecutive list entries: gather + mixed additions, no shared memory,
-//                         no barriers, every warp full (r1 ncu: the one-thread-per-point kernel ran 11-13 of 32 lanes)
-//   3. fb_fold_kernel     one CTA per MSM: strided sum of its segment partials, shared-memory tree, affine output
+//   2. fb_accumulate_kernel   ONE resident wave of threads; the entries of all MSMs of the launch form a flat index
+//                         space cut into equal shares, one per thread: gather + mixed additions, no barriers in the
+//                         loop, every warp full, every SM busy until the end
+//   3. fb_fold_kernel     one CTA per MSM: strided sum of its partials, shared-memory tree, affine output
 constexpr int FB_THREADS = 128;
-constexpr uint32_t FB_SEG = 32;
 constexpr int FB_FOLD_THREADS = 128;
 
 template <class SP>
@@ -172,25 +172,85 @@ __global__ void __launch_bounds__(FB_THREADS) fb_decode_kernel(uint32_t npts, ui
   }
 }
 
+// Exclusive prefix sum of the per-MSM entry counts into shared memory (every CTA recomputes it: n_msm <= FB_MAX_MSM words),
+// and the balanced share q = entries per thread.  All entries of all MSMs of a launch form ONE flat index space that is
+// cut into equal ranges, one per resident thread: no wave quantisation (r1d ncu: the per-segment grid ran 2.16 waves on
+// the IPA-round launches and left the fma pipe at 56-66 %), and ~8x fewer partial sums to fold.
+constexpr uint32_t FB_MAX_MSM = 4096;
+constexpr uint32_t FB_MIN_SHARE = 8;
+__device__ __forceinline__ uint32_t fb_plan(const uint32_t* __restrict__ list_count, uint32_t n_msm, uint32_t total_threads, uint32_t* off /* [n_msm + 1] shared */,
+                                            uint32_t* wsum /* [33] shared */) {
+  const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+  const uint32_t per = (n_msm + blockDim.x - 1) / blockDim.x, lo = min(tid * per, n_msm), hi = min(lo + per, n_msm);
+  uint32_t s = 0;
+  for (uint32_t i = lo; i < hi; ++i) s += list_count[i];
+  uint32_t incl = s;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= (uint32_t)d) incl += o; }
+  if (lane == 31) wsum[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t v = lane < nw ? wsum[lane] : 0u, iv = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { uint32_t o = __shfl_up_sync(0xffffffffu, iv, d); if (lane >= (uint32_t)d) iv += o; }
+    if (lane < nw) wsum[lane] = iv - v;
+    if (lane == 31) wsum[32] = iv;
+  }
+  __syncthreads();
+  uint32_t run = wsum[wid] + incl - s;
+  for (uint32_t i = lo; i < hi; ++i) { off[i] = run; run += list_count[i]; }
+  const uint32_t total = wsum[32];
+  if (tid == 0) off[n_msm] = total;
+  __syncthreads();
+  return max(FB_MIN_SHARE, (total + total_threads - 1) / total_threads);
+}
+
+// Warp W owns the flat entries [W*32q, (W+1)*32q); inside every MSM piece of that range lane l takes entries l, l+32, ...
+// (coalesced list reads) and keeps its own sum.  The table point of the NEXT entry is gathered before the current
+// addition starts, so the list -> table dependent DRAM round trips overlap the ~10 field multiplications of the addition.
+// A warp emits 32 partials per MSM it touches, at index (W + m)*32 + lane (unique and increasing along the flat order).
 template <class BP>
-__global__ void __launch_bounds__(FB_THREADS) fb_accumulate_kernel(const Affine<BP>* __restrict__ table, const uint32_t* __restrict__ lists,
-                                 uint32_t list_stride, const uint32_t* __restrict__ list_count, uint32_t segs_per_msm,
+__global__ void __launch_bounds__(FB_THREADS, 4) fb_accumulate_kernel(const Affine<BP>* __restrict__ table, const uint32_t* __restrict__ lists,
+                                 uint32_t list_stride, const uint32_t* __restrict__ list_count, uint32_t n_msm,
                                  Xyzz<BP>* __restrict__ partial, unsigned long long* __restrict__ add_counter) {
-  const uint32_t m = blockIdx.y, sidx = blockIdx.x * FB_THREADS + threadIdx.x;
-  const uint32_t cnt = list_count[m];
+  extern __shared__ uint32_t fb_off[];
+  __shared__ uint32_t wsum[33];
+  const uint32_t T = gridDim.x * FB_THREADS, t = blockIdx.x * FB_THREADS + threadIdx.x, lane = threadIdx.x & 31, W = t >> 5;
+  const uint32_t q = fb_plan(list_count, n_msm, T, fb_off, wsum);
+  const uint32_t total = fb_off[n_msm];
+  const uint64_t base64 = (uint64_t)W * 32u * q;
   uint32_t my_adds = 0;
-  if (sidx < segs_per_msm && sidx * FB_SEG < cnt) {
-    const uint32_t* list = lists + (size_t)m * list_stride + sidx * FB_SEG;
-    const uint32_t k = min(FB_SEG, cnt - sidx * FB_SEG);
-    Xyzz<BP> acc = xyzz_identity<BP>();
-    for (uint32_t j = 0; j < k; ++j) {
-      uint32_t ent = list[j];
-      Affine<BP> pt = aff_load(table + (ent & 0x7fffffffu));
-      xyzz_add_mixed_signed(acc, pt, (ent >> 31) != 0);
+  if (base64 < total) {
+    const uint32_t base = (uint32_t)base64, end = (uint32_t)min((uint64_t)total, base64 + (uint64_t)32 * q);
+    uint32_t lo = 0, hi = n_msm;                     // m = last MSM with off[m] <= base
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (fb_off[mid] <= base) lo = mid; else hi = mid; }
+    uint32_t m = lo, pbeg = base;
+    while (pbeg < end) {
+      while (fb_off[m + 1] <= pbeg) ++m;               // skip MSMs without entries
+      const uint32_t pend = min(end, fb_off[m + 1]);
+      const uint32_t* list = lists + (size_t)m * list_stride - fb_off[m];
+      Xyzz<BP> acc = xyzz_identity<BP>();
+      uint32_t p = pbeg + lane;
+      uint32_t ent = 0, ent_n = 0;
+      Affine<BP> pt;
+      if (p < pend) { ent = list[p]; pt = aff_load(table + (ent & 0x7fffffffu)); }
+      if (p + 32 < pend) ent_n = list[p + 32];
+      while (p < pend) {
+        const bool more = p + 32 < pend;
+        Affine<BP> pt_n;
+        uint32_t ent_nn = 0;
+        if (more) pt_n = aff_load(table + (ent_n & 0x7fffffffu));
+        if (p + 64 < pend) ent_nn = list[p + 64];
+        xyzz_add_mixed_signed(acc, pt, (ent >> 31) != 0);
+        ++my_adds;
+        if (more) pt = pt_n;
+        ent = ent_n; ent_n = ent_nn;
+        p += 32;
+      }
+      Xyzz<BP>* o = partial + ((size_t)W + m) * 32 + lane;
+      fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
+      pbeg = pend;
     }
-    my_adds = k;
-    Xyzz<BP>* o = partial + (size_t)m * segs_per_msm + sidx;
-    fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
   }
   if (add_counter) {       // profiling only: exact number of mixed additions this launch performed
     uint32_t tot = __reduce_add_sync(0xffffffffu, my_adds);
@@ -198,18 +258,25 @@ __global__ void __launch_bounds__(FB_THREADS) fb_accumulate_kernel(const Affine<
   }
 }
 
-// fold the segment partials of each MSM and normalise: one CTA per MSM -> affine (64 B), identity = zeros
+// fold the partials of each MSM and normalise: one CTA per MSM -> affine (64 B), identity = zeros
 template <class BP>
 __global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
-                                 uint32_t segs_per_msm, Affine<BP>* __restrict__ out) {
+                                 uint32_t n_msm, uint32_t acc_threads, Affine<BP>* __restrict__ out) {
+  extern __shared__ uint32_t fb_off[];
+  __shared__ uint32_t wsum[33];
   __shared__ Xyzz<BP> sh[FB_FOLD_THREADS];
   const uint32_t m = blockIdx.x, tid = threadIdx.x;
-  const uint32_t nseg = (list_count[m] + FB_SEG - 1) / FB_SEG;
+  const uint32_t q = fb_plan(list_count, n_msm, acc_threads, fb_off, wsum);
+  const uint32_t lo = fb_off[m], hi = fb_off[m + 1];
   Xyzz<BP> acc = xyzz_identity<BP>();
-  for (uint32_t j = tid; j < nseg; j += FB_FOLD_THREADS) {
-    const Xyzz<BP>* q = partial + (size_t)m * segs_per_msm + j;
-    Xyzz<BP> v; v.x = fe_load(&q->x); v.y = fe_load(&q->y); v.zz = fe_load(&q->zz); v.zzz = fe_load(&q->zzz);
-    acc = xyzz_add(acc, v);
+  if (hi > lo) {
+    const uint32_t w_first = lo / (32u * q), w_last = (hi - 1) / (32u * q);
+    const uint32_t npieces = (w_last - w_first + 1) * 32u;         // warp w, lane l -> (w + m) * 32 + l : contiguous
+    for (uint32_t t = tid; t < npieces; t += FB_FOLD_THREADS) {
+      const Xyzz<BP>* p = partial + ((size_t)w_first + m) * 32 + t;
+      Xyzz<BP> v; v.x = fe_load(&p->x); v.y = fe_load(&p->y); v.zz = fe_load(&p->zz); v.zzz = fe_load(&p->zzz);
+      acc = xyzz_add(acc, v);
+    }
   }
   sh[tid] = acc;
   __syncthreads();
@@ -228,25 +295,35 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
                             uint32_t n_msm, uint32_t /*chunks*/, void* d_out_affine) {
   cudaStream_t st = ctx->stream;
   if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
-  const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
-  const uint32_t segs = (list_stride + FB_SEG - 1) / FB_SEG;
-  ctx->scratch[0].ensure((size_t)n_msm * list_stride * 4);
-  ctx->scratch[1].ensure((size_t)n_msm * 4 + 64);
-  ctx->scratch[3].ensure((size_t)n_msm * segs * sizeof(Xyzz<BP>));
-  uint32_t* lists = ctx->scratch[0].as<uint32_t>();
-  uint32_t* counts = ctx->scratch[1].as<uint32_t>();
-  Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
-  BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)n_msm * 4, st));
-  unsigned long long* cnt = ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr;
-  {
-    ProfScope p(ctx, PROF_FIXED_MSM);
-    fb_decode_kernel<SP><<<dim3((fb.npts + FB_THREADS - 1) / FB_THREADS, n_msm), FB_THREADS, 0, st>>>(
-        fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main, n_main, (const Fe<SP>* const*)d_extra, lists, list_stride, counts);
-    fb_accumulate_kernel<BP><<<dim3((segs + FB_THREADS - 1) / FB_THREADS, n_msm), FB_THREADS, 0, st>>>(
-        fb.table.as<Affine<BP>>(), lists, list_stride, counts, segs, partial, cnt);
+  static int ctas_per_sm = 0;
+  if (!ctas_per_sm) {
+    BZ_CUDA(cudaFuncSetAttribute(fb_accumulate_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FB_MAX_MSM + 1) * 4)));
+    BZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fb_accumulate_kernel<BP>, FB_THREADS, (FB_MAX_MSM + 1) * 4));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
-  fb_fold_kernel<BP><<<n_msm, FB_FOLD_THREADS, 0, st>>>(partial, counts, segs, (Affine<BP>*)d_out_affine);
-  ctx->kernel_launches += 3;
+  const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
+  const uint32_t acc_ctas = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm, acc_threads = acc_ctas * FB_THREADS;
+  const uint32_t max_nm = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(FB_MAX_MSM, 0xffffffffull / list_stride));   // flat index fits 32 bits
+  for (uint32_t m0 = 0; m0 < n_msm; m0 += max_nm) {
+    const uint32_t nm = std::min(max_nm, n_msm - m0);
+    ctx->scratch[0].ensure((size_t)nm * list_stride * 4);
+    ctx->scratch[1].ensure((size_t)nm * 4 + 64);
+    ctx->scratch[3].ensure(((size_t)acc_threads + 32 * (size_t)nm + 32) * sizeof(Xyzz<BP>));
+    uint32_t* lists = ctx->scratch[0].as<uint32_t>();
+    uint32_t* counts = ctx->scratch[1].as<uint32_t>();
+    Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
+    BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)nm * 4, st));
+    unsigned long long* cnt = ctx->profiling ? (unsigned long long*)ctx->counters.p : nullptr;
+    const size_t smem = ((size_t)nm + 1) * 4;
+    {
+      ProfScope p(ctx, PROF_FIXED_MSM);
+      fb_decode_kernel<SP><<<dim3((fb.npts + FB_THREADS - 1) / FB_THREADS, nm), FB_THREADS, 0, st>>>(
+          fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main + m0, n_main, d_extra ? (const Fe<SP>* const*)d_extra + m0 : nullptr, lists, list_stride, counts);
+      fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, st>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
+      fb_fold_kernel<BP><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out_affine + m0);
+    }
+    ctx->kernel_launches += 3;
+  }
   BZ_CUDA(cudaGetLastError());
 }
 
