@@ -65,6 +65,7 @@ struct PkImpl {
   DevBuf shpoly;      // [F + M][n]  coefficient form
   DevBuf shcoset;     // [F + M + 5][ext_n]: fixed, sigma, l0, l_blind, l_last, active, coset_x
   DevBuf omega_pows;  // [n]
+  std::vector<uint64_t> vk_fixed_comm, vk_perm_comm;   // keygen_vk: commit_lagrange(column, Blind::default()) as affine (8 x u64 each)
   DevBuf tev;         // [2^(ext_k-k)]
   // programs
   DevBuf lk_code, q_code, lk_rot, q_rot;
@@ -111,6 +112,16 @@ template <class P> __global__ void geometric_kernel(::bz::Fe<P>* out, ::bz::Fe<P
 }
 
 static DFe dfe(const HFe& h) { DFe r; memcpy(r.l, h.l, 32); return r; }
+
+// pk.permutation.permutations from the copy-constraint cycles (U: plonk/permutation/keygen.rs `Assembly::build_pk`):
+// sigma_j[i] = delta^{col'} * omega^{row'}  where (col', row') = mapping[j][i]
+template <class P> __global__ void sigma_from_mapping_kernel(const uint32_t* __restrict__ mapping, const ::bz::Fe<P>* __restrict__ omega_pows,
+                                                             const ::bz::Fe<P>* __restrict__ delta_pows, ::bz::Fe<P>* __restrict__ out, uint64_t total) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const uint32_t c = mapping[2 * i], r = mapping[2 * i + 1];
+  fe_store(out + i, fe_mul(fe_load(delta_pows + c), fe_load(omega_pows + r)));
+}
 
 static uint32_t enc(uint32_t op, uint32_t x = 0, uint32_t y = 0) { return op | (x << 4) | (y << 16); }
 static uint32_t encc(uint32_t op, uint32_t idx) { return op | (idx << 4); }
@@ -420,7 +431,8 @@ API void bz_pk_destroy(bz_pk* pk) { delete pk; }
 API uint32_t bz_pk_num_random(const bz_pk* pk) { return pk ? pk->p.R : 0; }
 API uint32_t bz_pk_proof_size(const bz_pk* pk) { return pk ? pk->p.proof_size : 0; }
 
-API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values, bz_pk** out) {
+static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values,
+                          const uint32_t* mapping, bz_pk** out) {
   PV_TRY(ctx, {
     BZ_CHECK(out && params && cin, "null argument");
     *out = nullptr;
@@ -479,7 +491,23 @@ API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, cons
     const uint32_t FM = cs.F + pk.M;
     pk.lval.alloc((size_t)std::max(1u, FM) * n * 32);
     if (cs.F) BZ_CUDA(cudaMemcpyAsync(pk.lval.p, fixed_values, (size_t)cs.F * n * 32, cudaMemcpyHostToDevice, st));
-    if (pk.M) BZ_CUDA(cudaMemcpyAsync((char*)pk.lval.p + (size_t)cs.F * n * 32, sigma_values, (size_t)pk.M * n * 32, cudaMemcpyHostToDevice, st));
+    pk.omega_pows.alloc((size_t)n * 32);
+    geometric_kernel<FpP><<<(n + 127) / 128, 128, 0, st>>>((DFe*)pk.omega_pows.p, dfe(F.one()), dfe(pk.omega), n);
+    C->kernel_launches++;
+    if (pk.M && sigma_values) BZ_CUDA(cudaMemcpyAsync((char*)pk.lval.p + (size_t)cs.F * n * 32, sigma_values, (size_t)pk.M * n * 32, cudaMemcpyHostToDevice, st));
+    else if (pk.M) {
+      BZ_CHECK(mapping, "neither sigma values nor a permutation mapping given");
+      const uint64_t total = (uint64_t)pk.M * n;
+      for (uint64_t i = 0; i < total; ++i) BZ_CHECK(mapping[2 * i] < pk.M && mapping[2 * i + 1] < n, "permutation mapping out of range");
+      DevBuf d_map, d_delta;
+      d_map.alloc(total * 8); d_delta.alloc((size_t)pk.M * 32);
+      BZ_CUDA(cudaMemcpyAsync(d_map.p, mapping, total * 8, cudaMemcpyHostToDevice, st));
+      geometric_kernel<FpP><<<(pk.M + 127) / 128, 128, 0, st>>>((DFe*)d_delta.p, dfe(F.one()), dfe(F.delta()), pk.M);
+      sigma_from_mapping_kernel<FpP><<<(unsigned)((total + 127) / 128), 128, 0, st>>>((const uint32_t*)d_map.p, (const DFe*)pk.omega_pows.p, (const DFe*)d_delta.p,
+                                                                                    (DFe*)pk.lval.p + (size_t)cs.F * n, total);
+      C->kernel_launches += 2;
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
     pk.shpoly.alloc((size_t)std::max(1u, FM) * n * 32);
     pk.shcoset.alloc((size_t)(FM + 5) * en * 32);
     NttFusion inv; inv.post_mode = 1;
@@ -502,9 +530,7 @@ API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, cons
       BZ_CUDA(cudaStreamSynchronize(st));
     }
     geometric_kernel<FpP><<<(en + 127) / 128, 128, 0, st>>>((DFe*)pk.shcoset.p + (size_t)(FM + 4) * en, dfe(F.zeta()), dfe(pk.ext_omega), en);
-    pk.omega_pows.alloc((size_t)n * 32);
-    geometric_kernel<FpP><<<(n + 127) / 128, 128, 0, st>>>((DFe*)pk.omega_pows.p, dfe(F.one()), dfe(pk.omega), n);
-    C->kernel_launches += 2;
+    C->kernel_launches += 1;
     {  // t_evaluations
       uint32_t tn = 1u << (pk.ext_k - cs.k);
       HFe orig = F.pow_u64(F.zeta(), n), step = F.pow_u64(pk.ext_omega, n), cur = orig;
@@ -605,6 +631,56 @@ API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, cons
     build_programs(C, pk);
     BZ_CUDA(cudaStreamSynchronize(st));
     *out = h.release();
+  });
+}
+
+API int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values, bz_pk** out) {
+  if (!ctx) return BZ_ERR_INVALID;
+  if (cin && cin->n_perm_columns && !sigma_values) { ctx->c.last_error = "null sigma_values"; return BZ_ERR_INVALID; }
+  return pk_create_impl(ctx, params, cin, fixed_values, sigma_values, nullptr, out);
+}
+API int bz_pk_create_from_assembly(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const uint32_t* mapping, bz_pk** out) {
+  if (!ctx) return BZ_ERR_INVALID;
+  return pk_create_impl(ctx, params, cin, fixed_values, nullptr, mapping, out);
+}
+
+// keygen_vk's commitments: commit_lagrange(column, Blind::default() = 1) for every fixed and every sigma column
+API int bz_pk_vk_commitments(bz_ctx* ctx, bz_pk* pkh, void* fixed_commitments, void* perm_commitments) {
+  PV_TRY(ctx, {
+    BZ_CHECK(pkh, "null argument");
+    PkImpl& pk = pkh->p;
+    const uint32_t FM = pk.cs.F + pk.M, n = pk.n;
+    if (FM && pk.vk_fixed_comm.size() + pk.vk_perm_comm.size() != (size_t)FM * 8) {
+      cudaStream_t st = C->stream;
+      ParamsImpl& pr = *pk.params;
+      std::vector<void*> mainp(FM), extrap(FM);
+      DevBuf d_ptrs, d_extra, d_out;
+      d_ptrs.alloc((size_t)2 * FM * sizeof(void*)); d_extra.alloc((size_t)FM * 64); d_out.alloc((size_t)FM * 64);
+      std::vector<HFe> ex((size_t)FM * 2, C->fp.zero());
+      for (uint32_t j = 0; j < FM; ++j) { mainp[j] = (DFe*)pk.lval.p + (size_t)j * n; extrap[j] = (DFe*)d_extra.p + (size_t)j * 2; ex[2 * j] = C->fp.one(); }
+      BZ_CUDA(cudaMemcpyAsync(d_extra.p, ex.data(), ex.size() * 32, cudaMemcpyHostToDevice, st));
+      if (pr.use_tables) {
+        BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, mainp.data(), (size_t)FM * sizeof(void*), cudaMemcpyHostToDevice, st));
+        BZ_CUDA(cudaMemcpyAsync((void**)d_ptrs.p + FM, extrap.data(), (size_t)FM * sizeof(void*), cudaMemcpyHostToDevice, st));
+        fixed_msm_run(C, pr.fb_gl, (const void* const*)d_ptrs.p, n, (const void* const*)((void**)d_ptrs.p + FM), FM, 1, d_out.p);
+      } else {
+        DevBuf d_in, d_jac;
+        d_in.alloc((size_t)(n + 1) * 32); d_jac.alloc((size_t)FM * 96);
+        for (uint32_t j = 0; j < FM; ++j) {
+          BZ_CUDA(cudaMemcpyAsync(d_in.p, mainp[j], (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+          BZ_CUDA(cudaMemcpyAsync((char*)d_in.p + (size_t)n * 32, extrap[j], 32, cudaMemcpyDeviceToDevice, st));
+          msm_run(C, pr.curve, d_in.p, pr.gl_w.p, n + 1, (char*)d_jac.p + (size_t)j * 96, 0);
+        }
+        jac_to_affine_run(C, pr.curve, d_jac.p, d_out.p, FM);
+      }
+      std::vector<uint64_t> all((size_t)FM * 8);
+      BZ_CUDA(cudaMemcpyAsync(all.data(), d_out.p, all.size() * 8, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(cudaStreamSynchronize(st));
+      pk.vk_fixed_comm.assign(all.begin(), all.begin() + (size_t)pk.cs.F * 8);
+      pk.vk_perm_comm.assign(all.begin() + (size_t)pk.cs.F * 8, all.end());
+    }
+    if (fixed_commitments && pk.cs.F) memcpy(fixed_commitments, pk.vk_fixed_comm.data(), pk.vk_fixed_comm.size() * 8);
+    if (perm_commitments && pk.M) memcpy(perm_commitments, pk.vk_perm_comm.data(), pk.vk_perm_comm.size() * 8);
   });
 }
 

@@ -54,6 +54,10 @@ def _bind(lib):
     lib.bz_params_commit.argtypes = [vp, vp, i32, vp, vp, vp]
     lib.bz_pk_create.restype = i32
     lib.bz_pk_create.argtypes = [vp, vp, ctypes.POINTER(bz_circuit), vp, vp, ctypes.POINTER(vp)]
+    lib.bz_pk_create_from_assembly.restype = i32
+    lib.bz_pk_create_from_assembly.argtypes = [vp, vp, ctypes.POINTER(bz_circuit), vp, vp, ctypes.POINTER(vp)]
+    lib.bz_pk_vk_commitments.restype = i32
+    lib.bz_pk_vk_commitments.argtypes = [vp, vp, vp, vp]
     lib.bz_pk_destroy.restype = None
     lib.bz_pk_destroy.argtypes = [vp]
     lib.bz_pk_num_random.restype = u32
@@ -183,19 +187,30 @@ def sigma_values(ir, k, mapping, p=FP):
 class ProvingKey:
     """keygen_pk's device image for one circuit."""
 
-    def __init__(self, ctx, params, ir, fixed_values, mapping, vk_repr):
+    def __init__(self, ctx, params, ir, fixed_values, mapping, vk_repr, host_sigma=False):
         _bind(ctx.lib)
         self.ctx, self.params, self.ir = ctx, params, ir
         self.k, self.n = params.k, params.n
         circ, keep = flatten_circuit(ir, params.k, vk_repr)
         fixed = mont([v for col in fixed_values for v in col]) if fixed_values else np.zeros((1, 4), np.uint64)
-        sig = sigma_values(ir, params.k, mapping)
-        sigma = mont([v for col in sig for v in col]) if sig else np.zeros((1, 4), np.uint64)
         h = ctypes.c_void_p()
-        ctx._check(ctx.lib.bz_pk_create(ctx.h, params.h, ctypes.byref(circ), _np_ptr(fixed), _np_ptr(sigma), ctypes.byref(h)))
+        if host_sigma:          # pk.permutation.permutations computed by the caller (what a patched keygen_pk may already hold)
+            sig = sigma_values(ir, params.k, mapping)
+            sigma = mont([v for col in sig for v in col]) if sig else np.zeros((1, 4), np.uint64)
+            ctx._check(ctx.lib.bz_pk_create(ctx.h, params.h, ctypes.byref(circ), _np_ptr(fixed), _np_ptr(sigma), ctypes.byref(h)))
+        else:                   # Assembly::build_pk on the device from the copy-constraint cycles
+            mp = np.ascontiguousarray(np.array(mapping, dtype=np.uint32).reshape(-1, 2)) if len(mapping) else np.zeros((1, 2), np.uint32)
+            ctx._check(ctx.lib.bz_pk_create_from_assembly(ctx.h, params.h, ctypes.byref(circ), _np_ptr(fixed), _np_ptr(mp), ctypes.byref(h)))
         self.h = h
         self.num_random = ctx.lib.bz_pk_num_random(h)
         self.proof_size = ctx.lib.bz_pk_proof_size(h)
+
+    def vk_commitments(self):
+        """keygen_vk: (fixed_commitments (F, 8), permutation commitments (M, 8)) as Montgomery affine points."""
+        F, M = self.ir["num_fixed"], len(self.ir["permutation"])
+        fc, pc = np.zeros((max(F, 1), 8), dtype=np.uint64), np.zeros((max(M, 1), 8), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.bz_pk_vk_commitments(self.ctx.h, self.h, _np_ptr(fc), _np_ptr(pc)))
+        return fc[:F], pc[:M]
 
     def close(self):
         if self.h:

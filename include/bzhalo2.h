@@ -165,6 +165,15 @@ typedef struct {
  * quotient program are derived on the device. */
 int bz_pk_create(bz_ctx* ctx, bz_params* params, const bz_circuit* cs, const void* fixed_values,
                  const void* sigma_values, bz_pk** out);
+/* Same, with the permutation argument assembled on the device (U: plonk/permutation/keygen.rs `Assembly::build_pk`):
+ * mapping = n_perm_columns x n pairs (column', row') of u32 -- the copy-constraint cycles as `Assembly::copy` leaves
+ * them; sigma_j[i] = delta^column' * omega^row' is computed by a kernel. */
+int bz_pk_create_from_assembly(bz_ctx* ctx, bz_params* params, const bz_circuit* cs, const void* fixed_values,
+                               const uint32_t* mapping, bz_pk** out);
+/* keygen_vk's commitments (U: plonk/keygen.rs): commit_lagrange(column, Blind::default()) of every fixed column and
+ * every permutation (sigma) column, normalised: num_fixed x 64 B and n_perm_columns x 64 B affine (host; either may be
+ * NULL).  Computed once per pk with the fixed-base tables and cached. */
+int bz_pk_vk_commitments(bz_ctx* ctx, bz_pk* pk, void* fixed_commitments, void* perm_commitments);
 void bz_pk_destroy(bz_pk* pk);
 uint32_t bz_pk_num_random(const bz_pk* pk); /* Scalar::random draws one create_proof makes (protocol order) */
 uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yields */

@@ -98,3 +98,29 @@ def test_scaled_board_k13_both_commit_paths(ctx, force_general, monkeypatch):
     assert first_diff(proof, exp) is None, first_diff(proof, exp)
     assert job.verify(proof)
     pk.close(); params.close()
+
+
+@pytest.mark.parametrize("which", ["tiny", "shot"])
+def test_keygen_on_device_matches_oracle(ctx, oracle_c, which):
+    """keygen_vk / keygen_pk on the device (reference call sites /root/reference/benches/shot.rs:60-61):
+    fixed and permutation commitments equal the oracle keygen's, and the sigma columns assembled on the device from the
+    copy-constraint cycles give the same proof bytes as host-computed sigma values."""
+    from battlezips_halo2_b200.plonk import prover as PR
+    from tests.util_prover import VK_REPR
+    if which == "tiny":
+        job = Job(*tiny_circuit(5))
+    else:
+        from battlezips_halo2_b200.circuits import shot_circuit
+        cs, cfg, asg = shot_circuit(1)
+        job = Job(cs, asg)
+    params, pk = job.device_keys(ctx, window_bits=8)
+    fc, pc = pk.vk_commitments()
+    assert np.array_equal(fc, oracle_c.points_to_mont(0, job.opk.fixed_commitments))
+    assert np.array_equal(pc, oracle_c.points_to_mont(0, job.opk.perm_commitments))
+    pk2 = PR.ProvingKey(ctx, params, job.ir, job.asg.fixed, job.mapping, VK_REPR, host_sigma=True)
+    fc2, pc2 = pk2.vk_commitments()
+    assert np.array_equal(fc, fc2) and np.array_equal(pc, pc2)
+    a = _prove(job, pk, [2])[0]
+    b = _prove(job, pk2, [2])[0]
+    assert a == b == job.oracle_proof(index=2)
+    pk2.close(); pk.close(); params.close()
