@@ -139,6 +139,18 @@ template <class BP> __device__ __noinline__ Xyzz<BP> xyzz_mul_u32(const Xyzz<BP>
   return acc;
 }
 
+// [k]P, k canonical 256-bit, double-and-add from the top bit
+template <class BP> __device__ Xyzz<BP> xyzz_mul_scalar(const Xyzz<BP>& p, const uint32_t k[8]) {
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  int top = 255;
+  while (top >= 0 && !((k[top >> 5] >> (top & 31)) & 1)) --top;
+  for (int i = top; i >= 0; --i) {
+    acc = xyzz_dbl(acc);
+    if ((k[i >> 5] >> (i & 31)) & 1) acc = xyzz_add(acc, p);
+  }
+  return acc;
+}
+
 template <class BP> __device__ __forceinline__ Affine<BP> aff_load(const Affine<BP>* p) {
   Affine<BP> r; r.x = fe_load(&p->x); r.y = fe_load(&p->y); return r;
 }

@@ -58,6 +58,8 @@ def _bind(lib):
     lib.bz_pk_create_from_assembly.argtypes = [vp, vp, ctypes.POINTER(bz_circuit), vp, vp, ctypes.POINTER(vp)]
     lib.bz_pk_vk_commitments.restype = i32
     lib.bz_pk_vk_commitments.argtypes = [vp, vp, vp, vp]
+    lib.bz_verify_proofs.restype = i32
+    lib.bz_verify_proofs.argtypes = [vp, vp, u32, vp, vp, u32, vp, u32, vp]
     lib.bz_pk_destroy.restype = None
     lib.bz_pk_destroy.argtypes = [vp]
     lib.bz_pk_num_random.restype = u32
@@ -241,3 +243,32 @@ def create_proofs(pk, instances, advice, rand_wide):
     out = np.zeros((B, pk.proof_size), dtype=np.uint8)
     ctx._check(ctx.lib.bz_create_proofs(ctx.h, pk.h, B, _np_ptr(inst), _np_ptr(lens), stride, _np_ptr(advice), _np_ptr(rand_wide), _np_ptr(out)))
     return [bytes(out[b]) for b in range(B)]
+
+
+def _pack_instances(pk, instances, B):
+    ni = pk.ir["num_instance"]
+    lens = np.array([len(instances[0][i]) for i in range(ni)] or [0], dtype=np.uint32)
+    stride = max(1, int(lens.max()))
+    inst = np.zeros((B, max(1, ni), stride, 4), dtype=np.uint64)
+    for b in range(B):
+        assert len(instances[b]) == ni, "Error::InvalidInstances"
+        for i in range(ni):
+            assert len(instances[b][i]) == lens[i]
+            if lens[i]:
+                inst[b, i, :lens[i]] = mont(instances[b][i])
+    return inst, lens, stride
+
+
+def verify_proofs(pk, instances, proofs):
+    """plonk::verify_proof for a batch: instances[b] = list (num_instance) of int lists, proofs[b] = bytes (equal lengths).
+    Returns a list of bools (Ok / Err of the reference's SingleVerifier)."""
+    ctx = pk.ctx
+    B = len(proofs)
+    plen = len(proofs[0])
+    if any(len(p) != plen for p in proofs):
+        raise ValueError("verify_proofs: proofs of one batch must have equal lengths")
+    inst, lens, stride = _pack_instances(pk, instances, B)
+    buf = np.frombuffer(b"".join(proofs) or b"\0", dtype=np.uint8).copy()
+    res = np.zeros(B, dtype=np.uint8)
+    ctx._check(ctx.lib.bz_verify_proofs(ctx.h, pk.h, B, _np_ptr(inst), _np_ptr(lens), stride, _np_ptr(buf), plen, _np_ptr(res)))
+    return [bool(x) for x in res]

@@ -189,6 +189,15 @@ uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yie
 int bz_create_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instances, const uint32_t* instance_lens,
                      uint32_t instance_stride, const void* advice, const void* rand_wide, void* proofs);
 
+/* plonk::verify_proof (SingleVerifier semantics: one verdict per proof) for `batch` proofs of the same circuit
+ * (U: halo2_proofs 0.2.0 src/plonk/verifier.rs and the argument verifiers; reference call sites
+ * /root/reference/benches/board.rs:84, src/circuits/shot.rs:933-940, src/circuits/board.rs:925-932).
+ *   instances : as for bz_create_proofs      proofs : batch x proof_len bytes (host)
+ *   results   : batch bytes, 1 = Ok(()), 0 = Err(_) (malformed point / scalar, wrong length, failed opening)
+ * Point decompression, the instance commitments, compute_s and the final multi-scalar check run on the device. */
+int bz_verify_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instances, const uint32_t* instance_lens,
+                     uint32_t instance_stride, const void* proofs, uint32_t proof_len, uint8_t* results);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,99 @@
+"""GPU parity for verify_proof on the device through the C ABI: accepts what the restated reference
+verifier accepts (oracle and GPU proofs), rejects what it rejects (bit flips in every region of the proof, wrong
+instances, malformed encodings, wrong lengths), one verdict per proof of a mixed batch."""
+import numpy as np
+import pytest
+from tests.util_prover import Job, tiny_circuit
+
+pytestmark = pytest.mark.gpu
+
+
+def _prove(job, pk, indices):
+    from battlezips_halo2_b200.plonk import prover as PR
+    B = len(indices)
+    return PR.create_proofs(pk, [job.instances] * B, np.stack([job.advice] * B), np.stack([job.wide(i) for i in indices]))
+
+
+def _flip(proof, byte, bit=0):
+    b = bytearray(proof)
+    b[byte] ^= 1 << bit
+    return bytes(b)
+
+
+def test_tiny_accepts_and_rejects_like_the_oracle(ctx):
+    from battlezips_halo2_b200.plonk import prover as PR
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=6)
+    good = _prove(job, pk, [0, 1, 2])
+    assert PR.verify_proofs(pk, [job.instances] * 3, good) == [True, True, True]
+    assert PR.verify_proofs(pk, [job.instances], [job.oracle_proof(index=5)]) == [True]
+    # one flipped bit in every 32-byte item of the proof (points, evaluations, u-evaluations, L/R, c, f)
+    proof = good[0]
+    items = len(proof) // 32
+    bad = [_flip(proof, 32 * i + (7 * i) % 31, i % 8) for i in range(items)]
+    got = PR.verify_proofs(pk, [job.instances] * items, bad)
+    exp = [job.verify(p) for p in bad]
+    assert got == exp
+    assert not any(got)
+    # a mixed batch keeps per-proof verdicts
+    assert PR.verify_proofs(pk, [job.instances] * 4, [good[1], bad[3], good[2], bad[-1]]) == [True, False, True, False]
+    # wrong public input
+    assert PR.verify_proofs(pk, [[[12]]], [proof]) == [False] and not job.verify(proof, instances=[[12]])
+    # wrong lengths
+    assert PR.verify_proofs(pk, [job.instances], [proof[:-32]]) == [False]
+    assert PR.verify_proofs(pk, [job.instances], [proof + bytes(32)]) == [False]
+    pk.close(); params.close()
+
+
+def test_malformed_encodings_are_rejected(ctx):
+    from battlezips_halo2_b200.plonk import prover as PR
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=6)
+    proof = _prove(job, pk, [0])[0]
+    p = 0x40000000000000000000000000000000224698fc094cf91b992d30ed00000001
+    G = job.ir["num_advice"]
+    bad = []
+    bad.append(bytes(32) + proof[32:])                                   # identity where a commitment is expected
+    bad.append(b"\xff" * 31 + b"\x7f" + proof[32:])                      # x >= q
+    x_not_on_curve = None
+    for x in range(1, 50):                                              # smallest x with x^3 + 5 a non-residue mod q
+        q = 0x40000000000000000000000000000000224698fc0994a8dd8c46eb2100000001
+        if pow((x ** 3 + 5) % q, (q - 1) // 2, q) != 1:
+            x_not_on_curve = x
+            break
+    bad.append(x_not_on_curve.to_bytes(32, "little") + proof[32:])
+    ev_off = len(proof) - 64                                            # the scalar c: p itself is not canonical
+    bad.append(proof[:ev_off] + p.to_bytes(32, "little") + proof[ev_off + 32:])
+    got = PR.verify_proofs(pk, [job.instances] * len(bad), bad)
+    assert got == [False] * len(bad)
+    assert [job.verify(b) for b in bad] == got
+    pk.close(); params.close()
+
+
+def test_shot_batch_verifies(ctx):
+    """BASELINE config 3 in small: a batch of Shot proofs, every one verified on the device; the oracle agrees on the
+    first, and on a tampered copy."""
+    from battlezips_halo2_b200.circuits import shot_circuit
+    from battlezips_halo2_b200.plonk import prover as PR
+    cs, cfg, asg = shot_circuit(0)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    proofs = _prove(job, pk, list(range(8)))
+    assert PR.verify_proofs(pk, [job.instances] * 8, proofs) == [True] * 8
+    assert job.verify(proofs[0])
+    t = _flip(proofs[3], 1000, 2)
+    assert PR.verify_proofs(pk, [job.instances] * 2, [t, proofs[4]]) == [False, True]
+    assert not job.verify(t)
+    pk.close(); params.close()
+
+
+def test_board_verifies(ctx):
+    from battlezips_halo2_b200.circuits import board_circuit
+    from battlezips_halo2_b200.plonk import prover as PR
+    cs, cfg, asg = board_circuit(0)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    proof = _prove(job, pk, [0])[0]
+    assert PR.verify_proofs(pk, [job.instances], [proof]) == [True]
+    assert PR.verify_proofs(pk, [job.instances], [_flip(proof, 2048)]) == [False]
+    pk.close(); params.close()
