@@ -45,9 +45,16 @@ extern "C" {
     pub fn bz_params_commit(ctx: *mut bz_ctx, p: *mut bz_params, lagrange_basis: c_int, poly: *const c_void, blind: *const c_void, out_affine: *mut c_void) -> c_int;
     // plonk/prover.rs
     pub fn bz_pk_create(ctx: *mut bz_ctx, p: *mut bz_params, cs: *const bz_circuit, fixed_values: *const c_void, sigma_values: *const c_void, out: *mut *mut bz_pk) -> c_int;
+    pub fn bz_pk_create_from_assembly(ctx: *mut bz_ctx, p: *mut bz_params, cs: *const bz_circuit, fixed_values: *const c_void, mapping: *const u32, out: *mut *mut bz_pk) -> c_int;
+    pub fn bz_pk_vk_commitments(ctx: *mut bz_ctx, pk: *mut bz_pk, fixed_commitments: *mut c_void, perm_commitments: *mut c_void) -> c_int;
     pub fn bz_pk_destroy(pk: *mut bz_pk);
     pub fn bz_pk_num_random(pk: *const bz_pk) -> u32;
     pub fn bz_pk_proof_size(pk: *const bz_pk) -> u32;
+    // poly/commitment.rs `Params::new`, pasta_curves `hash_to_curve`
+    pub fn bz_params_new(ctx: *mut bz_ctx, k: u32, curve: c_int, g: *mut c_void, g_lagrange: *mut c_void, w: *mut c_void, u: *mut c_void) -> c_int;
+    pub fn bz_hash_to_curve(ctx: *mut bz_ctx, curve: c_int, domain_prefix: *const c_char, messages: *const c_void, msg_len: u32, count: u64, out_affine: *mut c_void) -> c_int;
+    // plonk/verifier.rs
+    pub fn bz_verify_proofs(ctx: *mut bz_ctx, pk: *mut bz_pk, batch: u32, instances: *const c_void, instance_lens: *const u32, instance_stride: u32, proofs: *const c_void, proof_len: u32, results: *mut u8) -> c_int;
     pub fn bz_create_proofs(ctx: *mut bz_ctx, pk: *mut bz_pk, batch: u32, instances: *const c_void, instance_lens: *const u32, instance_stride: u32, advice: *const c_void, rand_wide: *const c_void, proofs: *mut c_void) -> c_int;
 }
 
