@@ -25,7 +25,7 @@ template <class P> __device__ __forceinline__ Fe<P>* region_ptr(const Regions& r
 
 // ---- interpreter ---------------------------------------------------------------------------------
 enum : uint32_t { OP_PUSH_P = 0, OP_PUSH_S = 1, OP_PUSH_C = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL = 5, OP_NEG = 6,
-                  OP_MULC = 7, OP_ADDC = 8, OP_FOLD = 9, OP_STORE = 10, OP_END = 11, OP_MUL_T_STORE = 12 };
+                  OP_MULC = 7, OP_ADDC = 8, OP_FOLD = 9, OP_STORE = 10, OP_END = 11, OP_MUL_T_STORE = 12, OP_ACC_MULC = 13 };
 constexpr int EVAL_STACK = 10;
 
 template <class P> struct EvalArgs {
@@ -42,6 +42,7 @@ template <class P> struct EvalArgs {
   uint64_t ostride;
   const Fe<P>* tev;              // t_evaluations (for OP_MUL_T_STORE), length tn (power of two)
   uint32_t tn;
+  uint32_t stride_log;           // evaluate at domain points j = i << stride_log only (outputs stay dense, indexed by i)
 };
 
 template <class P>
@@ -52,7 +53,8 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
   const uint32_t N = 1u << a.logN;
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t b = blockIdx.y;
-  if (i >= N) return;
+  if (i >= (N >> a.stride_log)) return;
+  const uint32_t jp = i << a.stride_log;         // the domain point this thread evaluates
   const Fe<P>* pb = a.pbase + (uint64_t)b * a.pstride;
   const Fe<P>* cb = a.consts + (uint64_t)b * a.cstride;
   Fe<P> st[EVAL_STACK];
@@ -62,8 +64,8 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
     const uint32_t ins = s_code[pc];
     const uint32_t op = ins & 15u, x = (ins >> 4) & 0xfffu, y = ins >> 16;
     switch (op) {
-      case OP_PUSH_P: { uint32_t idx = (i + (uint32_t)a.rot[y]) & (N - 1); st[sp++] = fe_load(pb + ((uint64_t)x << a.logN) + idx); break; }
-      case OP_PUSH_S: { uint32_t idx = (i + (uint32_t)a.rot[y]) & (N - 1); st[sp++] = fe_load(a.sbase + ((uint64_t)x << a.logN) + idx); break; }
+      case OP_PUSH_P: { uint32_t idx = (jp + (uint32_t)a.rot[y]) & (N - 1); st[sp++] = fe_load(pb + ((uint64_t)x << a.logN) + idx); break; }
+      case OP_PUSH_S: { uint32_t idx = (jp + (uint32_t)a.rot[y]) & (N - 1); st[sp++] = fe_load(a.sbase + ((uint64_t)x << a.logN) + idx); break; }
       case OP_PUSH_C: st[sp++] = fe_load(cb + (ins >> 4)); break;
       case OP_ADD: --sp; st[sp - 1] = fe_add(st[sp - 1], st[sp]); break;
       case OP_SUB: --sp; st[sp - 1] = fe_sub(st[sp - 1], st[sp]); break;
@@ -73,10 +75,20 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
       case OP_ADDC: st[sp - 1] = fe_add(st[sp - 1], fe_load(cb + (ins >> 4))); break;
       case OP_FOLD: --sp; acc = fe_add(fe_mul(acc, fe_load(cb + (ins >> 4))), st[sp]); break;
       case OP_STORE: --sp; fe_store(a.out + (uint64_t)b * a.ostride + ((uint64_t)(ins >> 4) << a.logN) + i, st[sp]); break;
-      case OP_MUL_T_STORE: fe_store(a.out + (uint64_t)b * a.ostride + i, fe_mul(acc, fe_load(a.tev + (i & (a.tn - 1))))); break;
+      case OP_ACC_MULC: acc = fe_mul(acc, fe_load(cb + (ins >> 4))); break;
+      case OP_MUL_T_STORE: fe_store(a.out + (uint64_t)b * a.ostride + i, fe_mul(acc, fe_load(a.tev + (jp & (a.tn - 1))))); break;
       default: break;
     }
   }
+}
+
+// dst[b][i] += src[b][i]  (i < count): the low-degree part of h(X), interpolated on the half-size coset, joins the rest
+template <class P>
+__global__ void add_low_kernel(Fe<P>* __restrict__ dst, uint64_t dst_stride, const Fe<P>* __restrict__ src, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+  if (i >= count) return;
+  Fe<P>* d = dst + (uint64_t)b * dst_stride + i;
+  fe_store(d, fe_add(fe_load(d), fe_load(src + (uint64_t)b * count + i)));
 }
 
 // ---- 512-bit RNG words -> field elements (pasta Field::random = from_u512) --------------------------

@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <array>
 #include <cstdlib>
+#include <functional>
 #include <map>
 #include <set>
 
@@ -72,10 +73,11 @@ struct PkImpl {
   std::vector<uint64_t> vk_fixed_comm, vk_perm_comm;   // keygen_vk: commit_lagrange(column, Blind::default()) as affine (8 x u64 each)
   DevBuf tev;         // [2^(ext_k-k)]
   // programs
-  DevBuf lk_code, q_code, lk_rot, q_rot;
-  uint32_t lk_ninstr = 0, q_ninstr = 0;
+  DevBuf lk_code, q_code, lk_rot, q_rot, ql_code, ql_rot;   // ql_*: h(X) terms of low degree, evaluated on every 2nd extended point
+  uint32_t lk_ninstr = 0, q_ninstr = 0, ql_ninstr = 0;
+  uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
   // const table layout
-  uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, cstride;
+  uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, C_YP0, cstride;
   std::vector<int> rots;                 // distinct rotations of all queries (+1, -1, last)
   std::map<int, uint32_t> rot_const;     // rotation -> const index of x * omega^rot
   // randomness layout (indices into the per-proof draw stream)
@@ -101,7 +103,7 @@ struct PkImpl {
   // workspace cache
   struct Work {
     uint32_t batch = 0;
-    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac, lk_sorted, lk_err;
+    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, hext_low, hcoef_low, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac, lk_sorted, lk_err;
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
     uint32_t* h_err = nullptr;      // pinned: error word of the device lookup permutation
   } work;
@@ -157,6 +159,7 @@ struct ProgBuilder {
   void mulc(uint32_t c) { code.push_back(encc(OP_MULC, c)); }
   void addc(uint32_t c) { code.push_back(encc(OP_ADDC, c)); }
   void fold(uint32_t c) { code.push_back(encc(OP_FOLD, c)); pop(); }
+  void accmul(uint32_t c) { code.push_back(encc(OP_ACC_MULC, c)); }
   void store(uint32_t k) { code.push_back(encc(OP_STORE, k)); pop(); }
 };
 
@@ -217,61 +220,97 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       BZ_CUDA(cudaMemcpy(pk.lk_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  // ---- h(X) on the extended coset
+  // ---- h(X) on the extended coset:  N(X) = sum_e y^(E-1-e) expr_e(X),  h = N / t.
+  // Every expr_e of a satisfying witness vanishes on the whole domain, so it is divisible by t(X) = X^n - 1 on its own and
+  // expr_e / t has degree < (deg_e - 1) n.  Terms with (deg_e - 1) n <= ext_n / 2 are therefore evaluated on every SECOND
+  // point of the extended coset only (that is the coset of the half-size domain), interpolated by a half-size inverse NTT
+  // and added to the rest in coefficient form: same h(X), about a third fewer field multiplications for Shot / Board.
+  // (For a witness that violates a gate neither variant is a polynomial identity; both proofs are rejected, their bytes differ.)
   {
-    ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
+    struct Term { uint32_t degree; std::function<void(ProgBuilder&)> emit; };
+    std::vector<Term> terms;
+    auto expr_degree = [&](uint32_t lo, uint32_t hi) {
+      std::vector<uint32_t> st;
+      for (uint32_t t = lo; t < hi; ++t) {
+        const Token& k = cs.tokens[t];
+        switch (k.op) {
+          case 0: st.push_back(0); break;
+          case 1: case 2: case 3: st.push_back(1); break;
+          case 4: case 7: break;
+          case 5: { uint32_t r = st.back(); st.pop_back(); st.back() = std::max(st.back(), r); break; }
+          case 6: { uint32_t r = st.back(); st.pop_back(); st.back() += r; break; }
+          default: throw Error(-1, "bad token op");
+        }
+      }
+      return st.back();
+    };
+    auto compressed_degree = [&](const std::vector<std::pair<uint32_t, uint32_t>>& es) { uint32_t d = 0; for (auto& r : es) d = std::max(d, expr_degree(r.first, r.second)); return d; };
     const int last_rot = -((int)cs.bf + 1);
     for (size_t g = 0; g + 1 < cs.gate_off.size(); ++g) {
-      emit_expr(pb, cs, cs.gate_off[g], cs.gate_off[g + 1]);
-      pb.fold(pk.C_Y);
+      const uint32_t lo = cs.gate_off[g], hi = cs.gate_off[g + 1];
+      terms.push_back({expr_degree(lo, hi), [&cs, lo, hi](ProgBuilder& pb) { emit_expr(pb, cs, lo, hi); }});
     }
     if (pk.nsets) {
-      // l0 * (1 - z_0)
-      pb.pc(pk.C_ONE); pb.pp(pk.slot_pz(0), 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      // l_last * (z_l^2 - z_l)
-      uint32_t zl = pk.slot_pz(pk.nsets - 1);
-      pb.pp(zl, 0); pb.pp(zl, 0); pb.mul(); pb.pp(zl, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      // l0 * (z_i - z_{i-1}(w^last X))
-      for (uint32_t i = 1; i < pk.nsets; ++i) {
-        pb.pp(pk.slot_pz(i), 0); pb.pp(pk.slot_pz(i - 1), last_rot); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      }
+      terms.push_back({2, [&pk](ProgBuilder& pb) { pb.pc(pk.C_ONE); pb.pp(pk.slot_pz(0), 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});          // l0 * (1 - z_0)
+      terms.push_back({3, [&pk](ProgBuilder& pb) { uint32_t zl = pk.slot_pz(pk.nsets - 1);                                                               // l_last * (z_l^2 - z_l)
+                                                   pb.pp(zl, 0); pb.pp(zl, 0); pb.mul(); pb.pp(zl, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); }});
+      for (uint32_t i = 1; i < pk.nsets; ++i)                                                                                                            // l0 * (z_i - z_{i-1}(w^last X))
+        terms.push_back({2, [&pk, i, last_rot](ProgBuilder& pb) { pb.pp(pk.slot_pz(i), 0); pb.pp(pk.slot_pz(i - 1), last_rot); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});
       for (uint32_t s = 0; s < pk.nsets; ++s) {
-        uint32_t c0 = s * pk.chunk_len, c1 = std::min<uint32_t>(pk.M, c0 + pk.chunk_len);
-        pb.pp(pk.slot_pz(s), 1);
-        for (uint32_t j = c0; j < c1; ++j) {
-          push_column(pb, pk, cs.perm[j]); pb.ps(shslot_sigma(pk, j), 0); pb.mulc(pk.C_BETA); pb.add(); pb.addc(pk.C_GAMMA); pb.mul();
-        }
-        pb.pp(pk.slot_pz(s), 0);
-        for (uint32_t j = c0; j < c1; ++j) {
-          push_column(pb, pk, cs.perm[j]); pb.ps(shslot_x(pk), 0); pb.mulc(pk.C_BD0 + j); pb.add(); pb.addc(pk.C_GAMMA); pb.mul();
-        }
-        pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+        const uint32_t c0 = s * pk.chunk_len, c1 = std::min<uint32_t>(pk.M, c0 + pk.chunk_len);
+        terms.push_back({c1 - c0 + 2, [&pk, &cs, s, c0, c1](ProgBuilder& pb) {
+          pb.pp(pk.slot_pz(s), 1);
+          for (uint32_t j = c0; j < c1; ++j) { push_column(pb, pk, cs.perm[j]); pb.ps(shslot_sigma(pk, j), 0); pb.mulc(pk.C_BETA); pb.add(); pb.addc(pk.C_GAMMA); pb.mul(); }
+          pb.pp(pk.slot_pz(s), 0);
+          for (uint32_t j = c0; j < c1; ++j) { push_column(pb, pk, cs.perm[j]); pb.ps(shslot_x(pk), 0); pb.mulc(pk.C_BD0 + j); pb.add(); pb.addc(pk.C_GAMMA); pb.mul(); }
+          pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); }});
       }
     }
     for (uint32_t l = 0; l < pk.L; ++l) {
-      uint32_t a = pk.slot_lk(l, 0), sp = pk.slot_lk(l, 1), z = pk.slot_lk(l, 2);
-      pb.pc(pk.C_ONE); pb.pp(z, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      pb.pp(z, 0); pb.pp(z, 0); pb.mul(); pb.pp(z, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      const uint32_t a = pk.slot_lk(l, 0), sp = pk.slot_lk(l, 1), z = pk.slot_lk(l, 2);
+      terms.push_back({2, [&pk, z](ProgBuilder& pb) { pb.pc(pk.C_ONE); pb.pp(z, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});
+      terms.push_back({3, [&pk, z](ProgBuilder& pb) { pb.pp(z, 0); pb.pp(z, 0); pb.mul(); pb.pp(z, 0); pb.sub(); pb.ps(shslot_llast(pk), 0); pb.mul(); }});
       // z(wX)(a'+beta)(s'+gamma) - z(X)(A_theta+beta)(S_theta+gamma)
-      pb.pp(z, 1); pb.pp(a, 0); pb.addc(pk.C_BETA); pb.mul(); pb.pp(sp, 0); pb.addc(pk.C_GAMMA); pb.mul();
-      pb.pp(z, 0);
-      emit_compressed(pb, cs, cs.lookups[l].inputs, pk.C_THETA); pb.addc(pk.C_BETA); pb.mul();
-      emit_compressed(pb, cs, cs.lookups[l].tables, pk.C_THETA); pb.addc(pk.C_GAMMA); pb.mul();
-      pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      // l0 * (a' - s')
-      pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); pb.fold(pk.C_Y);
-      // active * (a' - s')(a' - a'(w^-1 X))
-      pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.pp(a, 0); pb.pp(a, -1); pb.sub(); pb.mul(); pb.ps(shslot_active(pk), 0); pb.mul(); pb.fold(pk.C_Y);
+      const uint32_t dprod = std::max(3u, 1 + compressed_degree(cs.lookups[l].inputs) + compressed_degree(cs.lookups[l].tables)) + 1;
+      terms.push_back({dprod, [&pk, &cs, l, a, sp, z](ProgBuilder& pb) {
+        pb.pp(z, 1); pb.pp(a, 0); pb.addc(pk.C_BETA); pb.mul(); pb.pp(sp, 0); pb.addc(pk.C_GAMMA); pb.mul();
+        pb.pp(z, 0);
+        emit_compressed(pb, cs, cs.lookups[l].inputs, pk.C_THETA); pb.addc(pk.C_BETA); pb.mul();
+        emit_compressed(pb, cs, cs.lookups[l].tables, pk.C_THETA); pb.addc(pk.C_GAMMA); pb.mul();
+        pb.sub(); pb.ps(shslot_active(pk), 0); pb.mul(); }});
+      terms.push_back({2, [&pk, a, sp](ProgBuilder& pb) { pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});                     // l0 * (a' - s')
+      terms.push_back({3, [&pk, a, sp](ProgBuilder& pb) { pb.pp(a, 0); pb.pp(sp, 0); pb.sub(); pb.pp(a, 0); pb.pp(a, -1); pb.sub(); pb.mul(); pb.ps(shslot_active(pk), 0); pb.mul(); }});
     }
-    pb.code.push_back(OP_MUL_T_STORE);
-    BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
-    pk.q_ninstr = (uint32_t)pb.code.size();
-    BZ_CHECK(pk.q_ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
-    pk.q_code.alloc(pb.code.size() * 4);
-    BZ_CUDA(cudaMemcpy(pk.q_code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
-    if (pb.rot_table.empty()) pb.rot_table.push_back(0);
-    pk.q_rot.alloc(pb.rot_table.size() * 4);
-    BZ_CUDA(cudaMemcpy(pk.q_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
+    BZ_CHECK(terms.size() == pk.n_exprs, "internal: expression count mismatch");
+    const char* tier_env = getenv("BZ_QUOTIENT_TIERS");
+    const bool tiers = !(tier_env && atoi(tier_env) == 0) && pk.ext_k > cs.k;
+    const uint32_t low_max_degree = tiers ? (pk.ext_n / 2) / pk.n + 1 : 0;          // (deg - 1) n <= ext_n / 2
+    auto build = [&](bool low, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
+      ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
+      const uint32_t E = (uint32_t)terms.size();
+      int prev = -1;
+      for (uint32_t e = 0; e < E; ++e) {
+        if ((terms[e].degree <= low_max_degree) != low) continue;
+        terms[e].emit(pb);
+        pb.fold(pk.C_YP0 + (prev < 0 ? 1u : e - (uint32_t)prev));          // acc = acc * y^(gap) + expr
+        prev = (int)e;
+      }
+      ninstr = 0;
+      if (prev < 0) return;                                                  // nothing in this tier
+      if ((uint32_t)prev != E - 1) pb.accmul(pk.C_YP0 + (E - 1 - (uint32_t)prev));
+      pb.code.push_back(OP_MUL_T_STORE);
+      BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
+      ninstr = (uint32_t)pb.code.size();
+      BZ_CHECK(ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
+      code.alloc(pb.code.size() * 4);
+      BZ_CUDA(cudaMemcpy(code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
+      if (pb.rot_table.empty()) pb.rot_table.push_back(0);
+      rot.alloc(pb.rot_table.size() * 4);
+      BZ_CUDA(cudaMemcpy(rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
+    };
+    build(false, pk.q_code, pk.q_rot, pk.q_ninstr);
+    build(true, pk.ql_code, pk.ql_rot, pk.ql_ninstr);
+    BZ_CHECK(pk.q_ninstr > 0, "internal: no full-degree term in h(X)");
   }
 }
 
@@ -315,6 +354,8 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.wide.alloc(B * (size_t)pk.R * 64);
   w.hext.alloc(B * en * E);
   w.hcoef.alloc(B * en * E);
+  w.hext_low.alloc(B * (en / 2) * E);
+  w.hcoef_low.alloc(B * (en / 2) * E);
   w.nd.alloc(4 * B * n * E);
   w.consts.alloc(B * (size_t)pk.cstride * E);
   w.extras.alloc(B * 64 * 2 * E);
@@ -558,6 +599,8 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
       pk.C_ROT0 = c;
       for (int r : rs) { pk.rots.push_back(r); pk.rot_const[r] = c++; }
     }
+    pk.n_exprs = cin->n_gate_polys + (pk.nsets ? 2 + (pk.nsets - 1) + pk.nsets : 0) + 5 * pk.L;
+    pk.C_YP0 = c; c += pk.n_exprs + 1;          // y^0 .. y^E
     pk.cstride = c;
     // ---- randomness layout
     uint32_t r = 0;
@@ -1117,7 +1160,12 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     to_coset(G + I, 3 * L + pk.nsets);
   }
   // ---- step 10
-  for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_Y] = t_squeeze(ps[b], F);
+  for (uint32_t b = 0; b < B; ++b) {
+    const HFe y = t_squeeze(ps[b], F);
+    ps[b].consts[pk.C_Y] = y;
+    HFe yp = F.one();
+    for (uint32_t g = 0; g <= pk.n_exprs; ++g) { ps[b].consts[pk.C_YP0 + g] = yp; yp = F.mul(yp, y); }
+  }
   upload_consts();
   desc_off = 0;
   // ---- steps 11-12: h(X)
@@ -1133,9 +1181,22 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       ProfScope prof(C, PROF_QUOTIENT);
       eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr * 4, st>>>(a);
       C->kernel_launches++;
+      if (pk.ql_ninstr) {      // low-degree terms: every second extended point
+        EvalArgs<FpP> al = a;
+        al.code = (const uint32_t*)pk.ql_code.p; al.n_instr = pk.ql_ninstr; al.rot = (const int32_t*)pk.ql_rot.p;
+        al.stride_log = 1; al.out = (DFe*)w.hext_low.p; al.ostride = en / 2;
+        eval_program_kernel<FpP><<<dim3((en / 2 + 127) / 128, B), 128, pk.ql_ninstr * 4, st>>>(al);
+        C->kernel_launches++;
+      }
     }
     NttFusion fu; fu.post_mode = 3;
     ntt_run(C, 0, w.hext.p, w.hcoef.p, pk.ext_k, true, B, fu);
+    if (pk.ql_ninstr) {
+      ntt_run(C, 0, w.hext_low.p, w.hcoef_low.p, pk.ext_k - 1, true, B, fu);
+      ProfScope prof(C, PROF_POLY);
+      add_low_kernel<FpP><<<dim3((en / 2 + 127) / 128, B), 128, 0, st>>>((DFe*)w.hcoef.p, en, (const DFe*)w.hcoef_low.p, en / 2);
+      C->kernel_launches++;
+    }
     std::vector<CommitReq> reqs;
     std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(pk.qdeg));
     for (uint32_t i = 0; i < pk.qdeg; ++i) reqs.push_back({PolyRef{R_HCOEF, i}, false});
