@@ -30,6 +30,7 @@ template <class P> struct NttPassArgs {
   const Fe<P>* tw_lo;
   const Fe<P>* tw_hi;
   uint32_t k_limit;
+  uint32_t zero_stages;              // zero-padded lines: the first log2(L / k_limit) stages only replicate (their second operand is 0)
   uint32_t pre_mode;
   uint32_t post_mode;
   Fe<P> pre[3];
@@ -47,6 +48,8 @@ template <class P> __device__ __forceinline__ void sm_st(uint4* p0, uint4* p1, u
   p0[i] = make_uint4(v.l[0], v.l[1], v.l[2], v.l[3]);
   p1[i] = make_uint4(v.l[4], v.l[5], v.l[6], v.l[7]);
 }
+
+constexpr uint32_t TW_FULL_LOG = 16;     // inter-pass twiddles w_M^e: one table of M entries up to 2^16 (2 MB, L2 resident), lo/hi split above
 
 template <class P>
 __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ NttPassArgs<P> a) {
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
       uint32_t i0 = ((grp << (s + 1)) + pos) << logT | line;
       uint32_t i1 = i0 + (d << logT);
       Fe<P> x = sm_ld<P>(p0, p1, i0);
+      if (s < a.zero_stages) { sm_st<P>(p0, p1, i1, x); continue; }          // x + 0*w, x - 0*w
       Fe<P> y = sm_ld<P>(p0, p1, i1);
       if (pos) y = fe_mul(y, fe_load(a.wsmall + ((uint64_t)pos << (WSMALL_LOG - 1 - s))));
       sm_st<P>(p0, p1, i0, fe_add(x, y));
@@ -108,7 +112,7 @@ __global__ void __launch_bounds__(512) ntt_pass_kernel(const __grid_constant__ N
     if (a.tw_logM) {
       uint64_t e = (uint64_t)k * (v0 + line);       // < M by construction
       if (e) {
-        if (a.tw_logM <= 12) x = fe_mul(x, fe_load(a.tw_lo + e));
+        if (a.tw_logM <= TW_FULL_LOG) x = fe_mul(x, fe_load(a.tw_lo + e));
         else {
           uint32_t elo = (uint32_t)(e & 4095), ehi = (uint32_t)(e >> 12);
           if (elo) x = fe_mul(x, fe_load(a.tw_lo + elo));
@@ -161,11 +165,11 @@ template <class P> static const NttTable& get_tw(Ctx* ctx, int field, bool inver
   if (it != ctx->ntt_tables.end()) return it->second;
   NttTable& t = ctx->ntt_tables[key];
   bzh::Fe w = omega_for(ctx->field(field), logM, inverse);
-  uint32_t nlo = logM <= 12 ? (1u << logM) : 4096u;
+  uint32_t nlo = logM <= (int)TW_FULL_LOG ? (1u << logM) : 4096u;
   t.lo.alloc((size_t)nlo * 32);
   pow_table_kernel<P><<<(nlo + 127) / 128, 128, 0, ctx->stream>>>(t.lo.as<Fe<P>>(), to_dev<P>(w), nlo, 1);
   ctx->kernel_launches++;
-  if (logM > 12) {
+  if (logM > (int)TW_FULL_LOG) {
     uint32_t nhi = 1u << (logM - 12);
     t.hi.alloc((size_t)nhi * 32);
     pow_table_kernel<P><<<(nhi + 127) / 128, 128, 0, ctx->stream>>>(t.hi.as<Fe<P>>(), to_dev<P>(w), nhi, 4096);
@@ -177,6 +181,9 @@ template <class P> static const NttTable& get_tw(Ctx* ctx, int field, bool inver
 
 template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t nlines, int batch, int batch2) {
   uint32_t tile = 1u << (a.logL + a.logT);
+  a.zero_stages = 0;
+  if (a.k_limit && a.k_limit < (1u << a.logL) && (a.k_limit & (a.k_limit - 1)) == 0)
+    while ((a.k_limit << a.zero_stages) < (1u << a.logL)) ++a.zero_stages;
   size_t smem = (size_t)tile * 32;
   int threads = tile >= 4096 ? 512 : (tile >= 512 ? 256 : (tile >= 64 ? (int)tile / 2 : 32));
   static bool attr_set[2] = {false, false};

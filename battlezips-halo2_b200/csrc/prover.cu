@@ -422,10 +422,11 @@ API int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, cons
     if (!c) {
       const char* e = getenv("BZ_FIXED_WINDOW");
       c = e ? (uint32_t)atoi(e) : 0;
-      if (!c) {   // largest window whose two tables stay under ~48 GB (k <= 13: c = 14 at k = 11, c = 13 at k = 12; measured on
-        // B200: 12 -> 1876, 13 -> 1936, 14 -> 1975, 15 -> 2002 Shot proofs/s) / ~80 GB (larger k) and under 2^31 entries
-        const double cap = k <= 13 ? 48e9 : 80e9;
-        for (c = 14; c > 4; --c) {
+      if (!c) {   // largest window whose two tables stay under ~100 GB of the 180 GB (k = 11: c = 15, 77 GB; k = 12: c = 14, 82 GB;
+        // k = 13: c = 13) and under 2^31 entries.  Measured on B200, Shot proofs/s: c = 13 -> 2422, 14 -> 2457, 15 -> 2560
+        // (17 instead of ~18.8 additions per scalar: the top window of a 255-bit scalar is almost never occupied at c = 15).
+        const double cap = 100e9;
+        for (c = std::min(15u, std::max(8u, k + 4)); c > 4; --c) {      // tiny domains: the table build is one thread per point
           double entries = (double)((256 + c - 1) / c) * (double)(1u << (c - 1)) * (double)(n + 2);
           if (2.0 * entries * 64.0 <= cap && entries < 2147483648.0) break;
         }
