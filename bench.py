@@ -29,7 +29,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "shot"))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("BZ_BATCH", "64")), help="proofs per step per GPU (shot / board)")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "3")),
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "4")),
                     help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board)")
     ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
