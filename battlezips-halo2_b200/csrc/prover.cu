@@ -25,6 +25,7 @@ namespace bz {
 
 void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+void lookup_permute_large_run(Ctx* ctx, const void* cin, const void* ctab, void* aout, void* sout, uint32_t usable, uint32_t* d_err);
 
 typedef ::bz::Fe<FpP> DFe;      // device element type of the prover's scalar field (Vesta scalars = Fp)
 
@@ -1014,9 +1015,17 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       eval_program_kernel<FpP><<<dim3((n + 127) / 128, B), 128, pk.lk_ninstr * 4, st>>>(a);
       C->kernel_launches++;
     }
-    const bool device_permute = n <= LKP_MAX_N && !getenv("BZ_LOOKUP_HOST");
+    const bool device_permute = !getenv("BZ_LOOKUP_HOST");      // the host permutation is kept for A/B checks only
     std::vector<HFe> up;
-    if (device_permute) {
+    if (device_permute && n > LKP_MAX_N) {
+      // large domains: device-wide radix sort / scans per (proof, lookup) (lookup.cu)
+      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, 4, st));
+      ProfScope prof(C, PROF_SCAN);
+      for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t l = 0; l < L; ++l)
+          lookup_permute_large_run(C, misc(b, pk.m_cin0 + 2 * l), misc(b, pk.m_cin0 + 2 * l + 1), val(b, pk.slot_lk(l, 0)), val(b, pk.slot_lk(l, 1)), usable, (uint32_t*)w.lk_err.p);
+      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, 4, cudaMemcpyDeviceToHost, st));
+    } else if (device_permute) {
       // device: sort / permute (U: lookup/prover.rs::permute_expression_pair), one CTA per (lookup, proof)
       static bool attr = false;
       if (!attr) { BZ_CUDA(cudaFuncSetAttribute(lookup_permute_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lookup_permute_smem(LKP_MAX_N))); attr = true; }

@@ -124,3 +124,51 @@ def test_keygen_on_device_matches_oracle(ctx, oracle_c, which):
     b = _prove(job, pk2, [2])[0]
     assert a == b == job.oracle_proof(index=2)
     pk2.close(); pk.close(); params.close()
+
+
+def test_lookup_permutation_paths_agree(ctx, monkeypatch):
+    """permute_expression_pair: the one-CTA kernel (n <= 4096), the device-wide radix-sort path (n = 8192) and the C++ host
+    permutation (BZ_LOOKUP_HOST, kept for A/B checks) give the same proof bytes; a lookup input missing from the table is
+    Error::ConstraintSystemFailure on every path."""
+    import battlezips_halo2_b200 as bz
+    from battlezips_halo2_b200.plonk import prover as PR
+    from battlezips_halo2_b200.circuits import board_circuit_scaled
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=6)
+    dev = _prove(job, pk, [4])[0]
+    monkeypatch.setenv("BZ_LOOKUP_HOST", "1")
+    assert _prove(job, pk, [4])[0] == dev == job.oracle_proof(index=4)
+    monkeypatch.delenv("BZ_LOOKUP_HOST")
+    pk.close(); params.close()
+    cs, cfg, asg = board_circuit_scaled(13)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    dev = _prove(job, pk, [1])[0]
+    monkeypatch.setenv("BZ_LOOKUP_HOST", "1")
+    assert _prove(job, pk, [1])[0] == dev
+    monkeypatch.delenv("BZ_LOOKUP_HOST")
+    # break the range-check lookup: input = q_lookup * (...advice...), so poison the advice column it reads on the rows
+    # where the lookup selector is on (a value far outside the 10-bit table)
+    adv = job.advice.copy()
+    lk_in = job.ir["lookups"][0]["input"][0]
+    assert lk_in[0] == "product" and lk_in[1][0] == "fixed"
+    sel_col = lk_in[1][1]
+
+    def first_advice(e):
+        if e[0] == "advice":
+            return e[1]
+        for sub in e[1:]:
+            if isinstance(sub, list):
+                r = first_advice(sub)
+                if r is not None:
+                    return r
+        return None
+    col = first_advice(lk_in)
+    rows = [r for r, v in enumerate(job.asg.fixed[sel_col]) if v][:4]
+    assert rows
+    for r in rows:
+        adv[col, r] = job.V.m(123456789)
+    with pytest.raises(bz.BzError) as e:
+        PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])
+    assert e.value.code == -4
+    pk.close(); params.close()
