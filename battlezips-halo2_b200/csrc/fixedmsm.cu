@@ -295,12 +295,14 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
                             uint32_t n_msm, uint32_t /*chunks*/, void* d_out_affine) {
   cudaStream_t st = ctx->stream;
   if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
-  static int ctas_per_sm = 0;
-  if (!ctas_per_sm) {
-    BZ_CUDA(cudaFuncSetAttribute(fb_accumulate_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FB_MAX_MSM + 1) * 4)));
-    BZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, fb_accumulate_kernel<BP>, FB_THREADS, (FB_MAX_MSM + 1) * 4));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-  }
+  static int ctas_per_sm = 0;          // per template instantiation; several prover lanes (host threads) may race to set it
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(fb_accumulate_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FB_MAX_MSM + 1) * 4));
+    int v = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fb_accumulate_kernel<BP>, FB_THREADS, (FB_MAX_MSM + 1) * 4);
+    ctas_per_sm = v < 1 ? 1 : v;
+  });
   const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
   const uint32_t acc_ctas = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm, acc_threads = acc_ctas * FB_THREADS;
   const uint32_t max_nm = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(FB_MAX_MSM, 0xffffffffull / list_stride));   // flat index fits 32 bits

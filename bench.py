@@ -45,6 +45,7 @@ def parse():
 # 71 IMAD.WIDE.U32(.X) at HALF rate (measured: bz_imad_wide_peak = 0.455 x bz_imad_peak) = 142, plus 25 IMAD.HI + 11 IMAD +
 # 18 IMAD.X at full rate = 54  ->  196  (cuobjdump -sass of fe_mul_raw)
 FMA_PER_MUL = 196
+NCU_DRAM_BYTES_PER_ADD = 129.8      # profiles/r1d_ncu_full_summary.csv, fb_accumulate_kernel
 
 
 def peaks():
@@ -417,6 +418,21 @@ class ProofWorkload:
     def step_e2e(self):
         return self._run(False)
 
+    def single_latency(self, reps=7):
+        """latency of ONE proof (batch 1, one lane, device-resident inputs): median wall ms of `reps` calls"""
+        import ctypes
+        lane = self.lanes[0]
+        c = lane["ctx"]
+        out = np.zeros((1, lane["pk"].proof_size), dtype=np.uint8)
+        ts = []
+        for _ in range(reps + 2):
+            t0 = time.perf_counter()
+            c._check(c.lib.bz_create_proofs(c.h, lane["pk"].h, 1, lane["d"][0].ptr, self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
+                                            lane["d"][1].ptr, lane["d"][2].ptr, out.ctypes.data_as(ctypes.c_void_p)))
+            ts.append(1e3 * (time.perf_counter() - t0))
+        assert bytes(out[0]) == bytes(lane["proofs"][0]), "single-proof call differs from the batched proof"
+        return float(np.median(ts[2:]))
+
     def step_profile(self):
         lane = self.lanes[0]
         self._lane_run(lane, [d.ptr for d in lane["d"]])
@@ -618,8 +634,12 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
         tot_ms, cnt = prof[tag]
         avg_s = tot_ms / cnt / 1e3
         ach = alg_bytes / avg_s / 1e9
+        # DRAM bytes per launch from the committed ncu --set full capture of this kernel (profiles/): fb_accumulate moves
+        # 129.8 B per mixed addition (dram__bytes_read + write = 324.6 MB for 2.50 M additions, r1d) -- two 32 B sectors of
+        # the table entry plus sector over-fetch on the entry list -- against 64 B algorithmic
+        traffic = (adds_total / cnt) * NCU_DRAM_BYTES_PER_ADD if tag == "fixed_msm" and adds_total else None
         roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
+                "traffic": traffic, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
                 "share_of_step": tot_ms / prof_ms, "measured": "single-lane pass of the same steps, CUDA-event scopes in the library",
                 "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
     cpu = None
@@ -633,7 +653,8 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
         "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "per-step working set (tables + batch) larger than L2" if isinstance(wl, ProofWorkload) else "inputs < L2; not flushed"},
         "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
-        "verified": getattr(wl, "check", lambda: None)(), "verify": getattr(wl, "verify_info", None)}
+        "verified": getattr(wl, "check", lambda: None)(), "verify": getattr(wl, "verify_info", None),
+        "single_proof_ms": wl.single_latency() if hasattr(wl, "single_latency") and rank == 0 else None}
 
 
 def main():
@@ -675,7 +696,7 @@ def main():
             if hasattr(w2, "close"):
                 w2.close()
             if r is not None:
-                extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "int_pipe", "verified", "verify")}
+                extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "int_pipe", "verified", "verify", "single_proof_ms")}
     if rank == 0:
         if extras:
             line["extras"] = extras

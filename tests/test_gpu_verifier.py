@@ -97,3 +97,28 @@ def test_board_verifies(ctx):
     assert PR.verify_proofs(pk, [job.instances], [proof]) == [True]
     assert PR.verify_proofs(pk, [job.instances], [_flip(proof, 2048)]) == [False]
     pk.close(); params.close()
+
+
+def test_shot_batch_config3_shape(ctx):
+    """BASELINE config 3 in small (the bench runs the full width): 128 independent Shot proofs in one call -- 8 distinct
+    witnesses (board pattern, shot cell, hit bit), every proof its own RNG stream, one proving key.  Size-independent
+    properties: every proof is accepted by verify_proof on the device, all proofs are distinct, a proof is rejected under
+    another job's public inputs; one member is byte-compared with the oracle prover."""
+    from battlezips_halo2_b200.circuits import shot_circuit
+    from battlezips_halo2_b200.plonk import prover as PR
+    jobs = [shot_circuit(i) for i in range(8)]
+    job = Job(jobs[0][0], jobs[0][2])
+    params, pk = job.device_keys(ctx)
+    B = 128
+    per_job = [np.stack([job.V.arr(col) for col in jobs[j][2].advice]) for j in range(8)]
+    advice = np.stack([per_job[b % 8] for b in range(B)])
+    instances = [jobs[b % 8][2].instance for b in range(B)]
+    wide = np.stack([job.wide(1000 + b) for b in range(B)])
+    proofs = PR.create_proofs(pk, instances, advice, wide)
+    assert PR.verify_proofs(pk, instances, proofs) == [True] * B
+    assert len(set(proofs)) == B
+    b = 77
+    assert proofs[b] == job.oracle_proof(index=1000 + b, advice=advice[b], instances=instances[b])
+    other = next(j for j in range(8) if jobs[j][2].instance != instances[b])
+    assert PR.verify_proofs(pk, [jobs[other][2].instance], [proofs[b]]) == [False]
+    pk.close(); params.close()
