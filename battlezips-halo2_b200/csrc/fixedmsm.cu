@@ -259,9 +259,9 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fb_accumulate_kernel(const Affi
 }
 
 // fold the partials of each MSM and normalise: one CTA per MSM -> affine (64 B), identity = zeros
-template <class BP>
+template <class BP, bool XYZZ_OUT>
 __global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
-                                 uint32_t n_msm, uint32_t acc_threads, Affine<BP>* __restrict__ out) {
+                                 uint32_t n_msm, uint32_t acc_threads, void* __restrict__ out_v) {
   extern __shared__ uint32_t fb_off[];
   __shared__ uint32_t wsum[33];
   __shared__ Xyzz<BP> sh[FB_FOLD_THREADS];
@@ -285,14 +285,20 @@ __global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>
     __syncthreads();
   }
   if (tid == 0) {
-    Affine<BP> r = xyzz_to_affine(sh[0]);
-    fe_store(&out[m].x, r.x); fe_store(&out[m].y, r.y);
+    if (XYZZ_OUT) {
+      Xyzz<BP>* o = reinterpret_cast<Xyzz<BP>*>(out_v) + m;
+      fe_store(&o->x, sh[0].x); fe_store(&o->y, sh[0].y); fe_store(&o->zz, sh[0].zz); fe_store(&o->zzz, sh[0].zzz);
+    } else {
+      Affine<BP>* out = reinterpret_cast<Affine<BP>*>(out_v);
+      Affine<BP> r = xyzz_to_affine(sh[0]);
+      fe_store(&out[m].x, r.x); fe_store(&out[m].y, r.y);
+    }
   }
 }
 
 template <class BP, class SP>
 static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_main, uint32_t n_main, const void* const* d_extra,
-                            uint32_t n_msm, uint32_t /*chunks*/, void* d_out_affine) {
+                            uint32_t n_msm, uint32_t /*chunks*/, void* d_out, bool xyzz_out) {
   cudaStream_t st = ctx->stream;
   if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
   static int ctas_per_sm = 0;          // per template instantiation; several prover lanes (host threads) may race to set it
@@ -322,7 +328,8 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
       fb_decode_kernel<SP><<<dim3((fb.npts + FB_THREADS - 1) / FB_THREADS, nm), FB_THREADS, 0, st>>>(
           fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main + m0, n_main, d_extra ? (const Fe<SP>* const*)d_extra + m0 : nullptr, lists, list_stride, counts);
       fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, st>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
-      fb_fold_kernel<BP><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out_affine + m0);
+      if (xyzz_out) fb_fold_kernel<BP, true><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Xyzz<BP>*)d_out + m0);
+      else fb_fold_kernel<BP, false><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out + m0);
     }
     ctx->kernel_launches += 3;
   }
@@ -330,12 +337,12 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
 }
 
 void fixed_msm_run(Ctx* ctx, const FixedBase& fb, const void* const* d_main, uint32_t n_main, const void* const* d_extra,
-                   uint32_t n_msm, uint32_t chunks, void* d_out_affine) {
+                   uint32_t n_msm, uint32_t chunks, void* d_out, bool xyzz_out) {
   if (!n_msm) return;
   BZ_CHECK(n_main <= fb.npts, "fixed msm: more scalars than table points");
   if (chunks < 1) chunks = 1;
-  if (fb.curve == 0) fixed_msm_run_t<FqP, FpP>(ctx, fb, d_main, n_main, d_extra, n_msm, chunks, d_out_affine);
-  else fixed_msm_run_t<FpP, FqP>(ctx, fb, d_main, n_main, d_extra, n_msm, chunks, d_out_affine);
+  if (fb.curve == 0) fixed_msm_run_t<FqP, FpP>(ctx, fb, d_main, n_main, d_extra, n_msm, chunks, d_out, xyzz_out);
+  else fixed_msm_run_t<FpP, FqP>(ctx, fb, d_main, n_main, d_extra, n_msm, chunks, d_out, xyzz_out);
 }
 
 }  // namespace bz

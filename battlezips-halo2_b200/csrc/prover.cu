@@ -361,7 +361,7 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.consts.alloc(B * (size_t)pk.cstride * E);
   w.extras.alloc(B * 64 * 2 * E);
   w.evalout.alloc(B * (pk.evals.size() + pk.point_sets.size() + 8) * E);
-  w.commits.alloc(B * 64 * 64);
+  w.commits.alloc(B * 64 * 128);
   w.ptrs.alloc(B * 64 * 2 * sizeof(void*));
   w.descs.alloc(64 * 1024);
   w.adv_in.alloc(1);
@@ -369,7 +369,7 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.lk_err.alloc(64);
   if (!w.h_err) BZ_CUDA(cudaMallocHost(&w.h_err, 64));
   if (w.h_pinned) cudaFreeHost(w.h_pinned);
-  w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(64 * 64, (pk.evals.size() + 16) * E)), 1 << 20);
+  w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(64 * 128, (pk.evals.size() + 16) * E)), 1 << 20);
   BZ_CUDA(cudaMallocHost(&w.h_pinned, w.h_pinned_bytes));
   w.batch = B;
 }
@@ -849,7 +849,7 @@ struct Prover {
     bool lag = reqs[0].lagrange;
     std::vector<void*> mainp((size_t)B * nr), extrap((size_t)B * nr);
     std::vector<HFe> ex((size_t)B * nr * 2, F.zero());
-    BZ_CHECK((size_t)B * nr * 2 * 32 <= w.extras.bytes && (size_t)B * nr * 2 * sizeof(void*) <= w.ptrs.bytes && (size_t)B * nr * 64 <= w.commits.bytes,
+    BZ_CHECK((size_t)B * nr * 2 * 32 <= w.extras.bytes && (size_t)B * nr * 2 * sizeof(void*) <= w.ptrs.bytes && (size_t)B * nr * 128 <= w.commits.bytes,
              "commit batch too large for the workspace");
     for (uint32_t b = 0; b < B; ++b)
       for (uint32_t i = 0; i < nr; ++i) {
@@ -873,7 +873,7 @@ struct Prover {
       BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
       BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + n_msm, extrap.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
       uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / std::max(1u, n_msm))));
-      fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + n_msm), n_msm, chunks, w.commits.p);
+      fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + n_msm), n_msm, chunks, w.commits.p, true);
       return;
     }
     const uint32_t npts = fb.npts, nextra = npts - n;
@@ -887,12 +887,38 @@ struct Prover {
     }
     jac_to_affine_run(C, pk.params->curve, w.msm_jac.p, w.commits.p, n_msm);
   }
+  // Commitments come back unnormalised from the table MSM (XYZZ, 128 B): one batched inversion on the host for the
+  // whole call (Montgomery's trick, ~9 host multiplications per point) instead of a single-thread Fermat chain per
+  // commitment on the device (~0.1 ms of latency per launch).  The bucket-MSM path (large k) returns affine points.
   void read_points(uint32_t n_msm, uint32_t nr, std::vector<std::vector<HostPoint>>& pts) {
-    BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.commits.p, (size_t)n_msm * 64, cudaMemcpyDeviceToHost, st));
+    const bool xyzz = pk.params->use_tables;
+    BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.commits.p, (size_t)n_msm * (xyzz ? 128 : 64), cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
     const uint64_t* h = (const uint64_t*)w.h_pinned;
-    for (uint32_t b = 0; b < B; ++b)
-      for (uint32_t i = 0; i < nr; ++i) affine_to_host(Fq, h + ((size_t)b * nr + i) * 8, pts[b][i]);
+    if (!xyzz) {
+      for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t i = 0; i < nr; ++i) affine_to_host(Fq, h + ((size_t)b * nr + i) * 8, pts[b][i]);
+      return;
+    }
+    std::vector<HFe> pre(n_msm);
+    HFe acc = Fq.one();
+    for (uint32_t j = 0; j < n_msm; ++j) {
+      HFe zzz; memcpy(zzz.l, h + (size_t)j * 16 + 12, 32);
+      pre[j] = acc;
+      if (!zzz.is_zero()) acc = Fq.mul(acc, zzz);
+    }
+    HFe inv = Fq.inv(acc);
+    for (int j = (int)n_msm - 1; j >= 0; --j) {
+      HFe x, y, zz, zzz;
+      memcpy(x.l, h + (size_t)j * 16, 32); memcpy(y.l, h + (size_t)j * 16 + 4, 32); memcpy(zz.l, h + (size_t)j * 16 + 8, 32); memcpy(zzz.l, h + (size_t)j * 16 + 12, 32);
+      HostPoint& p = pts[j / nr][j % nr];
+      if (zzz.is_zero()) { p.identity = true; memset(p.x, 0, 32); memset(p.y, 0, 32); continue; }
+      const HFe zi3 = Fq.mul(inv, pre[j]);             // 1 / zzz
+      inv = Fq.mul(inv, zzz);
+      const HFe t = Fq.mul(zz, zi3), zi2 = Fq.sqr(t);  // (zz / zzz)^2 = 1 / zz
+      p.identity = false;
+      Fq.to_repr(Fq.mul(x, zi2), p.x); Fq.to_repr(Fq.mul(y, zi3), p.y);
+    }
   }
 
   void launch_copy(const std::vector<CopyDesc>& d, uint64_t len) {
