@@ -73,6 +73,7 @@ def load_library():
         "bz_best_multiexp": (i32, [vp, i32, vp, vp, u64, vp]),
         "bz_msm_dev": (i32, [vp, i32, vp, vp, u64, vp, i32]),
         "bz_batch_normalize_dev": (i32, [vp, i32, vp, vp, u64]),
+        "bz_point_sum_dev": (i32, [vp, i32, vp, u32, vp]),
         "bz_best_fft": (i32, [vp, i32, vp, vp, u32]),
         "bz_ntt_dev": (i32, [vp, i32, vp, vp, u32, i32, i32]),
         "bz_lagrange_to_coeff_dev": (i32, [vp, i32, vp, vp, u32, i32]),

@@ -6,6 +6,7 @@
 namespace bz {
 void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+void jac_sum_run(Ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine);
 void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
 void curve_op_run(Ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n);
 
@@ -257,6 +258,14 @@ __attribute__((visibility("default"))) int bz_best_multiexp(bz_ctx* ctx, int cur
     bz::msm_run(&ctx->c, curve, ds.p, db.p, (uint32_t)n, dout.p, 0);
     BZ_CUDA(cudaMemcpyAsync(out_jac, dout.p, 96, cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+__attribute__((visibility("default"))) int bz_point_sum_dev(bz_ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    BZ_CHECK(d_jac && d_out_affine && count >= 1 && count <= 4096, "point sum: bad arguments");
+    bz::jac_sum_run(&ctx->c, curve, d_jac, count, d_out_affine);
   });
 }
 

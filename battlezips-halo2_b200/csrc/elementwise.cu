@@ -48,6 +48,26 @@ __global__ void curve_op_kernel(int op, const Affine<BP>* __restrict__ a, const 
   fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
 }
 
+// sum of `count` Jacobian points (the all-gathered partials of a point-range-split MSM) -> one affine point; one thread:
+// count is the number of GPUs
+template <class BP>
+__global__ void jac_sum_kernel(const Jac<BP>* __restrict__ in, uint32_t count, Affine<BP>* __restrict__ out) {
+  if (blockIdx.x || threadIdx.x) return;
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t i = 0; i < count; ++i) {
+    Jac<BP> p; p.x = fe_load(&in[i].x); p.y = fe_load(&in[i].y); p.z = fe_load(&in[i].z);
+    acc = xyzz_add(acc, jac_to_xyzz(p));
+  }
+  Affine<BP> r = xyzz_to_affine(acc);
+  fe_store(&out->x, r.x); fe_store(&out->y, r.y);
+}
+void jac_sum_run(Ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine) {
+  if (curve == 0) jac_sum_kernel<FqP><<<1, 32, 0, ctx->stream>>>((const Jac<FqP>*)d_jac, count, (Affine<FqP>*)d_out_affine);
+  else jac_sum_kernel<FpP><<<1, 32, 0, ctx->stream>>>((const Jac<FpP>*)d_jac, count, (Affine<FpP>*)d_out_affine);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+
 void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
   if (!n) return;
   unsigned blocks = (unsigned)((n + 127) / 128);

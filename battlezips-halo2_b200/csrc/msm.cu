@@ -97,7 +97,7 @@ __global__ void msm_segmap_kernel(const uint32_t* __restrict__ nseg, const uint3
 }
 
 template <class BP>
-__global__ void __launch_bounds__(128) msm_segment_kernel(const Affine<BP>* __restrict__ bases, const uint32_t* __restrict__ sorted,
+__global__ void __launch_bounds__(128, 4) msm_segment_kernel(const Affine<BP>* __restrict__ bases, const uint32_t* __restrict__ sorted,
                                   const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
                                   const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff,
                                   const uint32_t* __restrict__ seg_bucket, uint32_t total_buckets, uint32_t max_segs,
@@ -108,11 +108,21 @@ __global__ void __launch_bounds__(128) msm_segment_kernel(const Affine<BP>* __re
   uint32_t gb = seg_bucket[s];
   uint32_t j0 = (s - segoff[gb]) * SEG;
   uint32_t off = offsets[gb] + j0, cnt = min(SEG, counts[gb] - j0);
+  // software pipeline: the base point of entry j+1 (and the index of entry j+2) are in flight while addition j runs, so
+  // the dependent  sorted[] -> bases[]  DRAM round trips overlap the ~10 field multiplications of the addition
   Xyzz<BP> acc = xyzz_identity<BP>();
+  const uint32_t* ent = sorted + off;
+  uint32_t e = ent[0], e_n = cnt > 1 ? ent[1] : 0u;
+  Affine<BP> pt = aff_load(bases + (e & 0x7fffffffu));
   for (uint32_t j = 0; j < cnt; ++j) {
-    uint32_t e = sorted[off + j];
-    Affine<BP> pt = aff_load(bases + (e & 0x7fffffffu));
+    const bool more = j + 1 < cnt;
+    Affine<BP> pt_n;
+    uint32_t e_nn = 0;
+    if (more) pt_n = aff_load(bases + (e_n & 0x7fffffffu));
+    if (j + 2 < cnt) e_nn = ent[j + 2];
     xyzz_add_mixed_signed(acc, pt, (e >> 31) != 0);
+    if (more) pt = pt_n;
+    e = e_n; e_n = e_nn;
   }
   Xyzz<BP>* o = partial + s;
   fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);

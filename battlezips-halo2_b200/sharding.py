@@ -54,3 +54,14 @@ def allgather_point_sum(local_jac, normalize, add, device=None, group=None):
     for i in range(1, world):
         acc = add(acc, aff[i])
     return acc
+
+
+def allgather_point_sum_dev(ctx, curve, jac_tensor, gathered, out_affine, group=None):
+    """Device-resident form of `allgather_point_sum` for the NCCL path: `jac_tensor` (12 int64 on the GPU, written by
+    bz_msm_dev), `gathered` (world x 12) and `out_affine` (8) are torch CUDA tensors allocated once by the caller.  One
+    NCCL all-gather of 96 B per rank, then one kernel (bz_point_sum_dev) adds the partials -- no host round trip."""
+    import ctypes
+    import torch.distributed as dist
+    dist.all_gather_into_tensor(gathered, jac_tensor, group=group)
+    ctx._check(ctx.lib.bz_point_sum_dev(ctx.h, curve, ctypes.c_void_p(gathered.data_ptr()), gathered.shape[0], ctypes.c_void_p(out_affine.data_ptr())))
+    return out_affine

@@ -161,6 +161,7 @@ class MsmWorkload:
             sc, ba = self.host_inputs(0)                      # same global input on every rank
             lo, hi = shard_range(self.n, rank, world)
             self.n_total, self.n = self.n, hi - lo
+            self.full = (sc, ba) if rank == 0 else None
             self.scalars, self.bases = np.ascontiguousarray(sc[lo:hi]), np.ascontiguousarray(ba[lo:hi])
             self.scaling = "strong"
         else:
@@ -171,28 +172,42 @@ class MsmWorkload:
         self.d_scalars = ctx.to_device(self.scalars)
         self.d_bases = ctx.to_device(self.bases)
         self.d_out = ctx.alloc(96)
+        if world > 1:
+            self.t_jac = torch.zeros(12, dtype=torch.int64, device="cuda")
+            self.t_all = torch.zeros((world, 12), dtype=torch.int64, device="cuda")
+            self.t_sum = torch.zeros(8, dtype=torch.int64, device="cuda")
         self.h2d, self.d2h = self.n * 96, 96
 
     def _combine(self):
-        """all-gather the 96 B Jacobian partials over NCCL and add them on the device (bz_curve_op)"""
-        from battlezips_halo2_b200.sharding import allgather_point_sum
-        from battlezips_halo2_b200 import arithmetic as ar
-        c = self.ctx
-        jac = self.d_out.download((12,))
+        """all-gather the 96 B Jacobian partials over NCCL and add them on the device (bz_point_sum_dev); no host round trip"""
+        from battlezips_halo2_b200.sharding import allgather_point_sum_dev
+        allgather_point_sum_dev(self.ctx, self.curve, self.t_jac, self.t_all, self.t_sum)
 
-        def normalize(j):
-            d_j = c.to_device(j); d_a = c.alloc(64 * len(j))
-            c._check(c.lib.bz_batch_normalize_dev(c.h, self.curve, d_j.ptr, d_a.ptr, len(j)))
-            out = d_a.download((len(j), 8)); d_j.free(); d_a.free()
-            return out
-        self.result = allgather_point_sum(jac, normalize, lambda a, b: ar.curve_op(c, self.curve, "add", a, b)[0], device="cuda")
+    def result_affine(self):
+        return self.t_sum.cpu().numpy().view(np.uint64)
+
+    def check(self):
+        """N > 1: the all-gathered, summed result equals the un-split MSM of the whole input computed on rank 0's GPU"""
+        if self.world == 1 or self.full is None:
+            return None
+        c = self.ctx
+        sc, ba = self.full
+        d_s, d_b, d_j, d_a = c.to_device(sc), c.to_device(ba), c.alloc(96), c.alloc(64)
+        c._check(c.lib.bz_msm_dev(c.h, self.curve, d_s.ptr, d_b.ptr, self.n_total, d_j.ptr, 0))
+        c._check(c.lib.bz_batch_normalize_dev(c.h, self.curve, d_j.ptr, d_a.ptr, 1))
+        exp = d_a.download((8,))
+        for d in (d_s, d_b, d_j, d_a):
+            d.free()
+        return bool(np.array_equal(exp, self.result_affine()))
 
     def step_device(self):
+        import ctypes
         c = self.ctx
-        c._check(c.lib.bz_msm_dev(c.h, self.curve, self.d_scalars.ptr, self.d_bases.ptr, self.n, self.d_out.ptr, 0))
         if self.world > 1:
+            c._check(c.lib.bz_msm_dev(c.h, self.curve, self.d_scalars.ptr, self.d_bases.ptr, self.n, ctypes.c_void_p(self.t_jac.data_ptr()), 0))
             self._combine()
             return self.n_total / self.world       # bench multiplies by world: total points once per step
+        c._check(c.lib.bz_msm_dev(c.h, self.curve, self.d_scalars.ptr, self.d_bases.ptr, self.n, self.d_out.ptr, 0))
         return self.n
 
     def step_e2e(self):
@@ -202,7 +217,8 @@ class MsmWorkload:
         c._check(c.lib.bz_best_multiexp(c.h, self.curve, ctypes.c_void_p(self.h_scalars.data_ptr()),
                                         ctypes.c_void_p(self.h_bases.data_ptr()), self.n, out.ctypes.data_as(ctypes.c_void_p)))
         if self.world > 1:
-            self.d_out.upload(out)
+            import torch
+            self.t_jac.copy_(torch.from_numpy(out.view(np.int64)))
             self._combine()
             return self.n_total / self.world
         return self.n

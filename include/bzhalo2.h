@@ -85,6 +85,10 @@ int bz_best_multiexp(bz_ctx* ctx, int curve, const void* coeffs, const void* bas
 /* device-resident variant (all pointers from bz_dev_alloc); window_bits = 0 picks automatically */
 int bz_msm_dev(bz_ctx* ctx, int curve, const void* d_coeffs, const void* d_bases, uint64_t n, void* d_out_jac,
                int window_bits);
+/* Sum of `count` Jacobian points -> one affine point, all device pointers: the local half of the one real multi-GPU
+ * exchange on this path -- a large MSM split by point range leaves one 96 B partial per rank; NCCL all-gathers them
+ * (it has no elliptic-curve reduction) and every rank adds them here. */
+int bz_point_sum_dev(bz_ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine);
 /* group::Curve::batch_normalize: n Jacobian -> n affine (device pointers) */
 int bz_batch_normalize_dev(bz_ctx* ctx, int curve, const void* d_jac, void* d_affine, uint64_t n);
 

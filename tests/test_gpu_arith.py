@@ -196,3 +196,26 @@ def test_best_multiexp_large_skewed(ctx, oracle_c):
     got = ar.best_multiexp(ctx, curve, sm, bm)
     exp = co.best_multiexp(curve, sm, bm)
     assert np.array_equal(co.to_affine(curve, got), co.to_affine(curve, exp))
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_point_sum_dev(curve, ctx, oracle_c):
+    """bz_point_sum_dev: the local half of the multi-GPU MSM exchange (sum of the all-gathered Jacobian partials)."""
+    import ctypes
+    co = oracle_c
+    C, sf, bf = co.CURVES[curve]
+    pts = _bases(co, curve, 6)
+    pts[2] = None                                  # an identity partial (a rank whose range summed to zero)
+    pts[4] = C.neg(pts[3])                         # two partials that cancel
+    aff = co.points_to_mont(curve, pts)
+    one = np.frombuffer(co.FIELDS[bf].to_mont_bytes(1), dtype=np.uint64)
+    jac = np.concatenate([aff, np.repeat(one[None, :], len(pts), axis=0)], axis=1).copy()
+    jac[2, 8:] = 0                                 # z = 0
+    d_j, d_o = ctx.to_device(jac), ctx.alloc(64)
+    ctx._check(ctx.lib.bz_point_sum_dev(ctx.h, curve, d_j.ptr, len(pts), d_o.ptr))
+    got = d_o.download((8,))
+    exp = None
+    for p in pts:
+        exp = C.add(exp, p)
+    assert co.points_from_mont(curve, got[None, :])[0] == exp
+    d_j.free(); d_o.free()
