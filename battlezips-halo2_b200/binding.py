@@ -64,6 +64,7 @@ def load_library():
         "bz_profile_counter": (i32, [vp, i32, ctypes.POINTER(u64), i32]),
         "bz_imad_peak": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
         "bz_imad_wide_peak": (i32, [vp, ctypes.POINTER(ctypes.c_double)]),
+        "bz_dfma_peak": (i32, [vp, i32, ctypes.POINTER(ctypes.c_double)]),
         "bz_dev_alloc": (i32, [vp, ctypes.c_size_t, ctypes.POINTER(vp)]),
         "bz_dev_free": (i32, [vp, vp]),
         "bz_h2d": (i32, [vp, vp, vp, ctypes.c_size_t]),
@@ -182,6 +183,11 @@ class Context:
     def imad_peak(self):
         v = ctypes.c_double()
         self._check(self.lib.bz_imad_peak(self.h, ctypes.byref(v)))
+        return v.value
+
+    def dfma_peak(self, mixed=False):
+        v = ctypes.c_double()
+        self._check(self.lib.bz_dfma_peak(self.h, 1 if mixed else 0, ctypes.byref(v)))
         return v.value
 
     def imad_wide_peak(self):

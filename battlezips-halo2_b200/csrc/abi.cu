@@ -155,6 +155,53 @@ __global__ void imad_wide_peak_kernel(unsigned long long* out, uint32_t iters) {
   }
   out[blockIdx.x * blockDim.x + threadIdx.x] = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
 }
+// FP64 pipe probes for the round-2 question "can a 52-bit-limb DFMA multiplier run beside the IMAD one?":
+// mode 2 = DFMA chains only, mode 3 = IMAD.WIDE and DFMA chains interleaved in the same warp (ops counted together)
+__global__ void dfma_peak_kernel(double* out, uint32_t iters, int mixed) {
+  double d0 = threadIdx.x + 1.0, d1 = d0 * 3, d2 = d0 * 5, d3 = d0 * 7, d4 = d0 * 11, d5 = d0 * 13, d6 = d0 * 17, d7 = d0 * 19;
+  const double m = 1.0000001 + blockIdx.x * 1e-9, c = 0.5;
+  unsigned long long a0 = threadIdx.x + 1, a1 = a0 * 3, a2 = a0 * 5, a3 = a0 * 7, a4 = a0 * 11, a5 = a0 * 13, a6 = a0 * 17, a7 = a0 * 19;
+  const uint32_t mi = blockIdx.x * 2 + 1;
+  for (uint32_t i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      d0 = fma(d0, m, c); d1 = fma(d1, m, c); d2 = fma(d2, m, c); d3 = fma(d3, m, c);
+      d4 = fma(d4, m, c); d5 = fma(d5, m, c); d6 = fma(d6, m, c); d7 = fma(d7, m, c);
+      if (mixed) {
+        a0 = (unsigned long long)(uint32_t)a0 * mi + a0; a1 = (unsigned long long)(uint32_t)a1 * mi + a1;
+        a2 = (unsigned long long)(uint32_t)a2 * mi + a2; a3 = (unsigned long long)(uint32_t)a3 * mi + a3;
+        a4 = (unsigned long long)(uint32_t)a4 * mi + a4; a5 = (unsigned long long)(uint32_t)a5 * mi + a5;
+        a6 = (unsigned long long)(uint32_t)a6 * mi + a6; a7 = (unsigned long long)(uint32_t)a7 * mi + a7;
+      }
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = d0 + d1 + d2 + d3 + d4 + d5 + d6 + d7 + (double)(a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7);
+}
+__attribute__((visibility("default"))) int bz_dfma_peak(bz_ctx* ctx, int mixed_with_imad_wide, double* ops_per_sec) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(ops_per_sec, "null out");
+    const int blocks = ctx->c.sm_count * 8, threads = 256;
+    const uint32_t iters = 2048;
+    bz::DevBuf out; out.alloc((size_t)blocks * threads * 8);
+    cudaStream_t st = ctx->c.stream;
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.as<double>(), 64, mixed_with_imad_wide);
+    double best = 0;
+    for (int rep = 0; rep < 3; ++rep) {
+      cudaEventRecord(e0, st);
+      dfma_peak_kernel<<<blocks, threads, 0, st>>>(out.as<double>(), iters, mixed_with_imad_wide);
+      cudaEventRecord(e1, st);
+      BZ_CUDA(cudaEventSynchronize(e1));
+      float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+      double ops = (double)blocks * threads * iters * 64.0 * (mixed_with_imad_wide ? 2.0 : 1.0);
+      best = std::max(best, ops / (ms * 1e-3));
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->c.kernel_launches += 4;
+    *ops_per_sec = best;
+  });
+}
+
 __attribute__((visibility("default"))) int bz_imad_wide_peak(bz_ctx* ctx, double* imad_wide_per_sec) {
   BZ_TRY(ctx, {
     BZ_CHECK(imad_wide_per_sec, "null out");

@@ -65,6 +65,9 @@ int bz_imad_peak(bz_ctx* ctx, double* imad_per_sec);
 /* same for the 32x32+64->64 form (IMAD.WIDE.U32), which is what the field multiplication is built from */
 int bz_imad_wide_peak(bz_ctx* ctx, double* imad_wide_per_sec);
 
+/* FP64-pipe probe: DFMA/s alone (mixed = 0) or DFMA + IMAD.WIDE per second issued from the same warps (mixed = 1) */
+int bz_dfma_peak(bz_ctx* ctx, int mixed_with_imad_wide, double* ops_per_sec);
+
 /* ---- device memory (library-owned, freed by bz_dev_free or with the context) ------------------- */
 int bz_dev_alloc(bz_ctx* ctx, size_t bytes, void** dptr);
 int bz_dev_free(bz_ctx* ctx, void* dptr);
