@@ -1,0 +1,171 @@
+// Internal types shared by prover.cu (keygen + create_proof) and verifier.cu (verify_proof): the device images of
+// Params / ProvingKey, the flattened constraint system, the static multiopen structure, and the host transcript.
+// Not part of the C ABI (include/bzhalo2.h).
+#pragma once
+#include "../../include/bzhalo2.h"
+#include "common.h"
+#include "fixedmsm.h"
+#include "poly.cuh"
+#include "curve.cuh"
+#include "sqrt.cuh"
+#include "blake2b.h"
+#include <algorithm>
+#include <array>
+#include <cstdlib>
+#include <functional>
+#include <map>
+#include <set>
+
+typedef bzh::Fe HFe;
+
+namespace bz {
+
+void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
+void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+void lookup_permute_large_run(Ctx* ctx, const void* cin, const void* ctab, void* aout, void* sout, uint32_t usable, uint32_t* d_err);
+
+typedef ::bz::Fe<FpP> DFe;      // device element type of the prover's scalar field (Vesta scalars = Fp)
+
+// ------------------------------------------------------------------------------------------------------
+struct ParamsImpl {
+  uint32_t k = 0, n = 0;
+  int curve = 0;
+  DevBuf g_w_u;         // n + 2 affine points: g || w || u
+  DevBuf gl_w;          // n + 1 affine points: g_lagrange || w
+  FixedBase fb_g, fb_gl;
+  bool use_tables = true;   // small n: fixed-base window tables; large n (k >= 15): bucket MSM over the raw bases
+};
+
+struct Token { uint32_t op, a; int32_t b; };
+
+struct CircuitCopy {
+  uint32_t k, G, F, I, degree, bf;
+  std::vector<std::pair<int, int>> aq, fq, iq;
+  std::vector<std::pair<uint32_t, uint32_t>> perm;
+  std::vector<HFe> consts;
+  std::vector<Token> tokens;
+  std::vector<uint32_t> gate_off;
+  struct Lookup { std::vector<std::pair<uint32_t, uint32_t>> inputs, tables; };   // token ranges
+  std::vector<Lookup> lookups;
+  HFe vk_repr;
+};
+
+// kinds of the Regions table (see poly.cuh)
+enum { R_VAL = 0, R_POLY = 1, R_MISC = 2, R_RANDPOLY = 3, R_SPOLY = 4, R_SHPOLY = 5, R_SHVAL = 6, R_HCOEF = 7 };
+
+// commitment ids of the multiopen queries (instance / advice / permutation z / lookup (A', S', Z) / fixed / sigma / h / random)
+enum { cid_inst = 0, cid_adv = 100000, cid_pz = 200000, cid_lk = 300000, cid_fix = 400000, cid_sig = 500000, cid_h = 600000, cid_rand = 600001 };
+struct Query { int cid; int rot; PolyRef poly; int blind_kind; int blind_idx; int eval_idx; };   // eval_idx: position among the proof's evaluations (-1: h, computed by the verifier)   // blind_kind: 0 = one, 1 = per-proof blind slot
+
+struct PkImpl {
+  ParamsImpl* params = nullptr;
+  CircuitCopy cs;
+  uint32_t n = 0, ext_k = 0, ext_n = 0, qdeg = 0;
+  uint32_t M = 0, L = 0, nsets = 0, chunk_len = 0, NS = 0, NC = 0, usable = 0;
+  HFe omega, omega_inv, ext_omega;
+  // device images
+  DevBuf lval;        // [F + M][n]  fixed values then sigma values (Lagrange)
+  DevBuf shpoly;      // [F + M][n]  coefficient form
+  DevBuf shcoset;     // [F + M + 5][ext_n]: fixed, sigma, l0, l_blind, l_last, active, coset_x
+  DevBuf omega_pows;  // [n]
+  std::vector<uint64_t> vk_fixed_comm, vk_perm_comm;   // keygen_vk: commit_lagrange(column, Blind::default()) as affine (8 x u64 each)
+  DevBuf tev;         // [2^(ext_k-k)]
+  // programs
+  DevBuf lk_code, q_code, lk_rot, q_rot, ql_code, ql_rot;   // ql_*: h(X) terms of low degree, evaluated on every 2nd extended point
+  uint32_t lk_ninstr = 0, q_ninstr = 0, ql_ninstr = 0;
+  uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
+  // const table layout
+  uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, C_YP0, cstride;
+  std::vector<int> rots;                 // distinct rotations of all queries (+1, -1, last)
+  std::map<int, uint32_t> rot_const;     // rotation -> const index of x * omega^rot
+  // randomness layout (indices into the per-proof draw stream)
+  uint32_t R = 0;
+  uint32_t r_adv_rows, r_adv_blind, r_lk0, r_perm0, r_lkz0, r_randpoly, r_rand_blind, r_hblind, r_qprime, r_spoly, r_sblind, r_ipa;
+  // per-proof blind slots (host)
+  uint32_t nblinds = 0;
+  // static multiopen structure
+  std::vector<Query> queries;
+  struct CommInfo { PolyRef poly; int blind_kind, blind_idx; int set; int cid; };
+  std::vector<CommInfo> cmap;                  // first-appearance order
+  std::vector<std::vector<int>> point_sets;    // rotations per set, ordered by point index
+  // evaluation list (write order)
+  std::vector<EvalQuery> evals;
+  DevBuf d_evals;
+  // MISC slots
+  uint32_t NM = 0, m_cin0, m_hpoly, m_qset0, m_qtmp0, m_qprime, m_ppoly, m_pprime, m_b, m_coef, m_scl, m_scr;
+  uint32_t proof_size = 0;
+  // slots
+  uint32_t slot_inst(uint32_t i) const { return cs.G + i; }
+  uint32_t slot_lk(uint32_t l, uint32_t which) const { return cs.G + cs.I + 3 * l + which; }   // 0 A', 1 S', 2 Z
+  uint32_t slot_pz(uint32_t s) const { return cs.G + cs.I + 3 * L + s; }
+  // workspace cache
+  struct Work {
+    uint32_t batch = 0;
+    DevBuf val, poly, coset, misc, rnd, wide, hext, hcoef, hext_low, hcoef_low, nd, consts, extras, evalout, commits, ptrs, descs, adv_in, inst_in, msm_in, msm_jac, lk_sorted, lk_err;
+    void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
+    uint32_t* h_err = nullptr;      // pinned: error word of the device lookup permutation
+  } work;
+  ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); if (work.h_err) cudaFreeHost(work.h_err); }
+};
+
+struct HostPoint { uint8_t x[32], y[32]; bool identity; };
+
+static inline void affine_to_host(const bzh::Field& Fq, const uint64_t* mont, HostPoint& p) {
+  HFe x, y; memcpy(x.l, mont, 32); memcpy(y.l, mont + 4, 32);
+  p.identity = x.is_zero() && y.is_zero();
+  Fq.to_repr(x, p.x); Fq.to_repr(y, p.y);
+}
+
+struct ProofState {
+  bzh::Blake2b st{"Halo2-Transcript"};
+  uint8_t* out; size_t pos = 0;
+  std::vector<HFe> blinds;      // per-proof blind slots
+  std::vector<HFe> consts;      // per-proof const table (host copy)
+  const uint8_t* wide;         // this proof's RNG words
+};
+
+static inline void t_common_scalar(ProofState& ps, const bzh::Field& F, const HFe& s) {
+  uint8_t tag = 2, r[32]; F.to_repr(s, r); ps.st.update(&tag, 1); ps.st.update(r, 32);
+}
+static inline void t_write_scalar(ProofState& ps, const bzh::Field& F, const HFe& s) {
+  uint8_t tag = 2, r[32]; F.to_repr(s, r); ps.st.update(&tag, 1); ps.st.update(r, 32);
+  memcpy(ps.out + ps.pos, r, 32); ps.pos += 32;
+}
+static inline void t_common_point(ProofState& ps, const HostPoint& p) {
+  if (p.identity) throw Error(BZ_ERR_INVALID, "cannot write points at infinity to the transcript");
+  uint8_t tag = 1; ps.st.update(&tag, 1); ps.st.update(p.x, 32); ps.st.update(p.y, 32);
+}
+static inline void t_write_point(ProofState& ps, const HostPoint& p) {
+  t_common_point(ps, p);
+  memcpy(ps.out + ps.pos, p.x, 32);
+  ps.out[ps.pos + 31] |= (uint8_t)((p.y[0] & 1) << 7);
+  ps.pos += 32;
+}
+static inline HFe t_squeeze(ProofState& ps, const bzh::Field& F) {
+  uint8_t tag = 0, h[64]; ps.st.update(&tag, 1); ps.st.finalize(h);
+  return F.from_bytes_wide(h);
+}
+static inline HFe rnd_host(const ProofState& ps, const bzh::Field& F, uint32_t idx) { return F.from_bytes_wide(ps.wide + (size_t)idx * 64); }
+
+}  // namespace bz
+
+struct bz_params { bz::ParamsImpl p; };
+struct bz_pk { bz::PkImpl p; };
+static inline bz::Ctx* ctx_of(bz_ctx* c) { return &c->c; }
+
+#define PV_TRY(ctx_, ...)                                     \
+  bz::Ctx* C = ctx_of(ctx_);                                  \
+  try {                                                       \
+    cudaSetDevice(C->device);                                 \
+    __VA_ARGS__;                                              \
+    return BZ_OK;                                             \
+  } catch (const bz::Error& e) {                              \
+    C->last_error = e.what();                                 \
+    return e.code;                                            \
+  } catch (const std::exception& e) {                         \
+    C->last_error = e.what();                                 \
+    return BZ_ERR_INVALID;                                    \
+  }
+
+#define API __attribute__((visibility("default")))
+
