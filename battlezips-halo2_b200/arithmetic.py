@@ -94,3 +94,40 @@ def params_new(ctx, k, curve=0):
     w, u = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
     ctx._check(ctx.lib.bz_params_new(ctx.h, k, curve, _np_ptr(g), _np_ptr(gl), _np_ptr(w), _np_ptr(u)))
     return {"g": g, "g_lagrange": gl, "w": w, "u": u}
+
+
+def points_compress(ctx, curve, affine):
+    """(n, 8) uint64 Montgomery affine -> n x 32 bytes (pasta `to_bytes`)."""
+    affine = np.ascontiguousarray(affine, dtype=np.uint64).reshape(-1, 8)
+    out = np.zeros((len(affine), 32), dtype=np.uint8)
+    ctx._check(ctx.lib.bz_points_compress(ctx.h, curve, _np_ptr(affine), len(affine), _np_ptr(out)))
+    return out
+
+
+def points_decompress(ctx, curve, data):
+    """n x 32 bytes -> ((n, 8) uint64 Montgomery affine, status (n,) uint8: 0 ok, 1 identity, 2 invalid)."""
+    buf = np.frombuffer(bytes(data), dtype=np.uint8).reshape(-1, 32).copy()
+    out = np.zeros((len(buf), 8), dtype=np.uint64)
+    st = np.zeros(len(buf), dtype=np.uint8)
+    ctx._check(ctx.lib.bz_points_decompress(ctx.h, curve, _np_ptr(buf), len(buf), _np_ptr(out), _np_ptr(st)))
+    return out, st
+
+
+def params_write(ctx, urs, k, curve=0):
+    """`Params::write`: k as u32 LE, then g, g_lagrange (2^k points each), w, u in pasta's compressed encoding."""
+    pts = np.concatenate([urs["g"], urs["g_lagrange"], urs["w"][None, :], urs["u"][None, :]])
+    return int(k).to_bytes(4, "little") + points_compress(ctx, curve, pts).tobytes()
+
+
+def params_read(ctx, data, curve=0):
+    """`Params::read`: inverse of params_write; raises ValueError on a malformed stream (io::Error upstream)."""
+    if len(data) < 4:
+        raise ValueError("Params::read: truncated")
+    k = int.from_bytes(data[:4], "little")
+    if k > 24 or len(data) != 4 + 32 * (2 * (1 << k) + 2):
+        raise ValueError("Params::read: wrong length for k")
+    n = 1 << k
+    pts, st = points_decompress(ctx, curve, data[4:])
+    if (st == 2).any():
+        raise ValueError("Params::read: invalid point encoding")
+    return k, {"g": pts[:n].copy(), "g_lagrange": pts[n:2 * n].copy(), "w": pts[2 * n].copy(), "u": pts[2 * n + 1].copy()}

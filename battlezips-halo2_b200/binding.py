@@ -84,6 +84,8 @@ def load_library():
         "bz_coeff_to_extended": (i32, [vp, i32, vp, vp, u32, u32]),
         "bz_extended_to_coeff": (i32, [vp, i32, vp, u32]),
         "bz_params_new": (i32, [vp, u32, i32, vp, vp, vp, vp]),
+        "bz_points_compress": (i32, [vp, i32, vp, u64, vp]),
+        "bz_points_decompress": (i32, [vp, i32, vp, u64, vp, vp]),
         "bz_hash_to_curve": (i32, [vp, i32, ctypes.c_char_p, vp, u32, u64, vp]),
     }
     declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",

@@ -245,6 +245,83 @@ __global__ void xyzz_normalize_kernel(const Xyzz<BP>* __restrict__ in, Affine<BP
   }
 }
 
+// ---- point (de)compression: `Params::write / read`, proof points -------------------------------------------------------
+// compressed point (32 B: x little-endian, bit 255 = parity of y) -> affine Montgomery.  status: 0 ok, 1 identity
+// encoding (all zero), 2 invalid (x >= p or x^3 + 5 not a square)
+template <class BP>
+__global__ void decompress_points_kernel(const uint8_t* __restrict__ in, Affine<BP>* __restrict__ out, uint8_t* __restrict__ status, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(in + (size_t)i * 32);
+  Fe<BP> x;
+  uint32_t any = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { x.l[j] = w[j]; any |= w[j]; }
+  const uint32_t sign = x.l[7] >> 31;
+  x.l[7] &= 0x7fffffffu;
+  Affine<BP> r; r.x = fe_zero<BP>(); r.y = fe_zero<BP>();
+  uint8_t st = 0;
+  if (!any) st = 1;
+  else {
+    // canonical check: x < p
+    uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t[j] = x.l[j];
+    sub_cc(t[0], mod_limb<BP>(0));
+#pragma unroll
+    for (int j = 1; j < 8; ++j) subc_cc(t[j], mod_limb<BP>(j));
+    const bool below = subc(0u, 0u) != 0u;
+    if (!below) st = 2;
+    else {
+      Fe<BP> xm = fe_to_mont(x);
+      Fe<BP> five = fe_zero<BP>(); five.l[0] = 5; five = fe_to_mont(five);
+      Fe<BP> y2 = fe_add(fe_mul(fe_sqr(xm), xm), five), y;
+      if (!fe_sqrt(y2, y)) st = 2;
+      else {
+        if (fe_sgn0(y) != sign) y = fe_neg(y);
+        if (fe_sgn0(y) != sign) st = 2;             // y = 0 with the sign bit set
+        r.x = xm; r.y = y;
+      }
+    }
+  }
+  fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
+  status[i] = st;
+}
+
+
+// affine Montgomery -> compressed (pasta `to_bytes`): x canonical little-endian, bit 255 = parity of y; identity = zeros
+template <class BP>
+__global__ void compress_points_kernel(const Affine<BP>* __restrict__ in, uint8_t* __restrict__ out, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Affine<BP> p = aff_load(in + i);
+  uint32_t* w = reinterpret_cast<uint32_t*>(out + (size_t)i * 32);
+  if (aff_is_identity(p)) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) w[j] = 0;
+    return;
+  }
+  Fe<BP> x = fe_from_mont(p.x);
+  x.l[7] |= fe_sgn0(p.y) << 31;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) w[j] = x.l[j];
+}
+
+void decompress_points_run(Ctx* ctx, int curve, const void* d_in, void* d_out_affine, uint8_t* d_status, uint32_t count) {
+  if (!count) return;
+  if (curve == 0) decompress_points_kernel<FqP><<<(count + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)d_in, (Affine<FqP>*)d_out_affine, d_status, count);
+  else decompress_points_kernel<FpP><<<(count + 63) / 64, 64, 0, ctx->stream>>>((const uint8_t*)d_in, (Affine<FpP>*)d_out_affine, d_status, count);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+void compress_points_run(Ctx* ctx, int curve, const void* d_in_affine, void* d_out, uint32_t count) {
+  if (!count) return;
+  if (curve == 0) compress_points_kernel<FqP><<<(count + 127) / 128, 128, 0, ctx->stream>>>((const Affine<FqP>*)d_in_affine, (uint8_t*)d_out, count);
+  else compress_points_kernel<FpP><<<(count + 127) / 128, 128, 0, ctx->stream>>>((const Affine<FpP>*)d_in_affine, (uint8_t*)d_out, count);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+
 // ---- host drivers ----------------------------------------------------------------------------------------------------------------
 static std::vector<uint8_t> h2c_template(int curve, const char* domain, uint32_t msg_len, uint32_t& tail_len) {
   const std::string cid = curve == 0 ? "vesta" : "pallas", dom(domain);
@@ -328,6 +405,32 @@ void ec_ifft_run(Ctx* ctx, int curve, const void* d_g, void* d_out, uint32_t k) 
   }
 
 extern "C" {
+
+// group encoding of pasta_curves (`GroupEncoding::to_bytes / from_bytes`), n points per call, host buffers
+__attribute__((visibility("default"))) int bz_points_compress(bz_ctx* ctx, int curve, const void* affine, uint64_t n, void* out32) {
+  BZ_TRY2(ctx, {
+    BZ_CHECK((curve == 0 || curve == 1) && affine && out32 && n < (1ull << 31), "points_compress: bad arguments");
+    bz::DevBuf d_in, d_out; d_in.alloc(std::max<size_t>(1, n * 64)); d_out.alloc(std::max<size_t>(1, n * 32));
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(d_in.p, affine, n * 64, cudaMemcpyHostToDevice, st));
+    bz::compress_points_run(&ctx->c, curve, d_in.p, d_out.p, (uint32_t)n);
+    BZ_CUDA(cudaMemcpyAsync(out32, d_out.p, n * 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+// status[i]: 0 ok, 1 identity encoding, 2 not a curve point (from_bytes returns None)
+__attribute__((visibility("default"))) int bz_points_decompress(bz_ctx* ctx, int curve, const void* in32, uint64_t n, void* out_affine, uint8_t* status) {
+  BZ_TRY2(ctx, {
+    BZ_CHECK((curve == 0 || curve == 1) && in32 && out_affine && status && n < (1ull << 31), "points_decompress: bad arguments");
+    bz::DevBuf d_in, d_out, d_st; d_in.alloc(std::max<size_t>(1, n * 32)); d_out.alloc(std::max<size_t>(1, n * 64)); d_st.alloc(std::max<size_t>(1, n));
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(d_in.p, in32, n * 32, cudaMemcpyHostToDevice, st));
+    bz::decompress_points_run(&ctx->c, curve, d_in.p, d_out.p, d_st.as<uint8_t>(), (uint32_t)n);
+    BZ_CUDA(cudaMemcpyAsync(out_affine, d_out.p, n * 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaMemcpyAsync(status, d_st.p, n, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
 
 __attribute__((visibility("default"))) int bz_hash_to_curve(bz_ctx* ctx, int curve, const char* domain_prefix, const void* messages,
                                                             uint32_t msg_len, uint64_t count, void* out_affine) {

@@ -17,46 +17,7 @@ namespace bz {
 
 typedef ::bz::Fe<FqP> DFq;
 
-// compressed point (32 B: x little-endian, bit 255 = parity of y) -> affine Montgomery.  status: 0 ok, 1 identity
-// encoding (all zero), 2 invalid (x >= p or x^3 + 5 not a square)
-__global__ void decompress_points_kernel(const uint8_t* __restrict__ in, Affine<FqP>* __restrict__ out, uint8_t* __restrict__ status, uint32_t count) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(in + (size_t)i * 32);
-  DFq x;
-  uint32_t any = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) { x.l[j] = w[j]; any |= w[j]; }
-  const uint32_t sign = x.l[7] >> 31;
-  x.l[7] &= 0x7fffffffu;
-  Affine<FqP> r; r.x = fe_zero<FqP>(); r.y = fe_zero<FqP>();
-  uint8_t st = 0;
-  if (!any) st = 1;
-  else {
-    // canonical check: x < p
-    uint32_t t[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) t[j] = x.l[j];
-    sub_cc(t[0], mod_limb<FqP>(0));
-#pragma unroll
-    for (int j = 1; j < 8; ++j) subc_cc(t[j], mod_limb<FqP>(j));
-    const bool below = subc(0u, 0u) != 0u;
-    if (!below) st = 2;
-    else {
-      DFq xm = fe_to_mont(x);
-      DFq five = fe_zero<FqP>(); five.l[0] = 5; five = fe_to_mont(five);
-      DFq y2 = fe_add(fe_mul(fe_sqr(xm), xm), five), y;
-      if (!fe_sqrt(y2, y)) st = 2;
-      else {
-        if (fe_sgn0(y) != sign) y = fe_neg(y);
-        if (fe_sgn0(y) != sign) st = 2;             // y = 0 with the sign bit set
-        r.x = xm; r.y = y;
-      }
-    }
-  }
-  fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
-  status[i] = st;
-}
+// (point decompression: decompress_points_run in params.cu)
 
 // compute_s (U: poly/commitment/verifier.rs): s[idx] = init * prod_{bit i of idx set} u_rev[i];  s[0] += add0.
 // consts per proof: [0] init (= -c), [1] add0 (= -v, the g[0] term), [2 .. 2+k) u_rev
@@ -161,8 +122,7 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
   DevBuf d_comp, d_pts, d_stat, d_inst, d_ptrs, d_extra, d_icomm;
   d_comp.alloc(comp.size()); d_pts.alloc((size_t)B * NP * 64); d_stat.alloc((size_t)B * NP);
   BZ_CUDA(cudaMemcpyAsync(d_comp.p, comp.data(), comp.size(), cudaMemcpyHostToDevice, st));
-  decompress_points_kernel<<<(B * NP + 63) / 64, 64, 0, st>>>((const uint8_t*)d_comp.p, (Affine<FqP>*)d_pts.p, (uint8_t*)d_stat.p, B * NP);
-  C->kernel_launches++;
+  decompress_points_run(C, pr.curve, d_comp.p, d_pts.p, (uint8_t*)d_stat.p, B * NP);
   std::vector<uint64_t> h_pts((size_t)B * NP * 8), h_icomm((size_t)B * std::max(1u, I) * 8);
   std::vector<uint8_t> h_stat((size_t)B * NP);
   BZ_CUDA(cudaMemcpyAsync(h_pts.data(), d_pts.p, h_pts.size() * 8, cudaMemcpyDeviceToHost, st));

@@ -53,6 +53,8 @@ extern "C" {
     // poly/commitment.rs `Params::new`, pasta_curves `hash_to_curve`
     pub fn bz_params_new(ctx: *mut bz_ctx, k: u32, curve: c_int, g: *mut c_void, g_lagrange: *mut c_void, w: *mut c_void, u: *mut c_void) -> c_int;
     pub fn bz_hash_to_curve(ctx: *mut bz_ctx, curve: c_int, domain_prefix: *const c_char, messages: *const c_void, msg_len: u32, count: u64, out_affine: *mut c_void) -> c_int;
+    pub fn bz_points_compress(ctx: *mut bz_ctx, curve: c_int, affine: *const c_void, n: u64, out32: *mut c_void) -> c_int;
+    pub fn bz_points_decompress(ctx: *mut bz_ctx, curve: c_int, in32: *const c_void, n: u64, out_affine: *mut c_void, status: *mut u8) -> c_int;
     // plonk/verifier.rs
     pub fn bz_verify_proofs(ctx: *mut bz_ctx, pk: *mut bz_pk, batch: u32, instances: *const c_void, instance_lens: *const u32, instance_stride: u32, proofs: *const c_void, proof_len: u32, results: *mut u8) -> c_int;
     pub fn bz_create_proofs(ctx: *mut bz_ctx, pk: *mut bz_pk, batch: u32, instances: *const c_void, instance_lens: *const u32, instance_stride: u32, advice: *const c_void, rand_wide: *const c_void, proofs: *mut c_void) -> c_int;

@@ -140,6 +140,11 @@ int bz_params_new(bz_ctx* ctx, uint32_t k, int curve, void* g, void* g_lagrange,
  * KATs /root/reference/src/utils/constants/fixed_bases/board_commit_v.rs:5-14.) */
 int bz_hash_to_curve(bz_ctx* ctx, int curve, const char* domain_prefix, const void* messages, uint32_t msg_len,
                      uint64_t count, void* out_affine);
+/* pasta_curves `GroupEncoding::to_bytes / from_bytes` for n points (host buffers): 32 B = x little-endian canonical,
+ * bit 255 = parity of y, identity = 32 zero bytes -- the encoding of `Params::write / read` (k: u32 LE, then g,
+ * g_lagrange, w, u compressed) and of the proof's points.  status[i]: 0 ok, 1 identity, 2 not a curve point. */
+int bz_points_compress(bz_ctx* ctx, int curve, const void* affine, uint64_t n, void* out32);
+int bz_points_decompress(bz_ctx* ctx, int curve, const void* in32, uint64_t n, void* out_affine, uint8_t* status);
 /* Params::commit (lagrange_basis = 0) / Params::commit_lagrange (1): poly = n scalars (host), blind = 1 scalar;
  * result already normalised: 64 B affine (what `.to_affine()` / batch_normalize yields). */
 int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* poly, const void* blind,

@@ -71,3 +71,43 @@ def test_device_urs_proves_and_verifies(ctx):
     assert proof == job.oracle_proof(index=0)
     assert job.verify(proof)
     pk.close(); params.close()
+
+
+@pytest.mark.parametrize("curve", [0, 1])
+def test_point_encoding_matches_oracle(ctx, oracle_c, curve):
+    """pasta `to_bytes` / `from_bytes` on the device against the oracle's encoding, incl. identity and invalid encodings."""
+    from battlezips_halo2_b200 import arithmetic as ar
+    C = oracle_c.CURVES[curve][0]
+    h = C.hash_to_curve("enc-test")
+    pts = [h(bytes([i])) for i in range(9)] + [None]
+    pts.append(C.neg(pts[0]))
+    mont = oracle_c.points_to_mont(curve, pts)
+    enc = ar.points_compress(ctx, curve, mont)
+    assert [bytes(e) for e in enc] == [C.to_bytes(p) for p in pts]
+    dec, st = ar.points_decompress(ctx, curve, enc.tobytes())
+    assert list(st) == [0] * 9 + [1, 0]
+    assert np.array_equal(dec, mont)
+    p = C.base.p
+    x_bad = next(x for x in range(1, 100) if pow((x ** 3 + 5) % p, (p - 1) // 2, p) != 1)
+    bad = [x_bad.to_bytes(32, "little"), p.to_bytes(32, "little"), b"\xff" * 32]
+    _, st = ar.points_decompress(ctx, curve, b"".join(bad))
+    assert list(st) == [2, 2, 2]
+    for b in bad:
+        with pytest.raises(Exception):
+            C.from_bytes(b)
+
+
+def test_params_write_read_roundtrip(ctx):
+    """`Params::write` / `Params::read` byte format (k, g, g_lagrange, w, u) on the k = 11 URS."""
+    from battlezips_halo2_b200 import arithmetic as ar
+    fx = np.load(os.path.join(HERE, "golden", "params_vesta_k11.npz"))
+    urs = {k: fx[k] for k in ("g", "g_lagrange", "w", "u")}
+    blob = ar.params_write(ctx, urs, 11)
+    assert len(blob) == 4 + 32 * (2 * 2048 + 2) and blob[:4] == (11).to_bytes(4, "little")
+    k, back = ar.params_read(ctx, blob)
+    assert k == 11 and all(np.array_equal(back[n], urs[n]) for n in urs)
+    with pytest.raises(ValueError):
+        ar.params_read(ctx, blob[:-1])
+    broken = bytearray(blob); broken[4:36] = b"\xff" * 32
+    with pytest.raises(ValueError):
+        ar.params_read(ctx, bytes(broken))
