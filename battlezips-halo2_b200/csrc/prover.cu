@@ -1020,6 +1020,20 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       for (uint32_t s = 0; s < pk.nsets; ++s) { HFe x = rnd_host(ps[b], F, pk.r_perm0 + s * (bf + 1) + bf); bl[b].push_back(x); ps[b].blinds[G + 3 * L + s] = x; }
       for (uint32_t l = 0; l < L; ++l) { HFe x = rnd_host(ps[b], F, pk.r_lkz0 + l * (bf + 1) + bf); bl[b].push_back(x); ps[b].blinds[G + 3 * l + 2] = x; }
     }
+    if (getenv("BZ_SANITY_CHECKS")) {
+      // halo2_proofs' `sanity-checks` feature (U: plonk/permutation/prover.rs, plonk/lookup/prover.rs): every grand product
+      // must return to 1 on the first unusable row; otherwise the witness violates a copy constraint / lookup
+      std::vector<uint32_t> slots;
+      if (pk.nsets) slots.push_back(pk.slot_pz(pk.nsets - 1));
+      for (uint32_t l = 0; l < L; ++l) slots.push_back(pk.slot_lk(l, 2));
+      std::vector<HFe> zs((size_t)B * slots.size());
+      for (uint32_t b = 0; b < B; ++b)
+        for (size_t j = 0; j < slots.size(); ++j)
+          BZ_CUDA(cudaMemcpyAsync(&zs[(size_t)b * slots.size() + j], val(b, slots[j]) + (n - (bf + 1)), 32, cudaMemcpyDeviceToHost, st));
+      BZ_CUDA(cudaStreamSynchronize(st));
+      for (const HFe& z : zs)
+        if (!(z == F.one())) throw Error(BZ_ERR_SYNTHESIS, "sanity check: a grand product does not end in 1 (Error::ConstraintSystemFailure)");
+    }
     if (!reqs.empty()) {
       commit(reqs, bl, pts);
       for (uint32_t b = 0; b < B; ++b) for (size_t j = 0; j < reqs.size(); ++j) t_write_point(ps[b], pts[b][j]);

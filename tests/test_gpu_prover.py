@@ -172,3 +172,24 @@ def test_lookup_permutation_paths_agree(ctx, monkeypatch):
         PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])
     assert e.value.code == -4
     pk.close(); params.close()
+
+
+def test_sanity_checks_flag_catches_broken_copy_constraint(ctx, monkeypatch):
+    """halo2_proofs' optional `sanity-checks` feature, here BZ_SANITY_CHECKS: a witness that violates a copy constraint makes
+    the permutation grand product miss 1 on the first unusable row -> Error::ConstraintSystemFailure instead of an
+    (invalid) proof; a good witness is unaffected."""
+    import battlezips_halo2_b200 as bz
+    from battlezips_halo2_b200.plonk import prover as PR
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=6)
+    monkeypatch.setenv("BZ_SANITY_CHECKS", "1")
+    assert _prove(job, pk, [0])[0] == job.oracle_proof(index=0)
+    adv = job.advice.copy()
+    adv[1, 3] = job.V.m(5)                   # b[3] is copy-constrained to b[0] = 4
+    with pytest.raises(bz.BzError) as e:
+        PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])
+    assert e.value.code == -4
+    monkeypatch.delenv("BZ_SANITY_CHECKS")
+    bad = PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])[0]     # without the flag: a proof that does not verify
+    assert PR.verify_proofs(pk, [job.instances], [bad]) == [False]
+    pk.close(); params.close()
