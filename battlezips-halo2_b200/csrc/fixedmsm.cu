@@ -114,7 +114,8 @@ void fixed_base_build(Ctx* ctx, FixedBase& fb, int curve, const void* bases_dev,
 //                         loop, every warp full, every SM busy until the end
 //   3. fb_fold_kernel     one CTA per MSM: strided sum of its partials, shared-memory tree, affine output
 constexpr int FB_THREADS = 128;
-constexpr int FB_FOLD_THREADS = 128;
+constexpr int FB_FOLD_THREADS = 128;          // batched calls (many MSMs per launch)
+constexpr int FB_FOLD_THREADS_WIDE = 512;     // few MSMs per launch (single-proof latency): more threads per fold
 
 template <class SP>
 __global__ void __launch_bounds__(FB_THREADS) fb_decode_kernel(uint32_t npts, uint32_t c, uint32_t W, uint32_t nbk,
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(FB_THREADS) fb_decode_kernel(uint32_t npts, ui
 // cut into equal ranges, one per resident thread: no wave quantisation (r1d ncu: the per-segment grid ran 2.16 waves on
 // the IPA-round launches and left the fma pipe at 56-66 %), and ~8x fewer partial sums to fold.
 constexpr uint32_t FB_MAX_MSM = 4096;
-constexpr uint32_t FB_MIN_SHARE = 8;
+constexpr uint32_t FB_MIN_SHARE = 16;
 __device__ __forceinline__ uint32_t fb_plan(const uint32_t* __restrict__ list_count, uint32_t n_msm, uint32_t total_threads, uint32_t* off /* [n_msm + 1] shared */,
                                             uint32_t* wsum /* [33] shared */) {
   const uint32_t tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -259,12 +260,12 @@ __global__ void __launch_bounds__(FB_THREADS, 4) fb_accumulate_kernel(const Affi
 }
 
 // fold the partials of each MSM and normalise: one CTA per MSM -> affine (64 B), identity = zeros
-template <class BP, bool XYZZ_OUT>
-__global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
+template <class BP, bool XYZZ_OUT, int THREADS>
+__global__ void __launch_bounds__(THREADS) fb_fold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
                                  uint32_t n_msm, uint32_t acc_threads, void* __restrict__ out_v) {
-  extern __shared__ uint32_t fb_off[];
   __shared__ uint32_t wsum[33];
-  __shared__ Xyzz<BP> sh[FB_FOLD_THREADS];
+  extern __shared__ uint32_t fb_off[];
+  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(fb_off + (((size_t)n_msm + 1 + 31) & ~size_t(31)));      // after the offsets, 128 B aligned
   const uint32_t m = blockIdx.x, tid = threadIdx.x;
   const uint32_t q = fb_plan(list_count, n_msm, acc_threads, fb_off, wsum);
   const uint32_t lo = fb_off[m], hi = fb_off[m + 1];
@@ -272,7 +273,7 @@ __global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>
   if (hi > lo) {
     const uint32_t w_first = lo / (32u * q), w_last = (hi - 1) / (32u * q);
     const uint32_t npieces = (w_last - w_first + 1) * 32u;         // warp w, lane l -> (w + m) * 32 + l : contiguous
-    for (uint32_t t = tid; t < npieces; t += FB_FOLD_THREADS) {
+    for (uint32_t t = tid; t < npieces; t += THREADS) {
       const Xyzz<BP>* p = partial + ((size_t)w_first + m) * 32 + t;
       Xyzz<BP> v; v.x = fe_load(&p->x); v.y = fe_load(&p->y); v.zz = fe_load(&p->zz); v.zzz = fe_load(&p->zzz);
       acc = xyzz_add(acc, v);
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(FB_FOLD_THREADS) fb_fold_kernel(const Xyzz<BP>
   }
   sh[tid] = acc;
   __syncthreads();
-  for (uint32_t d = FB_FOLD_THREADS >> 1; d > 0; d >>= 1) {
+  for (uint32_t d = THREADS >> 1; d > 0; d >>= 1) {
     if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
     __syncthreads();
   }
@@ -308,6 +309,11 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
     int v = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, fb_accumulate_kernel<BP>, FB_THREADS, (FB_MAX_MSM + 1) * 4);
     ctas_per_sm = v < 1 ? 1 : v;
+    const int fold_smem = (int)((FB_MAX_MSM + 32) * 4 + FB_FOLD_THREADS_WIDE * sizeof(Xyzz<BP>));
+    cudaFuncSetAttribute(fb_fold_kernel<BP, true, FB_FOLD_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
+    cudaFuncSetAttribute(fb_fold_kernel<BP, false, FB_FOLD_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
+    cudaFuncSetAttribute(fb_fold_kernel<BP, true, FB_FOLD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
+    cudaFuncSetAttribute(fb_fold_kernel<BP, false, FB_FOLD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
   });
   const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
   const uint32_t acc_ctas = (uint32_t)ctx->sm_count * (uint32_t)ctas_per_sm, acc_threads = acc_ctas * FB_THREADS;
@@ -328,8 +334,16 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
       fb_decode_kernel<SP><<<dim3((fb.npts + FB_THREADS - 1) / FB_THREADS, nm), FB_THREADS, 0, st>>>(
           fb.npts, fb.c, fb.W, fb.nbk, (const Fe<SP>* const*)d_main + m0, n_main, d_extra ? (const Fe<SP>* const*)d_extra + m0 : nullptr, lists, list_stride, counts);
       fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, st>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
-      if (xyzz_out) fb_fold_kernel<BP, true><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Xyzz<BP>*)d_out + m0);
-      else fb_fold_kernel<BP, false><<<nm, FB_FOLD_THREADS, smem, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out + m0);
+      // fold: offsets + one XYZZ slot per thread in dynamic shared memory; wide CTAs when only a few MSMs are in flight
+      const bool wide = nm < 48;
+      const size_t fsm = (((size_t)nm + 1 + 31) & ~size_t(31)) * 4 + (size_t)(wide ? FB_FOLD_THREADS_WIDE : FB_FOLD_THREADS) * sizeof(Xyzz<BP>);
+      if (wide) {
+        if (xyzz_out) fb_fold_kernel<BP, true, FB_FOLD_THREADS_WIDE><<<nm, FB_FOLD_THREADS_WIDE, fsm, st>>>(partial, counts, nm, acc_threads, (Xyzz<BP>*)d_out + m0);
+        else fb_fold_kernel<BP, false, FB_FOLD_THREADS_WIDE><<<nm, FB_FOLD_THREADS_WIDE, fsm, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out + m0);
+      } else {
+        if (xyzz_out) fb_fold_kernel<BP, true, FB_FOLD_THREADS><<<nm, FB_FOLD_THREADS, fsm, st>>>(partial, counts, nm, acc_threads, (Xyzz<BP>*)d_out + m0);
+        else fb_fold_kernel<BP, false, FB_FOLD_THREADS><<<nm, FB_FOLD_THREADS, fsm, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out + m0);
+      }
     }
     ctx->kernel_launches += 3;
   }
