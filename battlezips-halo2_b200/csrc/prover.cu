@@ -352,6 +352,44 @@ API int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, con
   });
 }
 
+// Params::commit / commit_lagrange for `count` device-resident polynomials at once (count x n scalars, contiguous;
+// blinds: count scalars) -> count affine points on the device.  The unit of work the north star shards across GPUs
+// ("independent column commitments ... per GPU"): each rank commits its share of the columns, the 64 B results are
+// all-gathered (sharding.py).
+API int bz_params_commit_batch_dev(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* d_polys, const void* d_blinds,
+                                   uint32_t count, void* d_out_affine) {
+  PV_TRY(ctx, {
+    BZ_CHECK(params && d_polys && d_blinds && d_out_affine, "null argument");
+    if (!count) return BZ_OK;
+    ParamsImpl& p = params->p;
+    cudaStream_t st = C->stream;
+    const FixedBase& fb = lagrange_basis ? p.fb_gl : p.fb_g;
+    const uint32_t nextra = fb.npts - p.n;
+    // persistent staging (no cudaMalloc / cudaFree per call: large frees stall the whole device for 100+ ms now and then)
+    DevBuf &d_extra = C->stage[3], &d_ptrs = C->stage[4];
+    d_extra.ensure((size_t)count * nextra * 32); d_ptrs.ensure((size_t)2 * count * sizeof(void*));
+    BZ_CUDA(cudaMemsetAsync(d_extra.p, 0, (size_t)count * nextra * 32, st));
+    BZ_CUDA(cudaMemcpy2DAsync(d_extra.p, (size_t)nextra * 32, d_blinds, 32, 32, count, cudaMemcpyDeviceToDevice, st));   // blind -> the w slot
+    if (p.use_tables) {
+      std::vector<void*> ptrs((size_t)2 * count);
+      for (uint32_t j = 0; j < count; ++j) { ptrs[j] = (char*)d_polys + (size_t)j * p.n * 32; ptrs[count + j] = (char*)d_extra.p + (size_t)j * nextra * 32; }
+      BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
+      fixed_msm_run(C, fb, (const void* const*)d_ptrs.p, p.n, (const void* const*)((void**)d_ptrs.p + count), count, 1, d_out_affine);
+      BZ_CUDA(cudaStreamSynchronize(st));          // ptrs goes out of scope
+    } else {
+      DevBuf &d_in = C->stage[5], &d_jac = C->stage[0];
+      d_in.ensure((size_t)fb.npts * 32); d_jac.ensure((size_t)count * 96);
+      for (uint32_t j = 0; j < count; ++j) {
+        BZ_CUDA(cudaMemcpyAsync(d_in.p, (const char*)d_polys + (size_t)j * p.n * 32, (size_t)p.n * 32, cudaMemcpyDeviceToDevice, st));
+        BZ_CUDA(cudaMemcpyAsync((char*)d_in.p + (size_t)p.n * 32, (char*)d_extra.p + (size_t)j * nextra * 32, (size_t)nextra * 32, cudaMemcpyDeviceToDevice, st));
+        msm_run(C, p.curve, d_in.p, lagrange_basis ? p.gl_w.p : p.g_w_u.p, fb.npts, (char*)d_jac.p + (size_t)j * 96, 0);
+      }
+      jac_to_affine_run(C, p.curve, d_jac.p, d_out_affine, count);
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
+  });
+}
+
 API void bz_pk_destroy(bz_pk* pk) { delete pk; }
 API uint32_t bz_pk_num_random(const bz_pk* pk) { return pk ? pk->p.R : 0; }
 API uint32_t bz_pk_proof_size(const bz_pk* pk) { return pk ? pk->p.proof_size : 0; }

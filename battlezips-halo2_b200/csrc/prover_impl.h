@@ -106,6 +106,7 @@ struct PkImpl {
     void* h_pinned = nullptr; size_t h_pinned_bytes = 0;
     uint32_t* h_err = nullptr;      // pinned: error word of the device lookup permutation
   } work;
+  DevBuf vwork[16];      // verifier staging, kept across bz_verify_proofs calls (no cudaMalloc / cudaFree per call)
   ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); if (work.h_err) cudaFreeHost(work.h_err); }
 };
 

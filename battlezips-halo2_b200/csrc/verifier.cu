@@ -119,8 +119,8 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
   std::vector<uint8_t> comp((size_t)B * NP * 32);
   for (uint32_t b = 0; b < B; ++b)
     for (uint32_t i = 0; i < NP; ++i) memcpy(&comp[((size_t)b * NP + i) * 32], proofs + (size_t)b * proof_len + pt_off[i], 32);
-  DevBuf d_comp, d_pts, d_stat, d_inst, d_ptrs, d_extra, d_icomm;
-  d_comp.alloc(comp.size()); d_pts.alloc((size_t)B * NP * 64); d_stat.alloc((size_t)B * NP);
+  DevBuf &d_comp = pk.vwork[0], &d_pts = pk.vwork[1], &d_stat = pk.vwork[2], &d_inst = pk.vwork[3], &d_ptrs = pk.vwork[4], &d_extra = pk.vwork[5], &d_icomm = pk.vwork[6];
+  d_comp.ensure(comp.size()); d_pts.ensure((size_t)B * NP * 64); d_stat.ensure((size_t)B * NP);
   BZ_CUDA(cudaMemcpyAsync(d_comp.p, comp.data(), comp.size(), cudaMemcpyHostToDevice, st));
   decompress_points_run(C, pr.curve, d_comp.p, d_pts.p, (uint8_t*)d_stat.p, B * NP);
   std::vector<uint64_t> h_pts((size_t)B * NP * 8), h_icomm((size_t)B * std::max(1u, I) * 8);
@@ -128,7 +128,7 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
   BZ_CUDA(cudaMemcpyAsync(h_pts.data(), d_pts.p, h_pts.size() * 8, cudaMemcpyDeviceToHost, st));
   BZ_CUDA(cudaMemcpyAsync(h_stat.data(), d_stat.p, h_stat.size(), cudaMemcpyDeviceToHost, st));
   if (I) {
-    d_inst.alloc((size_t)B * I * n * 32); d_ptrs.alloc((size_t)2 * B * I * sizeof(void*)); d_extra.alloc((size_t)B * I * 64); d_icomm.alloc((size_t)B * I * 64);
+    d_inst.ensure((size_t)B * I * n * 32); d_ptrs.ensure((size_t)2 * B * I * sizeof(void*)); d_extra.ensure((size_t)B * I * 64); d_icomm.ensure((size_t)B * I * 64);
     BZ_CUDA(cudaMemsetAsync(d_inst.p, 0, (size_t)B * I * n * 32, st));
     std::vector<void*> mainp((size_t)B * I), extrap((size_t)B * I);
     std::vector<HFe> ex((size_t)B * I * 2, F.zero());
@@ -354,9 +354,9 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
     fx_extra[2 * b + 1] = F.neg(F.mul(F.mul(c_sc, bb), z));          // U
   }
   // ---- device: compute_s, the fixed-base part, the final check
-  DevBuf d_sc, d_s, d_fx, d_fptrs, d_fpart, d_vp, d_vs, d_ok;
-  d_sc.alloc(s_consts.size() * 32); d_s.alloc((size_t)B * n * 32); d_fx.alloc((size_t)B * 64); d_fptrs.alloc((size_t)2 * B * sizeof(void*));
-  d_fpart.alloc((size_t)B * 64); d_vp.alloc(v_pts.size() * 8); d_vs.alloc(v_scal.size() * 8); d_ok.alloc(B);
+  DevBuf &d_sc = pk.vwork[7], &d_s = pk.vwork[8], &d_fx = pk.vwork[9], &d_fptrs = pk.vwork[10], &d_fpart = pk.vwork[11], &d_vp = pk.vwork[12], &d_vs = pk.vwork[13], &d_ok = pk.vwork[14];
+  d_sc.ensure(s_consts.size() * 32); d_s.ensure((size_t)B * n * 32); d_fx.ensure((size_t)B * 64); d_fptrs.ensure((size_t)2 * B * sizeof(void*));
+  d_fpart.ensure((size_t)B * 64); d_vp.ensure(v_pts.size() * 8); d_vs.ensure(v_scal.size() * 8); d_ok.ensure(B);
   BZ_CUDA(cudaMemcpyAsync(d_sc.p, s_consts.data(), s_consts.size() * 32, cudaMemcpyHostToDevice, st));
   BZ_CUDA(cudaMemcpyAsync(d_fx.p, fx_extra.data(), fx_extra.size() * 32, cudaMemcpyHostToDevice, st));
   BZ_CUDA(cudaMemcpyAsync(d_vp.p, v_pts.data(), v_pts.size() * 8, cudaMemcpyHostToDevice, st));

@@ -52,6 +52,8 @@ def _bind(lib):
     lib.bz_params_destroy.argtypes = [vp]
     lib.bz_params_commit.restype = i32
     lib.bz_params_commit.argtypes = [vp, vp, i32, vp, vp, vp]
+    lib.bz_params_commit_batch_dev.restype = i32
+    lib.bz_params_commit_batch_dev.argtypes = [vp, vp, i32, vp, vp, u32, vp]
     lib.bz_pk_create.restype = i32
     lib.bz_pk_create.argtypes = [vp, vp, ctypes.POINTER(bz_circuit), vp, vp, ctypes.POINTER(vp)]
     lib.bz_pk_create_from_assembly.restype = i32
@@ -94,6 +96,11 @@ class Params:
 
     def commit_lagrange(self, poly, blind):
         return self.commit(poly, blind, lagrange=True)
+
+    def commit_batch_dev(self, d_polys, d_blinds, count, d_out, lagrange=False):
+        """`count` commitments, everything device-resident (int / c_void_p device addresses); d_out: count x 64 B."""
+        as_ptr = lambda p: p if isinstance(p, ctypes.c_void_p) else ctypes.c_void_p(int(p))
+        self.ctx._check(self.ctx.lib.bz_params_commit_batch_dev(self.ctx.h, self.h, 1 if lagrange else 0, as_ptr(d_polys), as_ptr(d_blinds), count, as_ptr(d_out)))
 
     def close(self):
         if self.h:

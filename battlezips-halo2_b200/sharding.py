@@ -1,6 +1,8 @@
 """Multi-GPU partitioning of the prover workload: independent proofs are sharded as contiguous index ranges,
 one process per GPU, with NO data-path collective -- ranks only exchange finished proof bytes (and timing maxima).
-NTT / grand product / IPA of a single proof do not shard: replicas only."""
+Independent column commitments of ONE large proof shard the same way (column ranges per GPU, the 64 B results all-gathered);
+one large MSM is split by point range with an all-gather of the 96 B partials.  NTT / grand product / IPA of a single proof
+do not shard: replicas only."""
 
 
 def shard_range(total, rank, world):
@@ -65,3 +67,23 @@ def allgather_point_sum_dev(ctx, curve, jac_tensor, gathered, out_affine, group=
     dist.all_gather_into_tensor(gathered, jac_tensor, group=group)
     ctx._check(ctx.lib.bz_point_sum_dev(ctx.h, curve, ctypes.c_void_p(gathered.data_ptr()), gathered.shape[0], ctypes.c_void_p(out_affine.data_ptr())))
     return out_affine
+
+
+def allgather_commitments(local, count, rank, world, group=None):
+    """Column-sharded commitments: rank r computed the affine commitments of columns shard_range(count, r, world) into
+    `local` (a torch int64 tensor of shape (ceil(count / world), 8), rows beyond its share are padding).  One all-gather of
+    64 B per column; returns the (count, 8) tensor in column order on every rank."""
+    import torch
+    import torch.distributed as dist
+    per = (count + world - 1) // world
+    assert local.shape == (per, 8)
+    if world == 1:
+        return local[:count]
+    flat = torch.empty((world * per, 8), dtype=local.dtype, device=local.device)      # concatenation layout (gloo and NCCL)
+    dist.all_gather_into_tensor(flat, local.contiguous(), group=group)
+    gathered = flat.view(world, per, 8)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(count, r, world)
+        parts.append(gathered[r, :hi - lo])
+    return torch.cat(parts)

@@ -4,6 +4,7 @@
 Workloads (BASELINE.json configs; `--workload`):
   shot  batched Shot proofs, k=11 (DEFAULT; config 3: independent proofs per GPU)  metric proofs_per_sec
   board Board proofs, k=12 (config 2)                                               metric proofs_per_sec
+  commit  column commitments of one large proof, sharded per GPU     (config 5)   metric commit_points_per_sec
   msm   raw MSM over Vesta/Pallas, 2^LOG points resident in HBM       (config 4)   metric msm_points_per_sec
   ntt   Fp NTT / coset extension, 2^LOG elements                      (config 4)   metric ntt_gbytes_per_sec
 
@@ -34,6 +35,7 @@ def parse():
     ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
+    ap.add_argument("--columns", type=int, default=32, help="independent column commitments per step (commit workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="default (shot) run only: skip the compact Board / MSM / NTT sub-benchmarks reported under `extras`")
@@ -65,6 +67,8 @@ class ClockSampler:
         self.idx, self.rows, self.proc = gpu_index, [], None
 
     def start(self):
+        if os.environ.get("BZ_NO_CLOCK_SAMPLER"):
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -304,6 +308,97 @@ class NttWorkload:
         return 64.0 * (1 << lg) / 1e9 / dt, f"best_fft restated (C, {co.get_threads()} threads) at 2^{lg}", co.get_threads(), dt
 
 
+class CommitWorkload:
+    """Params::commit of `columns` independent polynomials of 2^k uniform scalars (the large-column commit of BASELINE config 5),
+    column-sharded across the GPUs of the job; the commitments are all-gathered (64 B each)."""
+    dtype = "u32x8 (255-bit Montgomery, integer pipe)"
+
+    def __init__(self, args):
+        self.k, self.M = args.k, args.columns
+        self.n = 1 << self.k
+        self.metric, self.unit = "commit_points_per_sec", "points/s"
+        self.scaling = "strong"
+        self.name = (f"Params::commit of {self.M} independent columns of 2^{self.k} uniform scalars, device URS from Params::new, "
+                     f"columns sharded per GPU + all-gather of the commitments (BASELINE config 5 / north-star column sharding)")
+
+    def setup(self, ctx, rank):
+        import torch
+        from battlezips_halo2_b200 import arithmetic as ar
+        from battlezips_halo2_b200.plonk import prover as PR
+        from battlezips_halo2_b200.sharding import shard_range
+        self.ctx, self.rank = ctx, rank
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.urs = ar.params_new(ctx, self.k, curve=0)
+        self.params = PR.Params(ctx, self.k, self.urs["g"], self.urs["g_lagrange"], self.urs["w"], self.urs["u"])
+        self.lo, self.hi = shard_range(self.M, rank, self.world)
+        self.per = (self.M + self.world - 1) // self.world
+        cnt = self.hi - self.lo
+        rng = np.random.default_rng(777)                      # every rank draws the same global columns, keeps its range
+        cols = []
+        for j in range(self.M):
+            c = rand_field(rng, self.n)
+            if self.lo <= j < self.hi or (rank == 0 and j in (0, self.M - 1)):
+                cols.append((j, c))
+        mine = [c for j, c in cols if self.lo <= j < self.hi]
+        self.sample = {j: c for j, c in cols if j in (0, self.M - 1)} if rank == 0 else {}
+        self.blinds_np = rand_field(np.random.default_rng(778), self.M)
+        host = np.stack(mine) if mine else np.zeros((1, self.n, 4), np.uint64)
+        self.h_polys = torch.from_numpy(host.view(np.int64)).pin_memory()
+        self.d_polys = torch.empty_like(self.h_polys, device="cuda")
+        self.d_polys.copy_(self.h_polys)
+        self.d_blinds = torch.from_numpy(np.ascontiguousarray(self.blinds_np[self.lo:self.hi] if cnt else self.blinds_np[:1]).view(np.int64)).cuda()
+        self.d_local = torch.zeros((self.per, 8), dtype=torch.int64, device="cuda")
+        self.cnt = cnt
+        self.h2d, self.d2h = int(cnt * self.n * 32), int(self.M * 64)
+        torch.cuda.synchronize()
+
+    def _commit(self):
+        from battlezips_halo2_b200.sharding import allgather_commitments
+        if self.cnt:
+            self.params.commit_batch_dev(self.d_polys.data_ptr(), self.d_blinds.data_ptr(), self.cnt, self.d_local.data_ptr())
+        self.result = allgather_commitments(self.d_local, self.M, self.rank, self.world)
+        return self.M * self.n / self.world       # bench multiplies by world: all columns once per step
+
+    def step_device(self):
+        return self._commit()
+
+    def step_e2e(self):
+        self.d_polys.copy_(self.h_polys, non_blocking=True)
+        units = self._commit()
+        self.h_result = self.result.cpu()
+        return units
+
+    def dominant(self):
+        tag = "fixed_msm" if self.k <= 17 else "msm_bucket"
+        return tag, 96.0 * self.n
+
+    def check(self):
+        """rank 0: the gathered commitments of the first and last column equal the single-call Params::commit"""
+        if self.rank != 0:
+            return None
+        res = self.result.cpu().numpy().view(np.uint64)
+        for j, col in self.sample.items():
+            exp = self.params.commit(col, self.blinds_np[j])
+            if not np.array_equal(res[j], exp):
+                return False
+        return True
+
+    def cpu(self, sample_log, steps=1):
+        from oracle import c_oracle as co
+        m = 1 << min(sample_log, self.k)
+        col = next(iter(self.sample.values())) if self.sample else rand_field(np.random.default_rng(1), m)
+        s, b = np.ascontiguousarray(col[:m]), np.ascontiguousarray(self.urs["g"][:m])
+        t = time.perf_counter()
+        for _ in range(steps):
+            co.best_multiexp(0, s, b)
+        dt = (time.perf_counter() - t) / steps
+        return m / dt, f"best_multiexp restated (C, {co.get_threads()} threads) on the first 2^{min(sample_log, self.k)} terms of one column", co.get_threads(), dt
+
+    def close(self):
+        self.params.close()
+        self.d_polys = self.h_polys = None
+
+
 class ProofWorkload:
     """create_proof for a batch of independent proofs of the Shot (k=11) or Board (k=12) circuit mirror.
     unit = proofs; every proof has its own RNG stream; witnesses cycle over 8 distinct synthetic jobs."""
@@ -476,6 +571,8 @@ class ProofWorkload:
         """EVERY proof of the last step goes through verify_proof on the device (bz_verify_proofs: one verdict per proof);
         the restated reference verifier (oracle) cross-checks the first and last proof of the first and last lane."""
         PR = self.PR
+        for lane in self.lanes:
+            lane["pk"].vk_commitments()           # keygen_vk's commitments: once per key, not part of verify_proof
         t0 = time.perf_counter()
         total, accepted = 0, 0
         for lane in self.lanes:
@@ -518,7 +615,7 @@ class ProofWorkload:
 
 
 WORKLOADS = {"msm": MsmWorkload, "ntt": NttWorkload, "shot": lambda a: ProofWorkload(a, "shot"), "board": lambda a: ProofWorkload(a, "board"),
-             "board_scaled": lambda a: ProofWorkload(a, "board_scaled")}
+             "board_scaled": lambda a: ProofWorkload(a, "board_scaled"), "commit": CommitWorkload}
 
 
 # ------------------------------------------------------------------------------------------------------

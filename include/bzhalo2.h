@@ -150,6 +150,11 @@ int bz_points_decompress(bz_ctx* ctx, int curve, const void* in32, uint64_t n, v
 int bz_params_commit(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* poly, const void* blind,
                      void* out_affine);
 
+/* Batched, device-resident form: `count` polynomials (count x n scalars, contiguous) and `count` blinds in, `count` affine
+ * points out -- all device pointers.  Independent column commitments are what a multi-GPU prover shards per GPU. */
+int bz_params_commit_batch_dev(bz_ctx* ctx, bz_params* params, int lagrange_basis, const void* d_polys,
+                               const void* d_blinds, uint32_t count, void* d_out_affine);
+
 /* The constraint system `pk.vk.cs` flattened.  Expressions are postfix token streams. */
 typedef struct {
   uint32_t op; /* 0 Constant(a = constant index) 1 Advice(a = column, b = rotation) 2 Fixed 3 Instance 4 Negated 5 Sum

@@ -79,3 +79,34 @@ def test_point_range_split_msm_allgather(tmp_path):
     out = str(tmp_path / "msm.txt")
     mp.spawn(_msm_worker, args=(2, _free_port(), out), nprocs=2, join=True)
     assert open(out).read() == "ok"
+
+
+def _commit_worker(rank, world, port, count, out_path):
+    """column-sharded commitments: every rank commits its column range with the oracle, the 64 B results are all-gathered"""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import numpy as np
+    from oracle import c_oracle as co, halo2 as H
+    from battlezips_halo2_b200.sharding import allgather_commitments
+    params = H.Params.new(5, 0)
+    rng = np.random.default_rng(5)
+    cols = co.from_u512(0, rng.integers(0, 2**63, size=(count * 32, 8), dtype=np.uint64)).reshape(count, 32, 4)
+    lo, hi = shard_range(count, rank, world)
+    per = (count + world - 1) // world
+    local = np.zeros((per, 8), dtype=np.uint64)
+    for j in range(lo, hi):
+        local[j - lo] = co.to_affine(0, params.commit(cols[j], 1 + j))[0]
+    got = allgather_commitments(torch.from_numpy(local.view(np.int64)), count, rank, world).numpy().view(np.uint64)
+    exp = np.stack([co.to_affine(0, params.commit(cols[j], 1 + j))[0] for j in range(count)])
+    ok = got.shape == (count, 8) and np.array_equal(got, exp)
+    if rank == 0:
+        open(out_path, "w").write("ok" if ok else "bad")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("count", [5, 8])
+def test_column_sharded_commitments_allgather(tmp_path, count):
+    out = str(tmp_path / "commit.txt")
+    mp.spawn(_commit_worker, args=(2, _free_port(), count, out), nprocs=2, join=True)
+    assert open(out).read() == "ok"
