@@ -369,7 +369,7 @@ class CommitWorkload:
         return units
 
     def dominant(self):
-        tag = "fixed_msm" if self.k <= 17 else "msm_bucket"
+        tag = "fixed_msm" if self.k <= 19 else "msm_bucket"
         return tag, 96.0 * self.n
 
     def check(self):
@@ -801,15 +801,23 @@ def main():
     if args.workload == "shot" and args.extras:
         if hasattr(wl, "close"):
             wl.close()
-        names = ["board", "msm", "ntt"] if world == 1 else ["msm"]
+        names = ["board", "msm", "ntt", "commit"] if world == 1 else ["msm", "commit"]
         for name in names:
-            w2 = WORKLOADS[name](args)
-            w2.setup(ctx, rank)
-            r = measure(args, w2, ctx, stream, rank, world, local_rank, want_cpu=False, steps=min(args.steps, 3), warmup=3)
-            if hasattr(w2, "close"):
-                w2.close()
-            if r is not None:
-                extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "int_pipe", "verified", "verify", "single_proof_ms")}
+            # an extra must never take the headline line down with it; under torchrun every rank takes the same branch
+            # (setup errors are deterministic), so the collectives inside stay matched
+            try:
+                a2 = argparse.Namespace(**vars(args))
+                if name == "commit":
+                    a2.k, a2.columns = 18, 16
+                w2 = WORKLOADS[name](a2)
+                w2.setup(ctx, rank)
+                r = measure(a2, w2, ctx, stream, rank, world, local_rank, want_cpu=False, steps=min(args.steps, 3), warmup=3)
+                if hasattr(w2, "close"):
+                    w2.close()
+                if r is not None:
+                    extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "scaling", "config", "e2e", "gpu_launches", "roofline", "int_pipe", "verified", "verify", "single_proof_ms")}
+            except Exception as e:          # noqa: BLE001
+                extras[name] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if rank == 0:
         if extras:
             line["extras"] = extras
