@@ -320,17 +320,23 @@ template <class P> __device__ __forceinline__ Fe<P> warp_scan_mul(Fe<P> v, bool 
 // One CTA (256 threads) per proof scans a whole array tile by tile with a running carry.
 //   mode 0: out[i] = prod_{t<i} in[t]   (exclusive prefix)      mode 1: out[i] = prod_{t>=i} in[t]  (inclusive suffix)
 constexpr int SCAN_THREADS = 256, SCAN_PER = 8, SCAN_TILE = SCAN_THREADS * SCAN_PER;
+// Large arrays (the scaled circuit) run it three times: CTA c of grid.x owns `tiles_per_cta` tiles -- pass 1 writes only the
+// product of its tiles (totals_out), the same kernel then scans those totals (one tile), pass 3 rescans with the carry-in.
 template <class P>
-__global__ void __launch_bounds__(SCAN_THREADS) product_scan_kernel(const Fe<P>* __restrict__ in, Fe<P>* __restrict__ out, uint32_t n, uint64_t stride, int mode) {
+__global__ void __launch_bounds__(SCAN_THREADS) product_scan_kernel(const Fe<P>* __restrict__ in, Fe<P>* __restrict__ out, uint32_t n, uint64_t stride, int mode,
+                                                                    uint32_t tiles_per_cta = 0xffffffffu, const Fe<P>* __restrict__ carry_in = nullptr,
+                                                                    Fe<P>* __restrict__ totals_out = nullptr) {
   __shared__ Fe<P> warp_tot[SCAN_THREADS / 32];
   __shared__ Fe<P> carry_sh;
   const uint32_t b = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const Fe<P>* src = in + (uint64_t)b * stride;
   Fe<P>* dst = out + (uint64_t)b * stride;
   const bool rev = mode == 1;
-  Fe<P> carry = fe_one<P>();
+  Fe<P> carry = carry_in ? fe_load(carry_in + (uint64_t)b * gridDim.x + blockIdx.x) : fe_one<P>();
   const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
-  for (uint32_t tile = 0; tile < ntiles; ++tile) {
+  const uint32_t tile0 = tiles_per_cta == 0xffffffffu ? 0u : blockIdx.x * tiles_per_cta;
+  const uint32_t tile1 = tiles_per_cta == 0xffffffffu ? ntiles : min(ntiles, tile0 + tiles_per_cta);
+  for (uint32_t tile = tile0; tile < tile1; ++tile) {
     // element range of this thread inside the tile (in scan order)
     uint32_t base = tile * SCAN_TILE + tid * SCAN_PER;
     Fe<P> v[SCAN_PER];
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) product_scan_kernel(const Fe<P>*
 #pragma unroll
     for (int j = 0; j < SCAN_PER; ++j) {
       uint32_t pos = base + j;
-      if (pos < n) {
+      if (pos < n && !totals_out) {
         uint32_t idx = rev ? (n - 1 - pos) : pos;
         if (mode == 0) { fe_store(dst + idx, run); run = fe_mul(run, v[j]); }
         else { run = fe_mul(run, v[j]); fe_store(dst + idx, run); }
@@ -373,6 +379,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) product_scan_kernel(const Fe<P>*
     carry = carry_sh;
     __syncthreads();
   }
+  if (totals_out && tid == 0) fe_store(totals_out + (uint64_t)b * gridDim.x + blockIdx.x, carry);
 }
 
 // z[i] = z0 * pnum[i] * sden[i] / sden[0]   (z0: *z0_ptr[b * z0_stride] or 1 if null)

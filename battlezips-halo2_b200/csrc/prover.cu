@@ -811,8 +811,22 @@ struct Prover {
   void grand_product(PolyRef zref, bool has_z0, PolyRef z0ref, uint32_t z0_index) {
     DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n; DFe* pnum = den + (uint64_t)B * n; DFe* sden = pnum + (uint64_t)B * n;
     ProfScope prof(C, PROF_SCAN);
-    product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0);
-    product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
+    const uint32_t ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+    if (ntiles <= 8) {          // Shot / Board: one CTA per proof walks the 1-2 tiles
+      product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0);
+      product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
+    } else {                    // large domains: tile products, scan of the tile products, rescan with carry-in
+      BZ_CHECK(ntiles <= (uint32_t)SCAN_TILE, "grand product: domain too large for the two-level scan");
+      w.scan_tmp.ensure((size_t)4 * B * ntiles * 32);
+      DFe* tot_n = (DFe*)w.scan_tmp.p; DFe* car_n = tot_n + (size_t)B * ntiles; DFe* tot_d = car_n + (size_t)B * ntiles; DFe* car_d = tot_d + (size_t)B * ntiles;
+      product_scan_kernel<FpP><<<dim3(ntiles, B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0, 1u, nullptr, tot_n);
+      product_scan_kernel<FpP><<<dim3(ntiles, B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1, 1u, nullptr, tot_d);
+      product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(tot_n, car_n, ntiles, ntiles, 0);
+      product_scan_kernel<FpP><<<dim3(1, B), SCAN_THREADS, 0, st>>>(tot_d, car_d, ntiles, ntiles, 0);
+      product_scan_kernel<FpP><<<dim3(ntiles, B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0, 1u, car_n, nullptr);
+      product_scan_kernel<FpP><<<dim3(ntiles, B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1, 1u, car_d, nullptr);
+      C->kernel_launches += 4;
+    }
     grand_product_finish_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(pnum, sden, n, reg, zref, n, z0ref, z0_index, has_z0 ? 1 : 0);
     C->kernel_launches += 3;
   }

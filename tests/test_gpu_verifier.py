@@ -122,3 +122,26 @@ def test_shot_batch_config3_shape(ctx):
     other = next(j for j in range(8) if jobs[j][2].instance != instances[b])
     assert PR.verify_proofs(pk, [jobs[other][2].instance], [proofs[b]]) == [False]
     pk.close(); params.close()
+
+
+def test_scaled_board_k15_roundtrip_on_device_only(ctx):
+    """BASELINE config 5 in small, without the (slow) oracle: the Board circuit tiled down 2^15 rows -- URS from Params::new on
+    the device, keygen on the device, create_proof (two-level grand-product scans, radix-sort lookup permutation), and
+    verify_proof on the device accepts; a flipped bit is rejected.  Size-independent property: prover and verifier meet."""
+    from battlezips_halo2_b200 import arithmetic as ar
+    from battlezips_halo2_b200.circuits import board_circuit_scaled
+    from battlezips_halo2_b200.plonk import prover as PR
+    from oracle import halo2 as H
+    from tests.util_prover import VK_REPR
+    k = 15
+    cs, cfg, asg = board_circuit_scaled(k)
+    ir = cs.to_ir()
+    urs = ar.params_new(ctx, k, curve=0)
+    params = PR.Params(ctx, k, urs["g"], urs["g_lagrange"], urs["w"], urs["u"])
+    pk = PR.ProvingKey(ctx, params, ir, asg.fixed, asg.permutation_mapping(), VK_REPR)
+    advice = np.stack([PR.mont(col) for col in asg.advice])
+    wide = H.splitmix64_wide(0xB200 + k, pk.num_random)
+    proof = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
+    assert PR.verify_proofs(pk, [asg.instance], [proof]) == [True]
+    assert PR.verify_proofs(pk, [asg.instance], [_flip(proof, len(proof) // 2)]) == [False]
+    pk.close(); params.close()
