@@ -403,6 +403,8 @@ __global__ void grand_product_finish_kernel(const Fe<P>* __restrict__ pnum, cons
 // ---- Horner evaluation: one CTA per (query, proof) ---------------------------------------------------
 struct EvalQuery { PolyRef poly; uint32_t point_const; };     // point = consts[b][point_const]
 constexpr int EVALQ_THREADS = 128;
+// Large polynomials: gridDim.z CTAs per (query, proof), each over a contiguous slice; the slice sums go to `out` at
+// [(b * out_stride + qi) * gridDim.z + z] and eval_reduce_kernel adds them.
 template <class P>
 __global__ void __launch_bounds__(EVALQ_THREADS) eval_queries_kernel(Regions reg, uint32_t n, const EvalQuery* __restrict__ queries,
                                     const Fe<P>* __restrict__ consts, uint32_t cstride, Fe<P>* __restrict__ out, uint32_t out_stride) {
@@ -411,8 +413,9 @@ __global__ void __launch_bounds__(EVALQ_THREADS) eval_queries_kernel(Regions reg
   const EvalQuery q = queries[qi];
   const Fe<P>* poly = region_ptr<P>(reg, q.poly, b, n);
   const Fe<P> x = fe_load(consts + (uint64_t)b * cstride + q.point_const);
-  const uint32_t len = (n + EVALQ_THREADS - 1) / EVALQ_THREADS;
-  const uint32_t lo = tid * len, hi = min(lo + len, n);
+  const uint32_t slice = (n + gridDim.z - 1) / gridDim.z, s_lo = min(blockIdx.z * slice, n), s_hi = min(s_lo + slice, n);
+  const uint32_t len = (s_hi - s_lo + EVALQ_THREADS - 1) / EVALQ_THREADS;
+  const uint32_t lo = min(s_lo + tid * len, s_hi), hi = min(lo + len, s_hi);
   Fe<P> acc = fe_zero<P>();
   for (uint32_t i = hi; i > lo; --i) acc = fe_add(fe_mul(acc, x), fe_load(poly + i - 1));
   if (lo < hi && lo > 0) acc = fe_mul(acc, fe_pow_u64<P>(x, lo));
@@ -422,7 +425,16 @@ __global__ void __launch_bounds__(EVALQ_THREADS) eval_queries_kernel(Regions reg
     if (tid < d) sh[tid] = fe_add(sh[tid], sh[tid + d]);
     __syncthreads();
   }
-  if (tid == 0) fe_store(out + (uint64_t)b * out_stride + qi, sh[0]);
+  if (tid == 0) fe_store(out + ((uint64_t)b * out_stride + qi) * gridDim.z + blockIdx.z, sh[0]);
+}
+// out[i] = sum of the `splits` slice sums of evaluation i
+template <class P>
+__global__ void eval_reduce_kernel(const Fe<P>* __restrict__ partial, uint32_t splits, Fe<P>* __restrict__ out, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= count) return;
+  Fe<P> acc = fe_zero<P>();
+  for (uint32_t z = 0; z < splits; ++z) acc = fe_add(acc, fe_load(partial + (uint64_t)i * splits + z));
+  fe_store(out + i, acc);
 }
 
 // ---- out[i] = Horner_j( polys[j][i] ; x ) = ((p0 x + p1) x + p2) ...   (multiopen / vanishing / IPA combos) ----
@@ -446,17 +458,23 @@ __global__ void lincomb_kernel(Regions reg, uint32_t n, const LinCombDesc* __res
 // chunk transfer maps r[lo] = L + pt^len * r[hi].
 constexpr int KATE_THREADS = 256;
 struct KateDesc { PolyRef in, out; uint32_t point_const; };
+// Large polynomials: gridDim.z CTAs per (division, proof), CTA z over the contiguous slice [z*slice, (z+1)*slice).  Pass 1
+// (totals_out != null) only reports r[slice_lo] under a zero carry-in; kate_carry_kernel chains the slices from the top;
+// pass 2 (carry_in != null) redoes the slice with its true carry-in r[slice_hi] and writes the quotient.
 template <class P>
 __global__ void __launch_bounds__(KATE_THREADS) kate_division_kernel(Regions reg, uint32_t n, const KateDesc* __restrict__ descs,
-                                     const Fe<P>* __restrict__ consts, uint32_t cstride) {
+                                     const Fe<P>* __restrict__ consts, uint32_t cstride,
+                                     const Fe<P>* __restrict__ carry_in = nullptr, Fe<P>* __restrict__ totals_out = nullptr) {
   __shared__ Fe<P> sh[2][KATE_THREADS + 1];
   const KateDesc d = descs[blockIdx.x];
   const uint32_t b = blockIdx.y, tid = threadIdx.x;
   const Fe<P>* a = region_ptr<P>(reg, d.in, b, n);
   Fe<P>* q = region_ptr<P>(reg, d.out, b, n);
   const Fe<P> pt = fe_load(consts + (uint64_t)b * cstride + d.point_const);
-  const uint32_t len = (n + KATE_THREADS - 1) / KATE_THREADS;
-  const uint32_t lo = min(tid * len, n), hi = min(lo + len, n);
+  const uint32_t slice = (n + gridDim.z - 1) / gridDim.z, s_lo = min(blockIdx.z * slice, n), s_hi = min(s_lo + slice, n);
+  const uint64_t slot = ((uint64_t)b * gridDim.x + blockIdx.x) * gridDim.z + blockIdx.z;
+  const uint32_t len = (s_hi - s_lo + KATE_THREADS - 1) / KATE_THREADS;
+  const uint32_t lo = min(s_lo + tid * len, s_hi), hi = min(lo + len, s_hi);
   // local pass with zero carry-in
   Fe<P> r = fe_zero<P>();
   for (uint32_t i = hi; i > lo; --i) {
@@ -477,13 +495,35 @@ __global__ void __launch_bounds__(KATE_THREADS) kate_division_kernel(Regions reg
     cur ^= 1;
     __syncthreads();
   }
-  // carry-in for this thread = R_{t+1} = r[hi]
+  if (totals_out) {                                             // r[s_lo] under a zero carry-in
+    if (tid == 0) fe_store(totals_out + slot, sh[cur][0]);
+    return;
+  }
+  // carry-in for this thread = r[hi] = (zero-carry scan value of the next thread) + pt^(s_hi - hi) * (slice carry-in)
   Fe<P> carry = (tid + 1 < KATE_THREADS) ? sh[cur][tid + 1] : fe_zero<P>();
+  if (carry_in && lo < hi) carry = fe_add(carry, fe_mul(fe_pow_u64<P>(pt, s_hi - hi), fe_load(carry_in + slot)));
   r = carry;
   for (uint32_t i = hi; i > lo; --i) {
     Fe<P> ai = (i < n) ? fe_load(a + i) : fe_zero<P>();
     r = fe_add(ai, fe_mul(pt, r));
     fe_store(q + i - 1, r);
+  }
+}
+// carries[z] = r[slice_hi(z)], chained from the top slice down: one thread per (division, proof)
+template <class P>
+__global__ void kate_carry_kernel(uint32_t n, uint32_t splits, uint32_t ndiv, uint32_t batch, const KateDesc* __restrict__ descs,
+                                  const Fe<P>* __restrict__ consts, uint32_t cstride, const Fe<P>* __restrict__ totals, Fe<P>* __restrict__ carries) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= ndiv * batch) return;
+  const uint32_t b = t / ndiv, di = t % ndiv;
+  const Fe<P> pt = fe_load(consts + (uint64_t)b * cstride + descs[di].point_const);
+  const uint32_t slice = (n + splits - 1) / splits;
+  const uint64_t base = ((uint64_t)b * ndiv + di) * splits;
+  Fe<P> top = fe_zero<P>();
+  for (int z = (int)splits - 1; z >= 0; --z) {
+    const uint32_t s_lo = min((uint32_t)z * slice, n), s_hi = min(s_lo + slice, n);
+    fe_store(carries + base + z, top);
+    top = fe_add(fe_load(totals + base + z), fe_mul(fe_pow_u64<P>(pt, s_hi - s_lo), top));
   }
 }
 

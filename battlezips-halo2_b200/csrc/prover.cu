@@ -831,11 +831,22 @@ struct Prover {
     C->kernel_launches += 3;
   }
 
+  // Horner evaluation of nq polynomials per proof into w.evalout[b * nq + q]
+  void eval_launch(const EvalQuery* d_queries, uint32_t nq) {
+    const uint32_t splits = std::max(1u, n / 16384u);        // large domains: several CTAs per (query, proof)
+    if (splits == 1) eval_queries_kernel<FpP><<<dim3(nq, B), EVALQ_THREADS, 0, st>>>(reg, n, d_queries, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, nq);
+    else {
+      w.eval_tmp.ensure((size_t)B * nq * splits * 32);
+      eval_queries_kernel<FpP><<<dim3(nq, B, splits), EVALQ_THREADS, 0, st>>>(reg, n, d_queries, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.eval_tmp.p, nq);
+      eval_reduce_kernel<FpP><<<(B * nq + 127) / 128, 128, 0, st>>>((const DFe*)w.eval_tmp.p, splits, (DFe*)w.evalout.p, B * nq);
+      C->kernel_launches++;
+    }
+    C->kernel_launches++;
+  }
   void evaluate(const EvalQuery* d_queries, uint32_t nq, std::vector<std::vector<HFe>>& out) {
     {
       ProfScope prof(C, PROF_EVAL);
-      eval_queries_kernel<FpP><<<dim3(nq, B), EVALQ_THREADS, 0, st>>>(reg, n, d_queries, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, nq);
-      C->kernel_launches++;
+      eval_launch(d_queries, nq);
     }
     BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.evalout.p, (size_t)B * nq * 32, cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
@@ -1213,7 +1224,17 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         }
       KateDesc* dk = upload_desc(kd);
       ProfScope prof(C, PROF_POLY);
-      kate_division_kernel<FpP><<<dim3((unsigned)kd.size(), B), KATE_THREADS, 0, st>>>(reg, n, dk, (const DFe*)w.consts.p, pk.cstride);
+      const uint32_t splits = std::max(1u, n / 16384u);
+      if (splits == 1) kate_division_kernel<FpP><<<dim3((unsigned)kd.size(), B), KATE_THREADS, 0, st>>>(reg, n, dk, (const DFe*)w.consts.p, pk.cstride);
+      else {                       // large domains: slice totals, chain, redo with the carry-in
+        const size_t slots = (size_t)B * kd.size() * splits;
+        w.eval_tmp.ensure(2 * slots * 32);
+        DFe* totals = (DFe*)w.eval_tmp.p; DFe* carries = totals + slots;
+        kate_division_kernel<FpP><<<dim3((unsigned)kd.size(), B, splits), KATE_THREADS, 0, st>>>(reg, n, dk, (const DFe*)w.consts.p, pk.cstride, nullptr, totals);
+        kate_carry_kernel<FpP><<<(unsigned)((B * kd.size() + 63) / 64), 64, 0, st>>>(n, splits, (uint32_t)kd.size(), B, dk, (const DFe*)w.consts.p, pk.cstride, totals, carries);
+        kate_division_kernel<FpP><<<dim3((unsigned)kd.size(), B, splits), KATE_THREADS, 0, st>>>(reg, n, dk, (const DFe*)w.consts.p, pk.cstride, carries, nullptr);
+        C->kernel_launches += 2;
+      }
       C->kernel_launches++;
     }
     std::vector<LinCombDesc> l2{LinCombDesc{PolyRef{R_MISC, pk.m_qprime}, pk.C_X2, nps, 0}};
@@ -1251,9 +1272,9 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     EvalQuery* deq = upload_desc(eq);
     {
       ProfScope prof(C, PROF_EVAL);
-      eval_queries_kernel<FpP><<<dim3(1, B), EVALQ_THREADS, 0, st>>>(reg, n, deq, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, 1);
+      eval_launch(deq, 1);
       tweak_element_kernel<FpP><<<(B + 63) / 64, 64, 0, st>>>(reg, n, PolyRef{R_SPOLY, 0}, 0, (const DFe*)w.evalout.p, 1, 0, 0, B);
-      C->kernel_launches += 2;
+      C->kernel_launches += 1;
     }
     std::vector<CommitReq> rq{{PolyRef{R_SPOLY, 0}, false}};
     std::vector<std::vector<HFe>> sb(B, std::vector<HFe>(1));
@@ -1275,11 +1296,11 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     EvalQuery* deq2 = upload_desc(eq2);
     {
       ProfScope prof(C, PROF_IPA);
-      eval_queries_kernel<FpP><<<dim3(1, B), EVALQ_THREADS, 0, st>>>(reg, n, deq2, (const DFe*)w.consts.p, pk.cstride, (DFe*)w.evalout.p, 1);
+      eval_launch(deq2, 1);
       tweak_element_kernel<FpP><<<(B + 63) / 64, 64, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_pprime}, 0, (const DFe*)w.evalout.p, 1, 0, 0, B);
       powers_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_b}, (const DFe*)w.consts.p, pk.cstride, pk.C_X3);
       fill_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_coef}, n, dfe(F.one()));
-      C->kernel_launches += 4;
+      C->kernel_launches += 3;
     }
     // rounds
     std::vector<void*> mainp((size_t)B * 2), extrap((size_t)B * 2);
