@@ -17,7 +17,7 @@ class BzError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "lib", "libbzhalo2.so")
+    return os.environ.get("BZ_LIB") or os.path.join(_HERE, "lib", "libbzhalo2.so")       # BZ_LIB: A/B builds only
 
 
 def header_path():
