@@ -1322,10 +1322,16 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       }
       run_msms(false, mainp, extrap, n_msm);
       read_points(n_msm, 2, pts);
+      std::vector<HFe> us(B), uinvs(B);
       for (uint32_t b = 0; b < B; ++b) {
         t_write_point(ps[b], pts[b][0]);
         t_write_point(ps[b], pts[b][1]);
-        HFe u = t_squeeze(ps[b], F), uinv = F.inv(u);
+        us[b] = t_squeeze(ps[b], F);
+      }
+      uinvs = us;
+      host_batch_invert(F, uinvs);                  // one inversion per round for the whole batch
+      for (uint32_t b = 0; b < B; ++b) {
+        const HFe u = us[b], uinv = uinvs[b];
         ps[b].consts[pk.C_U] = u; ps[b].consts[pk.C_UINV] = uinv;
         HFe lr = rnd_host(ps[b], F, pk.r_ipa + 2 * j), rr = rnd_host(ps[b], F, pk.r_ipa + 2 * j + 1);
         fblind[b] = F.add(fblind[b], F.add(F.mul(lr, uinv), F.mul(rr, u)));

@@ -110,6 +110,20 @@ struct PkImpl {
   ~PkImpl() { if (work.h_pinned) cudaFreeHost(work.h_pinned); if (work.h_err) cudaFreeHost(work.h_err); }
 };
 
+// Montgomery's trick on the host: v[i] <- 1 / v[i] (zeros stay zero), one field inversion for the whole vector
+static inline void host_batch_invert(const bzh::Field& F, std::vector<HFe>& v) {
+  std::vector<HFe> pre(v.size());
+  HFe acc = F.one();
+  for (size_t i = 0; i < v.size(); ++i) { pre[i] = acc; if (!v[i].is_zero()) acc = F.mul(acc, v[i]); }
+  HFe inv = F.inv(acc);
+  for (size_t i = v.size(); i-- > 0;) {
+    if (v[i].is_zero()) continue;
+    const HFe t = F.mul(inv, pre[i]);
+    inv = F.mul(inv, v[i]);
+    v[i] = t;
+  }
+}
+
 struct HostPoint { uint8_t x[32], y[32]; bool identity; };
 
 static inline void affine_to_host(const bzh::Field& Fq, const uint64_t* mont, HostPoint& p) {

@@ -172,7 +172,7 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
   const uint32_t cstride = 2 + k;
   std::vector<HFe> s_consts((size_t)B * cstride, F.zero()), fx_extra((size_t)B * 2, F.zero());
   std::vector<uint8_t> alive(B, 1);
-  const HFe one = F.one();
+  const HFe one = F.one(), n_inv = F.inv(F.from_u64(n));
   for (uint32_t b = 0; b < B; ++b) {
     const uint8_t* proof = proofs + (size_t)b * proof_len;
     bool okp = true;
@@ -213,12 +213,14 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
     if (!okp) { alive[b] = 0; continue; }
     // ---- expected h(x)
     HFe xn = x; for (uint32_t i = 0; i < k; ++i) xn = F.sqr(xn);
-    const HFe xn_m1 = F.sub(xn, one), n_inv = F.inv(F.from_u64(n));
-    std::vector<HFe> l_evals;                       // rotations -(bf+1) .. 0
-    for (int rot = -((int)bf + 1); rot <= 0; ++rot) {
-      HFe w_i = F.pow_u64(pk.omega_inv, (uint64_t)(-rot));
-      l_evals.push_back(F.mul(F.mul(F.mul(w_i, xn_m1), n_inv), F.inv(F.sub(x, w_i))));
-    }
+    const HFe xn_m1 = F.sub(xn, one);
+    std::vector<HFe> w_is, inv1;                     // rotations -(bf+1) .. 0; one inversion for (x - w_i)..., (x^n - 1)
+    for (int rot = -((int)bf + 1); rot <= 0; ++rot) { w_is.push_back(F.pow_u64(pk.omega_inv, (uint64_t)(-rot))); inv1.push_back(F.sub(x, w_is.back())); }
+    inv1.push_back(xn_m1);
+    host_batch_invert(F, inv1);
+    std::vector<HFe> l_evals;
+    for (size_t i = 0; i < w_is.size(); ++i) l_evals.push_back(F.mul(F.mul(F.mul(w_is[i], xn_m1), n_inv), inv1[i]));
+    const HFe xn_m1_inv = inv1.back();
     const HFe l_last = l_evals[0], l_0 = l_evals[bf + 1];
     HFe l_blind = F.zero();
     for (uint32_t i = 1; i <= bf; ++i) l_blind = F.add(l_blind, l_evals[i]);
@@ -267,7 +269,7 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
       fold(F.mul(l_0, F.sub(a, s)));
       fold(F.mul(F.mul(F.sub(a, s), F.sub(a, a_inv)), one_minus));
     }
-    expected_h = F.mul(expected_h, F.inv(xn_m1));
+    expected_h = F.mul(expected_h, xn_m1_inv);
     // ---- multiopen verifier
     const HFe x1 = t_squeeze(ps, F), x2 = t_squeeze(ps, F);
     auto rot_point = [&](int r) { return r >= 0 ? F.mul(x, F.pow_u64(pk.omega, (uint64_t)r)) : F.mul(x, F.pow_u64(pk.omega_inv, (uint64_t)(-r))); };
@@ -298,17 +300,28 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
     for (uint32_t s2 = 0; s2 < nps && okp; ++s2) okp = read_scalar(off_uevals + 32 * s2, u_evals[s2]);
     if (!okp) { alive[b] = 0; continue; }
     HFe msm_eval = F.zero();
-    for (uint32_t s2 = 0; s2 < nps; ++s2) {
-      std::vector<HFe> pts;
-      for (int r : pk.point_sets[s2]) pts.push_back(rot_point(r));
-      HFe r_eval = F.zero(), den = one;                          // lagrange_interpolate(points, evals)(x3)
-      for (size_t j = 0; j < pts.size(); ++j) {
-        HFe num = one, dj = one;
-        for (size_t m2 = 0; m2 < pts.size(); ++m2) if (m2 != j) { num = F.mul(num, F.sub(x3, pts[m2])); dj = F.mul(dj, F.sub(pts[j], pts[m2])); }
-        r_eval = F.add(r_eval, F.mul(F.mul(q_eval_sets[s2][j], num), F.inv(dj)));
-        den = F.mul(den, F.sub(x3, pts[j]));
+    {
+      // lagrange_interpolate(points, evals)(x3) per set: all denominators of all sets share one inversion
+      std::vector<std::vector<HFe>> pts(nps), nums(nps);
+      std::vector<HFe> inv2;
+      for (uint32_t s2 = 0; s2 < nps; ++s2) {
+        for (int r : pk.point_sets[s2]) pts[s2].push_back(rot_point(r));
+        HFe den = one;
+        for (size_t j = 0; j < pts[s2].size(); ++j) {
+          HFe num = one, dj = one;
+          for (size_t m2 = 0; m2 < pts[s2].size(); ++m2) if (m2 != j) { num = F.mul(num, F.sub(x3, pts[s2][m2])); dj = F.mul(dj, F.sub(pts[s2][j], pts[s2][m2])); }
+          nums[s2].push_back(num); inv2.push_back(dj);
+          den = F.mul(den, F.sub(x3, pts[s2][j]));
+        }
+        inv2.push_back(den);
       }
-      msm_eval = F.add(F.mul(msm_eval, x2), F.mul(F.sub(u_evals[s2], r_eval), F.inv(den)));
+      host_batch_invert(F, inv2);
+      size_t at = 0;
+      for (uint32_t s2 = 0; s2 < nps; ++s2) {
+        HFe r_eval = F.zero();
+        for (size_t j = 0; j < pts[s2].size(); ++j) r_eval = F.add(r_eval, F.mul(F.mul(q_eval_sets[s2][j], nums[s2][j]), inv2[at++]));
+        msm_eval = F.add(F.mul(msm_eval, x2), F.mul(F.sub(u_evals[s2], r_eval), inv2[at++]));
+      }
     }
     const HFe x4 = t_squeeze(ps, F);
     HFe v = msm_eval;
@@ -345,7 +358,9 @@ void Verifier::run(const void* instances, const uint32_t* instance_lens, uint32_
     }
     push(point_mont(qprime_pt), x4pow[nps]);
     push(point_mont(s_pt), xi);
-    for (uint32_t j = 0; j < k; ++j) { push(point_mont(l_pt[j]), F.inv(us[j])); push(point_mont(r_pt[j]), us[j]); }
+    std::vector<HFe> us_inv = us;
+    host_batch_invert(F, us_inv);
+    for (uint32_t j = 0; j < k; ++j) { push(point_mont(l_pt[j]), us_inv[j]); push(point_mont(r_pt[j]), us[j]); }
     BZ_CHECK(nvi == NV, "internal: verifier point count mismatch");
     HFe* sc = &s_consts[(size_t)b * cstride];
     sc[0] = F.neg(c_sc); sc[1] = F.neg(v);
