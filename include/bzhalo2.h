@@ -76,7 +76,7 @@ int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes);
 
 /* ---- ff::Field / group ops on host slices (pasta_curves semantics; used by the parity suite and by the
  * shim for the few scalar-sized steps it does not want to do on the CPU) ------------------------------ */
-/* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 (0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
+/* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 over the slice (ff::BatchInvert: Montgomery trick, 0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
  *     6 canonical -> Montgomery, 7 -a, 8 a^2 */
 int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
 /* affine in, affine out (64 B each): op 0 a+b, 1 2a, 2 a-b, 3 2a+b (full projective add), 4 [k]a, k = first u32 of b */

@@ -30,7 +30,9 @@ def test_field_ops(field, ctx, oracle_c):
     assert co.from_mont(field, ar.field_op(ctx, field, "sub", am, bm)) == [(x - y) % p for x, y in zip(a, b)]
     assert co.from_mont(field, ar.field_op(ctx, field, "neg", am)) == [(-x) % p for x in a]
     assert co.from_mont(field, ar.field_op(ctx, field, "sqr", am)) == [x * x % p for x in a]
-    assert co.from_mont(field, ar.field_op(ctx, field, "inv", am[:64])) == [F.inv(x) for x in a[:64]]
+    # ff::BatchInvert semantics (zeros stay zero); 600 elements = 37 full runs of the Montgomery trick + a ragged tail
+    assert co.from_mont(field, ar.field_op(ctx, field, "inv", am)) == [F.inv(x) for x in a]
+    assert co.from_mont(field, ar.field_op(ctx, field, "inv", am[:1])) == [F.inv(a[0])]
     # Montgomery conversions are bit-exact with pasta's in-memory form
     raw = co.ints_to_raw(a)
     assert np.array_equal(ar.field_op(ctx, field, "to_mont", raw), am)
