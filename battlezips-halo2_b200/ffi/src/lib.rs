@@ -43,6 +43,7 @@ extern "C" {
     pub fn bz_params_create(ctx: *mut bz_ctx, k: u32, curve: c_int, g: *const c_void, g_lagrange: *const c_void, w: *const c_void, u: *const c_void, window_bits: c_int, out: *mut *mut bz_params) -> c_int;
     pub fn bz_params_destroy(p: *mut bz_params);
     pub fn bz_params_commit(ctx: *mut bz_ctx, p: *mut bz_params, lagrange_basis: c_int, poly: *const c_void, blind: *const c_void, out_affine: *mut c_void) -> c_int;
+    pub fn bz_params_commit_batch_dev(ctx: *mut bz_ctx, p: *mut bz_params, lagrange_basis: c_int, d_polys: *const c_void, d_blinds: *const c_void, count: u32, d_out_affine: *mut c_void) -> c_int;
     // plonk/prover.rs
     pub fn bz_pk_create(ctx: *mut bz_ctx, p: *mut bz_params, cs: *const bz_circuit, fixed_values: *const c_void, sigma_values: *const c_void, out: *mut *mut bz_pk) -> c_int;
     pub fn bz_pk_create_from_assembly(ctx: *mut bz_ctx, p: *mut bz_params, cs: *const bz_circuit, fixed_values: *const c_void, mapping: *const u32, out: *mut *mut bz_pk) -> c_int;
