@@ -12,6 +12,7 @@
 #include <tuple>
 #include <vector>
 #include "host_field.h"
+#include <nvtx3/nvToolsExt.h>
 
 namespace bz {
 
@@ -86,16 +87,32 @@ struct Ctx {
   ~Ctx();
 };
 
+// NVTX range (header-only nvtx3; a no-op unless a profiler is attached): prover phases and kernel classes show up by name
+// in Nsight timelines and can be used as ncu range filters
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
+inline const char* prof_tag_name(int tag) {
+  static const char* names[] = {"ntt_pass", "msm_digits", "msm_sort", "msm_bucket", "msm_reduce", "msm_combine", "fixed_msm", "quotient",
+                                "scan", "eval", "poly", "ipa", "other"};
+  return tag >= 0 && tag < (int)(sizeof(names) / sizeof(names[0])) ? names[tag] : "?";
+}
+
 // RAII scope: records a start/stop event pair around the launches issued inside it (only when profiling)
 struct ProfScope {
   Ctx* c; ProfRec r; bool on;
   ProfScope(Ctx* ctx, int tag) : c(ctx), on(ctx->profiling) {
+    nvtxRangePushA(prof_tag_name(tag));
     if (!on) return;
     r.tag = tag;
     cudaEventCreate(&r.a); cudaEventCreate(&r.b);
     cudaEventRecord(r.a, c->stream);
   }
   ~ProfScope() {
+    nvtxRangePop();
     if (!on) return;
     cudaEventRecord(r.b, c->stream);
     c->prof.push_back(r);

@@ -907,8 +907,10 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         BZ_CUDA(cudaMemcpyAsync(val(b, pk.slot_inst(i)), (const char*)instances + ((size_t)b * I + i) * instance_stride * 32,
                                 (size_t)instance_lens[i] * 32, cudaMemcpyDefault, st));
   }
+  std::unique_ptr<NvtxRange> phase;
   desc_off = 0;
   // ---- step 1: instance commitments (blind 1), absorbed
+  phase.reset(); phase.reset(new NvtxRange("step 1-2: instance + advice commitments, NTTs"));
   std::vector<std::vector<HostPoint>> pts;
   if (I) {
     std::vector<CommitReq> reqs;
@@ -935,6 +937,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   for (uint32_t b = 0; b < B; ++b) ps[b].consts[pk.C_THETA] = t_squeeze(ps[b], F);
   upload_consts();
   // ---- steps 4-5: lookups
+  phase.reset(); phase.reset(new NvtxRange("steps 4-5: lookup compression, permutation, commitments"));
   if (L) {
     {
       EvalArgs<FpP> a{};
@@ -1043,6 +1046,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   upload_consts();
   desc_off = 0;
   // ---- steps 7-9: permutation products, lookup products, random polynomial: one commitment batch
+  phase.reset(); phase.reset(new NvtxRange("steps 7-9: grand products, random polynomial"));
   {
     DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n;
     for (uint32_t s = 0; s < pk.nsets; ++s) {
@@ -1124,6 +1128,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   upload_consts();
   desc_off = 0;
   // ---- steps 11-12: h(X)
+  phase.reset(); phase.reset(new NvtxRange("steps 11-13: h(X), pieces"));
   {
     EvalArgs<FpP> a{};
     a.code = (const uint32_t*)pk.q_code.p; a.n_instr = pk.q_ninstr; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot.p;
@@ -1181,12 +1186,14 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     lincomb(ld, refs);
   }
   // ---- steps 14-18: evaluations
+  phase.reset(); phase.reset(new NvtxRange("steps 14-18: evaluations"));
   {
     std::vector<std::vector<HFe>> ev;
     evaluate((const EvalQuery*)pk.d_evals.p, (uint32_t)pk.evals.size(), ev);
     for (uint32_t b = 0; b < B; ++b) for (const HFe& e : ev[b]) t_write_scalar(ps[b], F, e);
   }
   // ---- step 20: multiopen
+  phase.reset(); phase.reset(new NvtxRange("step 20: multiopen"));
   const uint32_t nps = (uint32_t)pk.point_sets.size();
   std::vector<std::vector<HFe>> q_blinds(B, std::vector<HFe>(nps));
   {
@@ -1265,6 +1272,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     }
   }
   // ---- step 21: inner product argument
+  phase.reset(); phase.reset(new NvtxRange("step 21: inner product argument"));
   {
     desc_off = 0;
     // S(X): random coefficients with S(x3) = 0
