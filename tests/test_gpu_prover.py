@@ -193,3 +193,32 @@ def test_sanity_checks_flag_catches_broken_copy_constraint(ctx, monkeypatch):
     bad = PR.create_proofs(pk, [job.instances], adv[None], job.wide(0)[None])[0]     # without the flag: a proof that does not verify
     assert PR.verify_proofs(pk, [job.instances], [bad]) == [False]
     pk.close(); params.close()
+
+
+def test_device_proofs_equal_committed_goldens(ctx):
+    """The committed oracle goldens (tests/golden/proofs.npz): tiny k = 5, Shot k = 11 and Board k = 12 proofs from the
+    device are byte-identical -- no oracle run needed on the GPU box for this comparison (the witness / keys still come
+    from the circuit mirrors)."""
+    import os
+    from battlezips_halo2_b200.plonk import prover as PR
+    from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
+    from tests.util_prover import VK_REPR
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proofs.npz"))
+    job = Job(*tiny_circuit(5))
+    params, pk = job.device_keys(ctx, window_bits=7)
+    got = _prove(job, pk, [0, 3])
+    assert got[0] == bytes(gold["tiny_k5_idx0"]) and got[1] == bytes(gold["tiny_k5_idx3"])
+    pk.close(); params.close()
+    for make, name in ((shot_circuit, "shot_w0_idx0"), (board_circuit, "board_w0_idx0")):
+        cs, _, asg = make(0)
+        k = asg.k
+        fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"params_vesta_k{k}.npz"))
+        params = PR.Params(ctx, k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])
+        pk = PR.ProvingKey(ctx, params, cs.to_ir(), asg.fixed, asg.permutation_mapping(), VK_REPR)
+        advice = np.stack([PR.mont(col) for col in asg.advice])
+        from oracle import halo2 as H
+        wide = H.splitmix64_wide(0xB200B200B200B200, pk.num_random)
+        proof = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
+        assert proof == bytes(gold[name]), name
+        assert PR.verify_proofs(pk, [asg.instance], [proof]) == [True]
+        pk.close(); params.close()

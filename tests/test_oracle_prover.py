@@ -60,3 +60,18 @@ def test_board_circuit_shape():
     assert len(cs.gates) == 57 and cs.degree() == 9 and len(cs.permutation) == 13 and cs.num_advice == 11
     assert cs.blinding_factors() in (7, 8)
     assert asg.check_satisfied() is None
+
+
+def test_oracle_reproduces_committed_golden_proofs(tiny):
+    """tests/golden/proofs.npz (made by tests/golden/make_proofs.py) freezes the oracle's proof bytes: any drift in the
+    restated protocol order, RNG draw order or transcript shows up here, on the CPU, before a GPU run is spent."""
+    import os
+    import numpy as np
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proofs.npz"))
+    assert tiny.oracle_proof(index=0) == bytes(gold["tiny_k5_idx0"])
+    assert tiny.oracle_proof(index=3) == bytes(gold["tiny_k5_idx3"])
+    from battlezips_halo2_b200.circuits import shot_circuit
+    cs, _, asg = shot_circuit(0)
+    job = Job(cs, asg)
+    proof = job.oracle_proof(index=0)
+    assert proof == bytes(gold["shot_w0_idx0"]) and job.verify(proof)
