@@ -183,13 +183,19 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
     BZ_CHECK(terms.size() == pk.n_exprs, "internal: expression count mismatch");
     const char* tier_env = getenv("BZ_QUOTIENT_TIERS");
     const bool tiers = !(tier_env && atoi(tier_env) == 0) && pk.ext_k > cs.k;
-    const uint32_t low_max_degree = tiers ? (pk.ext_n / 2) / pk.n + 1 : 0;          // (deg - 1) n <= ext_n / 2
-    auto build = [&](bool low, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
+    // tier of a term: the largest t <= 2 with (deg - 1) n <= ext_n >> t  (and at least n points)
+    auto tier_of = [&](uint32_t degree) {
+      uint32_t t = 0;
+      if (!tiers) return t;
+      while (t + 1 < PkImpl::Q_TIERS && (pk.ext_n >> (t + 1)) >= pk.n && (uint64_t)(degree - 1) * pk.n <= (pk.ext_n >> (t + 1))) ++t;
+      return t;
+    };
+    auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
       ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
       const uint32_t E = (uint32_t)terms.size();
       int prev = -1;
       for (uint32_t e = 0; e < E; ++e) {
-        if ((terms[e].degree <= low_max_degree) != low) continue;
+        if (tier_of(std::max(1u, terms[e].degree)) != tier) continue;
         terms[e].emit(pb);
         pb.fold(pk.C_YP0 + (prev < 0 ? 1u : e - (uint32_t)prev));          // acc = acc * y^(gap) + expr
         prev = (int)e;
@@ -207,9 +213,8 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       rot.alloc(pb.rot_table.size() * 4);
       BZ_CUDA(cudaMemcpy(rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
     };
-    build(false, pk.q_code, pk.q_rot, pk.q_ninstr);
-    build(true, pk.ql_code, pk.ql_rot, pk.ql_ninstr);
-    BZ_CHECK(pk.q_ninstr > 0, "internal: no full-degree term in h(X)");
+    for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) build(t, pk.q_code[t], pk.q_rot[t], pk.q_ninstr[t]);
+    BZ_CHECK(pk.q_ninstr[0] > 0, "internal: no full-degree term in h(X)");
   }
 }
 
@@ -253,7 +258,7 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.wide.alloc(B * (size_t)pk.R * 64);
   w.hext.alloc(B * en * E);
   w.hcoef.alloc(B * en * E);
-  w.hext_low.alloc(B * (en / 2) * E);
+  w.hext_low.alloc(B * (en / 2 + en / 4) * E);        // tiers 1 and 2, back to back
   w.hcoef_low.alloc(B * (en / 2) * E);
   w.nd.alloc(4 * B * n * E);
   w.consts.alloc(B * (size_t)pk.cstride * E);
@@ -1131,7 +1136,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   phase.reset(); phase.reset(new NvtxRange("steps 11-13: h(X), pieces"));
   {
     EvalArgs<FpP> a{};
-    a.code = (const uint32_t*)pk.q_code.p; a.n_instr = pk.q_ninstr; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot.p;
+    a.code = (const uint32_t*)pk.q_code[0].p; a.n_instr = pk.q_ninstr[0]; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot[0].p;
     a.pbase = (const DFe*)w.coset.p; a.pstride = (uint64_t)pk.NS * en; a.sbase = (const DFe*)pk.shcoset.p;
     a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
     a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
@@ -1139,23 +1144,31 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     std::call_once(once, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
     {
       ProfScope prof(C, PROF_QUOTIENT);
-      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr * 4, st>>>(a);
+      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr[0] * 4, st>>>(a);
       C->kernel_launches++;
-      if (pk.ql_ninstr) {      // low-degree terms: every second extended point
+      DFe* low_out = (DFe*)w.hext_low.p;
+      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {      // lower-degree terms: every 2^t-th extended point
+        if (!pk.q_ninstr[t]) continue;
         EvalArgs<FpP> al = a;
-        al.code = (const uint32_t*)pk.ql_code.p; al.n_instr = pk.ql_ninstr; al.rot = (const int32_t*)pk.ql_rot.p;
-        al.stride_log = 1; al.out = (DFe*)w.hext_low.p; al.ostride = en / 2;
-        eval_program_kernel<FpP><<<dim3((en / 2 + 127) / 128, B), 128, pk.ql_ninstr * 4, st>>>(al);
+        al.code = (const uint32_t*)pk.q_code[t].p; al.n_instr = pk.q_ninstr[t]; al.rot = (const int32_t*)pk.q_rot[t].p;
+        al.stride_log = t; al.out = low_out; al.ostride = en >> t;
+        eval_program_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, pk.q_ninstr[t] * 4, st>>>(al);
         C->kernel_launches++;
+        low_out += (size_t)B * (en >> t);
       }
     }
     NttFusion fu; fu.post_mode = 3;
     ntt_run(C, 0, w.hext.p, w.hcoef.p, pk.ext_k, true, B, fu);
-    if (pk.ql_ninstr) {
-      ntt_run(C, 0, w.hext_low.p, w.hcoef_low.p, pk.ext_k - 1, true, B, fu);
-      ProfScope prof(C, PROF_POLY);
-      add_low_kernel<FpP><<<dim3((en / 2 + 127) / 128, B), 128, 0, st>>>((DFe*)w.hcoef.p, en, (const DFe*)w.hcoef_low.p, en / 2);
-      C->kernel_launches++;
+    {
+      const DFe* low_in = (const DFe*)w.hext_low.p;
+      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {
+        if (!pk.q_ninstr[t]) continue;
+        ntt_run(C, 0, low_in, w.hcoef_low.p, pk.ext_k - t, true, B, fu);
+        ProfScope prof(C, PROF_POLY);
+        add_low_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, 0, st>>>((DFe*)w.hcoef.p, en, (const DFe*)w.hcoef_low.p, en >> t);
+        C->kernel_launches++;
+        low_in += (size_t)B * (en >> t);
+      }
     }
     std::vector<CommitReq> reqs;
     std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(pk.qdeg));

@@ -72,8 +72,9 @@ struct PkImpl {
   std::vector<uint64_t> vk_fixed_comm, vk_perm_comm;   // keygen_vk: commit_lagrange(column, Blind::default()) as affine (8 x u64 each)
   DevBuf tev;         // [2^(ext_k-k)]
   // programs
-  DevBuf lk_code, q_code, lk_rot, q_rot, ql_code, ql_rot;   // ql_*: h(X) terms of low degree, evaluated on every 2nd extended point
-  uint32_t lk_ninstr = 0, q_ninstr = 0, ql_ninstr = 0;
+  static constexpr uint32_t Q_TIERS = 3;     // h(X) tier t: terms whose quotient fits ext_n >> t points, evaluated on every 2^t-th extended point
+  DevBuf lk_code, lk_rot, q_code[Q_TIERS], q_rot[Q_TIERS];
+  uint32_t lk_ninstr = 0, q_ninstr[Q_TIERS] = {0, 0, 0};
   uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
   // const table layout
   uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, C_YP0, cstride;
