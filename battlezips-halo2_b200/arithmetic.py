@@ -49,6 +49,17 @@ def extended_to_coeff(ctx, field, a, extended_k):
     return a
 
 
+def batch_invert_assigned(ctx, field, numerators, denominators):
+    """poly::batch_invert_assigned on one column (or any flat slice): Assigned<F> = numerator / denominator -> F, with
+    ff::BatchInvert semantics (denominator 0 -> 0).  U: halo2_proofs 0.2.0 src/poly.rs."""
+    num = np.ascontiguousarray(numerators, dtype=np.uint64).reshape(-1, 4)
+    den = np.ascontiguousarray(denominators, dtype=np.uint64).reshape(-1, 4)
+    assert len(num) == len(den)
+    out = np.empty_like(num)
+    ctx._check(ctx.lib.bz_batch_invert_assigned(ctx.h, field, _np_ptr(num), _np_ptr(den), _np_ptr(out), len(num)))
+    return out
+
+
 _FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "from_u512": 4, "from_mont": 5, "to_mont": 6, "neg": 7, "sqr": 8}
 
 

@@ -87,9 +87,11 @@ def load_library():
         "bz_points_compress": (i32, [vp, i32, vp, u64, vp]),
         "bz_points_decompress": (i32, [vp, i32, vp, u64, vp, vp]),
         "bz_hash_to_curve": (i32, [vp, i32, ctypes.c_char_p, vp, u32, u64, vp]),
+        "bz_batch_invert_assigned": (i32, [vp, i32, vp, vp, vp, u64]),
+        "bz_batch_invert_assigned_dev": (i32, [vp, i32, vp, vp, vp, u64]),
     }
     declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",
-                          "bz_pk_num_random", "bz_pk_proof_size", "bz_create_proofs", "bz_pk_create_from_assembly", "bz_pk_vk_commitments", "bz_verify_proofs", "bz_params_commit_batch_dev"}     # bound in plonk/prover.py
+                          "bz_pk_num_random", "bz_pk_proof_size", "bz_pk_quotient_muls", "bz_create_proofs", "bz_pk_create_from_assembly", "bz_pk_vk_commitments", "bz_verify_proofs", "bz_params_commit_batch_dev"}     # bound in plonk/prover.py
     missing = [n for n in EXPORTS if n not in sigs and n not in declared_elsewhere]
     assert not missing, f"unbound C-ABI symbols: {missing}"
     for name, (res, args) in sigs.items():

@@ -9,6 +9,7 @@ void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t
 void jac_sum_run(Ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine);
 void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
 void curve_op_run(Ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n);
+void batch_invert_assigned_run(Ctx* ctx, int field, const void* num, const void* den, void* out, uint64_t n);
 
 Ctx::~Ctx() {}
 }  // namespace bz
@@ -265,6 +266,25 @@ __attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, i
     if (b && op <= 2) BZ_CUDA(cudaMemcpyAsync(db.p, b, n * 32, cudaMemcpyHostToDevice, st));
     bz::field_op_run(&ctx->c, field, op, da.p, db.p, dout.p, n);
     BZ_CUDA(cudaMemcpyAsync(out, dout.p, n * 32, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+__attribute__((visibility("default"))) int bz_batch_invert_assigned_dev(bz_ctx* ctx, int field, const void* d_num, const void* d_den, void* d_out, uint64_t n) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::batch_invert_assigned_run(&ctx->c, field, d_num, d_den, d_out, n);
+  });
+}
+__attribute__((visibility("default"))) int bz_batch_invert_assigned(bz_ctx* ctx, int field, const void* num, const void* den, void* out, uint64_t n) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(field == 0 || field == 1, "bad field id");
+    bz::DevBuf dn, dd;
+    dn.alloc(n * 32 + 32); dd.alloc(n * 32 + 32);
+    cudaStream_t st = ctx->c.stream;
+    BZ_CUDA(cudaMemcpyAsync(dn.p, num, n * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(dd.p, den, n * 32, cudaMemcpyHostToDevice, st));
+    bz::batch_invert_assigned_run(&ctx->c, field, dn.p, dd.p, dn.p, n);          // in place over the numerators
+    BZ_CUDA(cudaMemcpyAsync(out, dn.p, n * 32, cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
   });
 }

@@ -54,6 +54,40 @@ __global__ void batch_invert_kernel(const Fe<P>* __restrict__ in, Fe<P>* __restr
   }
 }
 
+// poly::batch_invert_assigned (U: halo2_proofs 0.2.0 src/poly.rs): the witness columns arrive as Assigned<F>
+// = numerator / denominator (Zero and Trivial carry denominator one); all denominators of a column are inverted with
+// ff::BatchInvert (zeros skipped, so n / 0 evaluates to 0 like Assigned::evaluate) and multiplied into the numerators.
+template <class P, int RUN>
+__global__ void batch_invert_assigned_kernel(const Fe<P>* num, const Fe<P>* __restrict__ den, Fe<P>* out /* may alias num */, uint64_t n) {
+  const uint64_t lo = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) * RUN;
+  if (lo >= n) return;
+  const uint32_t cnt = (uint32_t)min((uint64_t)RUN, n - lo);
+  Fe<P> pre[RUN], v[RUN];
+  Fe<P> acc = fe_one<P>();
+  bool all_one = true;
+  for (uint32_t j = 0; j < cnt; ++j) {
+    v[j] = fe_load(den + lo + j);
+    pre[j] = acc;
+    if (!fe_is_zero(v[j]) && !fe_eq(v[j], fe_one<P>())) { acc = fe_mul(acc, v[j]); all_one = false; }
+  }
+  Fe<P> inv = all_one ? acc : fe_inv(acc);            // a run of Trivial cells (the common case) needs no Fermat chain
+  for (int j = (int)cnt - 1; j >= 0; --j) {
+    Fe<P> r = fe_zero<P>();
+    if (fe_eq(v[j], fe_one<P>())) r = fe_load(num + lo + j);
+    else if (!fe_is_zero(v[j])) { r = fe_mul(fe_mul(inv, pre[j]), fe_load(num + lo + j)); inv = fe_mul(inv, v[j]); }
+    fe_store(out + lo + j, r);
+  }
+}
+void batch_invert_assigned_run(Ctx* ctx, int field, const void* num, const void* den, void* out, uint64_t n) {
+  if (!n) return;
+  const uint64_t threads = (n + 7) / 8;
+  const unsigned bl = (unsigned)((threads + 63) / 64);
+  if (field == 0) batch_invert_assigned_kernel<FpP, 8><<<bl, 64, 0, ctx->stream>>>((const Fe<FpP>*)num, (const Fe<FpP>*)den, (Fe<FpP>*)out, n);
+  else batch_invert_assigned_kernel<FqP, 8><<<bl, 64, 0, ctx->stream>>>((const Fe<FqP>*)num, (const Fe<FqP>*)den, (Fe<FqP>*)out, n);
+  ctx->kernel_launches++;
+  BZ_CUDA(cudaGetLastError());
+}
+
 // op 0: a + b (mixed), 1: 2a, 2: a - b, 3: full XYZZ add of (a+a) and b, 4: [k]a with k = low 32 bits of b.x raw
 template <class BP>
 __global__ void curve_op_kernel(int op, const Affine<BP>* __restrict__ a, const Affine<BP>* __restrict__ b, Affine<BP>* __restrict__ out, uint64_t n) {

@@ -1,0 +1,225 @@
+// Program format of the expression evaluator (poly.cuh `eval_program_kernel`) and the host-side compiler that turns
+// the gate polynomials of a constraint system into it.  Replaces what halo2_proofs 0.2.0 does with `poly::Evaluator`
+// over an `Ast` (U: src/poly/evaluator.rs, src/plonk/prover.rs "Evaluate the h(X) polynomial's constraint system
+// expressions"): there every gate polynomial is walked as a tree, one fresh Vec per node.  Here all gate polynomials that
+// are evaluated in one launch are hash-consed into ONE DAG, so that
+//   * a sub-expression that occurs several times (the curve equation of the ECC gates, (x_p - x_q), running-sum
+//     differences, ...) is computed once per point and kept in a per-thread temporary (OP_TEE / OP_PUSH_T), and
+//   * consecutive polynomials of one gate that share a factor (normally the selector:  s*e_1, s*e_2, ...) are folded as
+//     acc <- acc*y^G + s*(e_1*y^.. + ... + e_m):  m + 1 multiplications instead of 2m.
+// Both rewrites compute the same field element at every point (exact arithmetic), so h(X) and the proof bytes do not change.
+// This header has no CUDA dependency: tests/host/evalprog_host_test.cc compiles it with g++ and checks the emitted
+// programs against direct evaluation of the expression trees.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#define BZ_EP_CHECK(cond, msg) do { if (!(cond)) throw std::runtime_error(std::string(msg)); } while (0)
+
+namespace bz {
+
+enum : uint32_t { OP_PUSH_P = 0, OP_PUSH_S = 1, OP_PUSH_C = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL = 5, OP_NEG = 6,
+                  OP_MULC = 7, OP_ADDC = 8, OP_FOLD = 9, OP_STORE = 10, OP_END = 11, OP_MUL_T_STORE = 12, OP_ACC_MULC = 13,
+                  OP_TEE = 14,        // tmp[x] = top of stack (stays on the stack)
+                  OP_PUSH_T = 15 };   // push tmp[x]
+constexpr int EVAL_STACK = 12;
+constexpr int EVAL_TMP = 24;
+
+// postfix token of a gate / lookup expression as it crosses the ABI (bz_circuit IR):
+// 0 const(a) 1 advice(a = column, b = rotation) 2 fixed 3 instance 4 neg 5 add 6 mul 7 scale by const(a)
+struct Token { uint32_t op, a; int32_t b; };
+
+inline uint32_t enc(uint32_t op, uint32_t x = 0, uint32_t y = 0) { return op | (x << 4) | (y << 16); }
+inline uint32_t encc(uint32_t op, uint32_t idx) { return op | (idx << 4); }
+
+struct ProgBuilder {
+  std::vector<uint32_t> code;
+  std::vector<int32_t> rot_table;
+  std::map<int, uint32_t> rot_index;
+  int scale = 1;
+  int depth = 0, max_depth = 0;
+  uint32_t rot(int r) {
+    auto it = rot_index.find(r);
+    if (it != rot_index.end()) return it->second;
+    uint32_t idx = (uint32_t)rot_table.size();
+    rot_table.push_back(r * scale);
+    rot_index[r] = idx;
+    BZ_EP_CHECK(idx < 65536, "too many rotations");
+    return idx;
+  }
+  void push() { if (++depth > max_depth) max_depth = depth; }
+  void pop(int k = 1) { depth -= k; }
+  void pp(uint32_t slot, int r) { BZ_EP_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_P, slot, rot(r))); push(); }
+  void ps(uint32_t slot, int r) { BZ_EP_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_S, slot, rot(r))); push(); }
+  void pc(uint32_t c) { code.push_back(encc(OP_PUSH_C, c)); push(); }
+  void add() { code.push_back(OP_ADD); pop(); }
+  void sub() { code.push_back(OP_SUB); pop(); }
+  void mul() { code.push_back(OP_MUL); pop(); }
+  void neg() { code.push_back(OP_NEG); }
+  void mulc(uint32_t c) { code.push_back(encc(OP_MULC, c)); }
+  void addc(uint32_t c) { code.push_back(encc(OP_ADDC, c)); }
+  void fold(uint32_t c) { code.push_back(encc(OP_FOLD, c)); pop(); }
+  void accmul(uint32_t c) { code.push_back(encc(OP_ACC_MULC, c)); }
+  void store(uint32_t k) { code.push_back(encc(OP_STORE, k)); pop(); }
+  void tee(uint32_t t) { code.push_back(encc(OP_TEE, t)); }
+  void pt(uint32_t t) { code.push_back(encc(OP_PUSH_T, t)); push(); }
+};
+
+// The gate polynomials of one launch as a hash-consed DAG.  Usage: add() every polynomial in protocol order (with its
+// index e among all expressions of h(X)), plan(), then emit_group() for the groups in order.
+struct GateDag {
+  struct Node {
+    uint32_t op, a; int32_t b; int x, y;      // token op; children (-1: none)
+    uint32_t uses = 0;                        // references the emitted program makes to this node
+    uint32_t left = 0;                        // references not emitted yet
+    int tmp = -1;                             // temporary holding the value, -1: none
+    bool has_mul = false;                     // contains a multiplication: worth keeping
+    int need = 1;                             // stack slots an emission needs (Sethi-Ullman estimate)
+  };
+  struct Poly { int root; uint32_t e; };
+  struct Group { uint32_t first, count; int factor; std::vector<int> rest; };   // polys [first, first+count); factor -1: plain emission
+  std::vector<Node> nodes;
+  std::map<std::tuple<uint32_t, uint32_t, int32_t, int, int>, int> index;
+  std::vector<Poly> polys;
+  std::vector<Group> groups;
+  bool cse = true, hoist = true;
+  uint32_t advice_slot_of_instance = 0;       // instance column c lives in per-proof slot G + c
+  std::vector<int> free_tmp;
+
+  int intern(uint32_t op, uint32_t a, int32_t b, int x, int y) {
+    if ((op == 5 || op == 6) && x > y) std::swap(x, y);                // commutative
+    auto key = std::make_tuple(op, a, b, x, y);
+    if (cse) { auto it = index.find(key); if (it != index.end()) return it->second; }
+    Node n; n.op = op; n.a = a; n.b = b; n.x = x; n.y = y;
+    n.has_mul = op == 6 || op == 7 || (x >= 0 && nodes[x].has_mul) || (y >= 0 && nodes[y].has_mul);
+    const int nx = x >= 0 ? nodes[x].need : 0, ny = y >= 0 ? nodes[y].need : 0;
+    n.need = op <= 3 ? 1 : y < 0 ? nx : (nx == ny ? nx + 1 : std::max(nx, ny));
+    nodes.push_back(n);
+    const int id = (int)nodes.size() - 1;
+    if (cse) index[key] = id;
+    return id;
+  }
+  int from_tokens(const std::vector<Token>& tokens, uint32_t lo, uint32_t hi) {
+    std::vector<int> st;
+    for (uint32_t t = lo; t < hi; ++t) {
+      const Token& k = tokens[t];
+      switch (k.op) {
+        case 0: st.push_back(intern(0, k.a, 0, -1, -1)); break;
+        case 1: case 2: case 3: st.push_back(intern(k.op, k.a, k.b, -1, -1)); break;
+        case 4: BZ_EP_CHECK(!st.empty(), "bad expression"); st.back() = intern(4, 0, 0, st.back(), -1); break;
+        case 5: case 6: { BZ_EP_CHECK(st.size() >= 2, "bad expression"); int r = st.back(); st.pop_back(); st.back() = intern(k.op, 0, 0, st.back(), r); break; }
+        case 7: BZ_EP_CHECK(!st.empty(), "bad expression"); st.back() = intern(7, k.a, 0, st.back(), -1); break;
+        default: BZ_EP_CHECK(false, "bad token op");
+      }
+    }
+    BZ_EP_CHECK(st.size() == 1, "bad expression");
+    return st.back();
+  }
+  void add(const std::vector<Token>& tokens, uint32_t lo, uint32_t hi, uint32_t e) { polys.push_back(Poly{from_tokens(tokens, lo, hi), e}); }
+
+  // children as the emission references them: a + (-b) is emitted as a b SUB, so it references b, not the negation
+  void refs(int v, int& c0, int& c1, bool& is_sub) const {
+    const Node& n = nodes[v];
+    c0 = n.x; c1 = n.y; is_sub = false;
+    if (n.op == 5) {
+      if (nodes[n.y].op == 4) { c1 = nodes[n.y].x; is_sub = true; }
+      else if (nodes[n.x].op == 4) { c0 = n.y; c1 = nodes[n.x].x; is_sub = true; }
+    }
+  }
+  void count(int v, std::vector<char>& seen) {
+    nodes[v].uses++;
+    if (seen[v]) return;
+    seen[v] = 1;
+    int c0, c1; bool s; refs(v, c0, c1, s);
+    if (c0 >= 0) count(c0, seen);
+    if (c1 >= 0) count(c1, seen);
+  }
+  void plan() {
+    groups.clear();
+    for (uint32_t i = 0; i < polys.size();) {
+      Group g{i, 1, -1, {}};
+      const Node& r = nodes[polys[i].root];
+      if (hoist && r.op == 6) {
+        std::vector<int> cand = {r.x, r.y};
+        uint32_t j = i + 1;
+        for (; j < polys.size(); ++j) {     // (a common factor is all it takes: the polynomials need not belong to one gate)
+          const Node& q = nodes[polys[j].root];
+          if (q.op != 6) break;
+          std::vector<int> keep;
+          for (int c : cand) if (c == q.x || c == q.y) keep.push_back(c);
+          if (keep.empty()) break;
+          cand = keep;
+        }
+        if (j - i >= 2) {
+          g.count = j - i; g.factor = cand[0];
+          for (uint32_t p = i; p < j; ++p) { const Node& q = nodes[polys[p].root]; g.rest.push_back(q.x == g.factor ? q.y : q.x); }
+        }
+      }
+      groups.push_back(g);
+      i += g.count;
+    }
+    std::vector<char> seen(nodes.size(), 0);
+    for (auto& n : nodes) { n.uses = 0; n.tmp = -1; }
+    for (const Group& g : groups) {
+      if (g.factor < 0) count(polys[g.first].root, seen);
+      else { for (int r : g.rest) count(r, seen); count(g.factor, seen); }
+    }
+    for (auto& n : nodes) n.left = n.uses;
+    free_tmp.clear();
+    for (int t = EVAL_TMP - 1; t >= 0; --t) free_tmp.push_back(t);
+  }
+
+  void emit(ProgBuilder& pb, int v) {
+    Node& n = nodes[v];
+    if (n.left) --n.left;
+    if (n.tmp >= 0) {
+      pb.pt((uint32_t)n.tmp);
+      if (!n.left) { free_tmp.push_back(n.tmp); n.tmp = -1; }
+      return;
+    }
+    switch (n.op) {
+      case 0: pb.pc(n.a); break;
+      case 1: pb.pp(n.a, n.b); break;
+      case 2: pb.ps(n.a, n.b); break;
+      case 3: pb.pp(advice_slot_of_instance + n.a, n.b); break;
+      case 4: emit(pb, n.x); pb.neg(); break;
+      case 7: emit(pb, n.x); pb.mulc(n.a); break;
+      case 5: case 6: {
+        int c0, c1; bool is_sub; refs(v, c0, c1, is_sub);
+        if (is_sub) { emit(pb, c0); emit(pb, c1); pb.sub(); }
+        else {
+          if (nodes[c1].need > nodes[c0].need) std::swap(c0, c1);        // deeper operand first: shallower stack
+          emit(pb, c0); emit(pb, c1);
+          if (n.op == 5) pb.add(); else pb.mul();
+        }
+        break;
+      }
+      default: BZ_EP_CHECK(false, "bad node");
+    }
+    Node& m = nodes[v];                                                    // (no reallocation happens during emission)
+    if (m.left && m.has_mul && !free_tmp.empty()) { m.tmp = free_tmp.back(); free_tmp.pop_back(); pb.tee((uint32_t)m.tmp); }
+  }
+  // value of group g on the stack is folded into the accumulator:  acc <- acc * y^(gap_total) + (terms of the group).
+  // `yp(d)` = constant index of y^d; `prev_e` = index of the last expression folded before this group (-1: none).
+  template <class YP> void emit_group(ProgBuilder& pb, const Group& g, int prev_e, YP yp) {
+    const uint32_t e0 = polys[g.first].e, e_last = polys[g.first + g.count - 1].e;
+    const uint32_t gap0 = prev_e < 0 ? 1u : e0 - (uint32_t)prev_e;
+    if (g.factor < 0) { emit(pb, polys[g.first].root); pb.fold(yp(gap0)); return; }
+    emit(pb, g.rest[0]);
+    for (uint32_t i = 1; i < g.count; ++i) {
+      pb.mulc(yp(polys[g.first + i].e - polys[g.first + i - 1].e));
+      emit(pb, g.rest[i]);
+      pb.add();
+    }
+    emit(pb, g.factor);
+    pb.mul();
+    pb.fold(yp(gap0 + (e_last - e0)));
+  }
+};
+
+}  // namespace bz

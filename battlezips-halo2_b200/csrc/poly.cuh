@@ -9,6 +9,7 @@
 // per-proof challenges live in a device scalar table `sc[b][*]`.
 #pragma once
 #include "field.cuh"
+#include "evalprog.h"
 
 namespace bz {
 
@@ -24,9 +25,7 @@ template <class P> __device__ __forceinline__ Fe<P>* region_ptr(const Regions& r
 }
 
 // ---- interpreter ---------------------------------------------------------------------------------
-enum : uint32_t { OP_PUSH_P = 0, OP_PUSH_S = 1, OP_PUSH_C = 2, OP_ADD = 3, OP_SUB = 4, OP_MUL = 5, OP_NEG = 6,
-                  OP_MULC = 7, OP_ADDC = 8, OP_FOLD = 9, OP_STORE = 10, OP_END = 11, OP_MUL_T_STORE = 12, OP_ACC_MULC = 13 };
-constexpr int EVAL_STACK = 10;
+// opcodes, EVAL_STACK / EVAL_TMP and the host-side program builder: evalprog.h
 
 template <class P> struct EvalArgs {
   const uint32_t* code;
@@ -58,6 +57,7 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
   const Fe<P>* pb = a.pbase + (uint64_t)b * a.pstride;
   const Fe<P>* cb = a.consts + (uint64_t)b * a.cstride;
   Fe<P> st[EVAL_STACK];
+  Fe<P> tmp[EVAL_TMP];           // shared sub-expressions of the gate DAG (evalprog.h)
   Fe<P> acc = fe_zero<P>();
   int sp = 0;
   for (uint32_t pc = 0; pc < a.n_instr; ++pc) {
@@ -77,6 +77,8 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
       case OP_STORE: --sp; fe_store(a.out + (uint64_t)b * a.ostride + ((uint64_t)(ins >> 4) << a.logN) + i, st[sp]); break;
       case OP_ACC_MULC: acc = fe_mul(acc, fe_load(cb + (ins >> 4))); break;
       case OP_MUL_T_STORE: fe_store(a.out + (uint64_t)b * a.ostride + i, fe_mul(acc, fe_load(a.tev + (jp & (a.tn - 1))))); break;
+      case OP_TEE: tmp[ins >> 4] = st[sp - 1]; break;
+      case OP_PUSH_T: st[sp++] = tmp[ins >> 4]; break;
       default: break;
     }
   }

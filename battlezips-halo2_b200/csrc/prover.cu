@@ -28,40 +28,6 @@ template <class P> __global__ void sigma_from_mapping_kernel(const uint32_t* __r
   fe_store(out + i, fe_mul(fe_load(delta_pows + c), fe_load(omega_pows + r)));
 }
 
-static uint32_t enc(uint32_t op, uint32_t x = 0, uint32_t y = 0) { return op | (x << 4) | (y << 16); }
-static uint32_t encc(uint32_t op, uint32_t idx) { return op | (idx << 4); }
-
-struct ProgBuilder {
-  std::vector<uint32_t> code;
-  std::vector<int32_t> rot_table;
-  std::map<int, uint32_t> rot_index;
-  int scale = 1;
-  int depth = 0, max_depth = 0;
-  uint32_t rot(int r) {
-    auto it = rot_index.find(r);
-    if (it != rot_index.end()) return it->second;
-    uint32_t idx = (uint32_t)rot_table.size();
-    rot_table.push_back(r * scale);
-    rot_index[r] = idx;
-    BZ_CHECK(idx < 65536, "too many rotations");
-    return idx;
-  }
-  void push() { if (++depth > max_depth) max_depth = depth; }
-  void pop(int k = 1) { depth -= k; }
-  void pp(uint32_t slot, int r) { BZ_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_P, slot, rot(r))); push(); }
-  void ps(uint32_t slot, int r) { BZ_CHECK(slot < 4096, "slot overflow"); code.push_back(enc(OP_PUSH_S, slot, rot(r))); push(); }
-  void pc(uint32_t c) { code.push_back(encc(OP_PUSH_C, c)); push(); }
-  void add() { code.push_back(OP_ADD); pop(); }
-  void sub() { code.push_back(OP_SUB); pop(); }
-  void mul() { code.push_back(OP_MUL); pop(); }
-  void neg() { code.push_back(OP_NEG); }
-  void mulc(uint32_t c) { code.push_back(encc(OP_MULC, c)); }
-  void addc(uint32_t c) { code.push_back(encc(OP_ADDC, c)); }
-  void fold(uint32_t c) { code.push_back(encc(OP_FOLD, c)); pop(); }
-  void accmul(uint32_t c) { code.push_back(encc(OP_ACC_MULC, c)); }
-  void store(uint32_t k) { code.push_back(encc(OP_STORE, k)); pop(); }
-};
-
 // emit one expression (postfix tokens [lo,hi)); advice -> per-proof slot col, instance -> slot G + col, fixed -> shared slot col
 static void emit_expr(ProgBuilder& pb, const CircuitCopy& cs, uint32_t lo, uint32_t hi) {
   for (uint32_t t = lo; t < hi; ++t) {
@@ -126,7 +92,7 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
   // and added to the rest in coefficient form: same h(X), about a third fewer field multiplications for Shot / Board.
   // (For a witness that violates a gate neither variant is a polynomial identity; both proofs are rejected, their bytes differ.)
   {
-    struct Term { uint32_t degree; std::function<void(ProgBuilder&)> emit; };
+    struct Term { uint32_t degree; std::function<void(ProgBuilder&)> emit; bool gate = false; uint32_t lo = 0, hi = 0; };
     std::vector<Term> terms;
     auto expr_degree = [&](uint32_t lo, uint32_t hi) {
       std::vector<uint32_t> st;
@@ -147,7 +113,7 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
     const int last_rot = -((int)cs.bf + 1);
     for (size_t g = 0; g + 1 < cs.gate_off.size(); ++g) {
       const uint32_t lo = cs.gate_off[g], hi = cs.gate_off[g + 1];
-      terms.push_back({expr_degree(lo, hi), [&cs, lo, hi](ProgBuilder& pb) { emit_expr(pb, cs, lo, hi); }});
+      terms.push_back({expr_degree(lo, hi), [&cs, lo, hi](ProgBuilder& pb) { emit_expr(pb, cs, lo, hi); }, true, lo, hi});
     }
     if (pk.nsets) {
       terms.push_back({2, [&pk](ProgBuilder& pb) { pb.pc(pk.C_ONE); pb.pp(pk.slot_pz(0), 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});          // l0 * (1 - z_0)
@@ -190,14 +156,29 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       while (t + 1 < PkImpl::Q_TIERS && (pk.ext_n >> (t + 1)) >= pk.n && (uint64_t)(degree - 1) * pk.n <= (pk.ext_n >> (t + 1))) ++t;
       return t;
     };
+    // BZ_QUOTIENT_CSE=0: every gate polynomial as its own expression tree (the reference's evaluation order), for A/B runs
+    const char* cse_env = getenv("BZ_QUOTIENT_CSE");
+    const bool use_dag = !(cse_env && atoi(cse_env) == 0);
     auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
       ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
       const uint32_t E = (uint32_t)terms.size();
+      auto yp = [&pk](uint32_t d) { return pk.C_YP0 + d; };
       int prev = -1;
+      // the gate polynomials of this tier: one DAG (shared sub-expressions once, common factors hoisted; evalprog.h)
+      GateDag dag; dag.advice_slot_of_instance = cs.G;
+      if (use_dag) {
+        for (uint32_t e = 0; e < E; ++e)
+          if (terms[e].gate && tier_of(std::max(1u, terms[e].degree)) == tier) dag.add(cs.tokens, terms[e].lo, terms[e].hi, e);
+        dag.plan();
+        for (const GateDag::Group& g : dag.groups) {
+          dag.emit_group(pb, g, prev, yp);
+          prev = (int)dag.polys[g.first + g.count - 1].e;
+        }
+      }
       for (uint32_t e = 0; e < E; ++e) {
-        if (tier_of(std::max(1u, terms[e].degree)) != tier) continue;
+        if ((use_dag && terms[e].gate) || tier_of(std::max(1u, terms[e].degree)) != tier) continue;
         terms[e].emit(pb);
-        pb.fold(pk.C_YP0 + (prev < 0 ? 1u : e - (uint32_t)prev));          // acc = acc * y^(gap) + expr
+        pb.fold(yp(prev < 0 ? 1u : e - (uint32_t)prev));          // acc = acc * y^(gap) + expr
         prev = (int)e;
       }
       ninstr = 0;
@@ -206,6 +187,8 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       pb.code.push_back(OP_MUL_T_STORE);
       BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
       ninstr = (uint32_t)pb.code.size();
+      pk.q_muls[tier] = 0;
+      for (uint32_t ins : pb.code) { const uint32_t op = ins & 15u; pk.q_muls[tier] += op == OP_MUL || op == OP_MULC || op == OP_FOLD || op == OP_ACC_MULC || op == OP_MUL_T_STORE; }
       BZ_CHECK(ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
       code.alloc(pb.code.size() * 4);
       BZ_CUDA(cudaMemcpy(code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
@@ -401,6 +384,11 @@ API int bz_params_commit_batch_dev(bz_ctx* ctx, bz_params* params, int lagrange_
 API void bz_pk_destroy(bz_pk* pk) { delete pk; }
 API uint32_t bz_pk_num_random(const bz_pk* pk) { return pk ? pk->p.R : 0; }
 API uint32_t bz_pk_proof_size(const bz_pk* pk) { return pk ? pk->p.proof_size : 0; }
+API uint32_t bz_pk_quotient_muls(const bz_pk* pk, uint32_t tier, uint32_t* points) {
+  if (!pk || tier >= PkImpl::Q_TIERS) return 0;
+  if (points) *points = pk->p.q_ninstr[tier] ? pk->p.ext_n >> tier : 0;
+  return pk->p.q_muls[tier];
+}
 
 static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values,
                           const uint32_t* mapping, bz_pk** out) {

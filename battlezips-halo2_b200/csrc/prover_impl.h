@@ -37,7 +37,6 @@ struct ParamsImpl {
   bool use_tables = true;   // small n: fixed-base window tables; large n (k >= 15): bucket MSM over the raw bases
 };
 
-struct Token { uint32_t op, a; int32_t b; };
 
 struct CircuitCopy {
   uint32_t k, G, F, I, degree, bf;
@@ -74,7 +73,7 @@ struct PkImpl {
   // programs
   static constexpr uint32_t Q_TIERS = 3;     // h(X) tier t: terms whose quotient fits ext_n >> t points, evaluated on every 2^t-th extended point
   DevBuf lk_code, lk_rot, q_code[Q_TIERS], q_rot[Q_TIERS];
-  uint32_t lk_ninstr = 0, q_ninstr[Q_TIERS] = {0, 0, 0};
+  uint32_t lk_ninstr = 0, q_ninstr[Q_TIERS] = {0, 0, 0}, q_muls[Q_TIERS] = {0, 0, 0};
   uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
   // const table layout
   uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, C_YP0, cstride;

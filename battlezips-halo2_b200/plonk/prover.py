@@ -68,6 +68,8 @@ def _bind(lib):
     lib.bz_pk_num_random.argtypes = [vp]
     lib.bz_pk_proof_size.restype = u32
     lib.bz_pk_proof_size.argtypes = [vp]
+    lib.bz_pk_quotient_muls.restype = u32
+    lib.bz_pk_quotient_muls.argtypes = [vp, u32, vp]
     lib.bz_create_proofs.restype = i32
     lib.bz_create_proofs.argtypes = [vp, vp, u32, vp, vp, u32, vp, vp, vp]
     lib._prover_bound = True
@@ -213,6 +215,11 @@ class ProvingKey:
         self.h = h
         self.num_random = ctx.lib.bz_pk_num_random(h)
         self.proof_size = ctx.lib.bz_pk_proof_size(h)
+        # (multiplications per point, points) of every h(X) evaluation tier: the quotient kernel's algorithmic work
+        self.quotient_muls = []
+        for t in range(3):
+            pts = ctypes.c_uint32(0)
+            self.quotient_muls.append((ctx.lib.bz_pk_quotient_muls(h, t, ctypes.byref(pts)), pts.value))
 
     def vk_commitments(self):
         """keygen_vk: (fixed_commitments (F, 8), permutation commitments (M, 8)) as Montgomery affine points."""

@@ -79,6 +79,13 @@ int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes);
 /* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 over the slice (ff::BatchInvert: Montgomery trick, 0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
  *     6 canonical -> Montgomery, 7 -a, 8 a^2 */
 int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
+/* poly::batch_invert_assigned (U: halo2_proofs 0.2.0 src/poly.rs `batch_invert_assigned`, called by create_proof on the
+ * advice columns a circuit assigned as Assigned<F>; reference call path R:src/circuits/shot.rs:921 -> create_proof):
+ * out[i] = num[i] / den[i] with ff::BatchInvert semantics (den = 0 -> 0).  Assigned::Zero is (0, 1), Trivial(x) is (x, 1).
+ * Host slices; the _dev form takes device pointers (may alias out = num) and is asynchronous on the context's stream,
+ * so the shim can write a whole advice region (num_advice x n) in one call straight where bz_create_proofs reads it. */
+int bz_batch_invert_assigned(bz_ctx* ctx, int field, const void* numerators, const void* denominators, void* out, uint64_t n);
+int bz_batch_invert_assigned_dev(bz_ctx* ctx, int field, const void* d_numerators, const void* d_denominators, void* d_out, uint64_t n);
 /* affine in, affine out (64 B each): op 0 a+b, 1 2a, 2 a-b, 3 2a+b (full projective add), 4 [k]a, k = first u32 of b */
 int bz_curve_op(bz_ctx* ctx, int curve, int op, const void* a, const void* b, void* out, uint64_t n);
 
@@ -194,6 +201,10 @@ int bz_pk_vk_commitments(bz_ctx* ctx, bz_pk* pk, void* fixed_commitments, void* 
 void bz_pk_destroy(bz_pk* pk);
 uint32_t bz_pk_num_random(const bz_pk* pk); /* Scalar::random draws one create_proof makes (protocol order) */
 uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yields */
+/* Static count of field multiplications one point of the compiled h(X) program costs in evaluation tier `tier`
+ * (0: every point of the extended coset, 1: every second, 2: every fourth; the figure SURVEY 8d's quotient roofline is
+ * computed from); 0 for an empty tier.  *points, if not NULL, receives the number of coset points of that tier. */
+uint32_t bz_pk_quotient_muls(const bz_pk* pk, uint32_t tier, uint32_t* points);
 
 /* create_proof for `batch` independent proofs of the same circuit, in lockstep on the device.
  *   instances : batch x num_instance x instance_stride scalars; instance_lens[num_instance] values are used

@@ -173,6 +173,13 @@ class Params:
         return self._commit(self._glw, poly, blind)
 
 
+def batch_invert_assigned(V, numerators, denominators):
+    """poly::batch_invert_assigned (U: halo2_proofs 0.2.0 src/poly.rs): the denominators of one column's Assigned<F> cells
+    go through ff::BatchInvert (zeros are skipped and stay zero), then every numerator is multiplied by its inverse --
+    `Polynomial<Assigned<F>>::invert`.  Zero / Trivial cells are (0, 1) / (x, 1).  (n,4) Montgomery arrays in and out."""
+    return V.mul(numerators, V.batch_invert(denominators))
+
+
 def _affine_pts(curve_id, jacs):
     """list of Jacobian (12,) -> list of affine int tuples (batch_normalize)."""
     if not len(jacs):

@@ -1,0 +1,140 @@
+// Host check of the gate-DAG compiler (csrc/evalprog.h): random families of gate polynomials with shared
+// sub-expressions and shared factors are compiled with every combination of {cse, hoist}; the emitted program is run
+// by a scalar model of eval_program_kernel over F_p (p = 2^61 - 1) and must equal  sum_e y^(E-1-e) * expr_e  evaluated
+// straight from the token streams.  Also reports the multiplication counts (the quantity the rewrite is for).
+#include "../../battlezips-halo2_b200/csrc/evalprog.h"
+#include <cstdio>
+#include <cstdlib>
+#include <random>
+using namespace bz;
+typedef unsigned long long u64;
+static const u64 P = (1ull << 61) - 1;
+static u64 mulm(u64 a, u64 b) { return (u64)((unsigned __int128)a * b % P); }
+static u64 addm(u64 a, u64 b) { return (a + b) % P; }
+static u64 subm(u64 a, u64 b) { return (a + P - b) % P; }
+
+static std::mt19937_64 rng(12345);
+static const int NADV = 6, NFIX = 4, NINST = 2, NCONST = 8, G = NADV;
+static u64 val_adv[NADV + NINST][3], val_fix[NFIX][3], val_const[64];
+static std::vector<std::vector<Token>> pool;
+
+static std::vector<Token> gen(int depth) {
+  if (!pool.empty() && depth < 4 && rng() % 10 < 3) return pool[rng() % pool.size()];
+  std::vector<Token> r;
+  if (depth == 0 || rng() % 6 == 0) {
+    switch (rng() % 4) {
+      case 0: r.push_back(Token{0, (uint32_t)(rng() % NCONST), 0}); break;
+      case 1: r.push_back(Token{1, (uint32_t)(rng() % NADV), (int32_t)(rng() % 3) - 1}); break;
+      case 2: r.push_back(Token{2, (uint32_t)(rng() % NFIX), (int32_t)(rng() % 3) - 1}); break;
+      default: r.push_back(Token{3, (uint32_t)(rng() % NINST), (int32_t)(rng() % 3) - 1}); break;
+    }
+    return r;
+  }
+  const int kind = rng() % 8;
+  std::vector<Token> a = gen(depth - 1);
+  if (kind == 0) { r = a; r.push_back(Token{4, 0, 0}); }
+  else if (kind == 1) { r = a; r.push_back(Token{7, (uint32_t)(rng() % NCONST), 0}); }
+  else {
+    std::vector<Token> b = (rng() % 8 == 0) ? a : gen(depth - 1);
+    r = a; r.insert(r.end(), b.begin(), b.end());
+    if (kind >= 5 && rng() % 2) { r.push_back(Token{4, 0, 0}); r.push_back(Token{5, 0, 0}); }     // a - b
+    else r.push_back(Token{kind <= 4 ? 6u : 5u, 0, 0});
+  }
+  if (r.size() > 2 && r.size() < 40 && rng() % 3 == 0) pool.push_back(r);
+  return r;
+}
+
+static u64 eval_tokens(const std::vector<Token>& t, uint32_t lo, uint32_t hi, u64& nmul) {
+  std::vector<u64> st;
+  for (uint32_t i = lo; i < hi; ++i) {
+    const Token& k = t[i];
+    switch (k.op) {
+      case 0: st.push_back(val_const[k.a]); break;
+      case 1: st.push_back(val_adv[k.a][k.b + 1]); break;
+      case 2: st.push_back(val_fix[k.a][k.b + 1]); break;
+      case 3: st.push_back(val_adv[G + k.a][k.b + 1]); break;
+      case 4: st.back() = subm(0, st.back()); break;
+      case 5: { u64 r = st.back(); st.pop_back(); st.back() = addm(st.back(), r); break; }
+      case 6: { u64 r = st.back(); st.pop_back(); st.back() = mulm(st.back(), r); ++nmul; break; }
+      case 7: st.back() = mulm(st.back(), val_const[k.a]); ++nmul; break;
+    }
+  }
+  return st.back();
+}
+
+static u64 run_program(const ProgBuilder& pb, u64& nmul) {
+  u64 st[EVAL_STACK], tmp[EVAL_TMP], acc = 0; int sp = 0;
+  for (uint32_t ins : pb.code) {
+    const uint32_t op = ins & 15u, x = (ins >> 4) & 0xfffu, y = ins >> 16;
+    switch (op) {
+      case OP_PUSH_P: st[sp++] = val_adv[x][pb.rot_table[y] + 1]; break;
+      case OP_PUSH_S: st[sp++] = val_fix[x][pb.rot_table[y] + 1]; break;
+      case OP_PUSH_C: st[sp++] = val_const[ins >> 4]; break;
+      case OP_ADD: --sp; st[sp - 1] = addm(st[sp - 1], st[sp]); break;
+      case OP_SUB: --sp; st[sp - 1] = subm(st[sp - 1], st[sp]); break;
+      case OP_MUL: --sp; st[sp - 1] = mulm(st[sp - 1], st[sp]); ++nmul; break;
+      case OP_NEG: st[sp - 1] = subm(0, st[sp - 1]); break;
+      case OP_MULC: st[sp - 1] = mulm(st[sp - 1], val_const[ins >> 4]); ++nmul; break;
+      case OP_ADDC: st[sp - 1] = addm(st[sp - 1], val_const[ins >> 4]); break;
+      case OP_FOLD: --sp; acc = addm(mulm(acc, val_const[ins >> 4]), st[sp]); ++nmul; break;
+      case OP_ACC_MULC: acc = mulm(acc, val_const[ins >> 4]); ++nmul; break;
+      case OP_TEE: if ((ins >> 4) >= (uint32_t)EVAL_TMP) { printf("tmp overflow\n"); exit(1); } tmp[ins >> 4] = st[sp - 1]; break;
+      case OP_PUSH_T: st[sp++] = tmp[ins >> 4]; break;
+      default: printf("bad op\n"); exit(1);
+    }
+    if (sp < 0 || sp > EVAL_STACK) { printf("stack out of range %d\n", sp); exit(1); }
+  }
+  if (sp != 0) { printf("stack not empty\n"); exit(1); }
+  return acc;
+}
+
+int main() {
+  u64 tot_naive = 0, tot[4] = {0, 0, 0, 0};
+  int deepest = 0;
+  for (int trial = 0; trial < 400; ++trial) {
+    pool.clear();
+    for (auto& r : val_adv) for (u64& v : r) v = rng() % P;
+    for (auto& r : val_fix) for (u64& v : r) v = rng() % P;
+    for (int i = 0; i < NCONST; ++i) val_const[i] = rng() % P;
+    const uint32_t E = 4 + rng() % 30, YP0 = 16;               // constants 16.. : y^0 .. y^E
+    const u64 y = rng() % P;
+    { u64 p = 1; for (uint32_t d = 0; d <= E; ++d) { val_const[YP0 + d] = p; p = mulm(p, y); } }
+    // polynomials: "gates" of 1..4 polynomials sharing a selector-like factor, at a random subset of the indices 0..E-1
+    std::vector<Token> tokens; std::vector<uint32_t> lo, hi, eidx;
+    for (uint32_t e = 0; e < E;) {
+      const uint32_t m = 1 + rng() % 4;
+      std::vector<Token> sel = rng() % 4 ? std::vector<Token>{Token{2, (uint32_t)(rng() % NFIX), 0}} : gen(2);
+      for (uint32_t i = 0; i < m && e < E; ++i, ++e) {
+        if (rng() % 4 == 0) continue;                          // this index belongs to another launch
+        std::vector<Token> body = gen(1 + rng() % 4), poly;
+        const int shape = rng() % 4;
+        if (shape == 0) poly = body;                           // no common factor
+        else if (shape == 1) { poly = body; poly.insert(poly.end(), sel.begin(), sel.end()); poly.push_back(Token{6, 0, 0}); }
+        else { poly = sel; poly.insert(poly.end(), body.begin(), body.end()); poly.push_back(Token{6, 0, 0}); }
+        lo.push_back((uint32_t)tokens.size()); tokens.insert(tokens.end(), poly.begin(), poly.end()); hi.push_back((uint32_t)tokens.size()); eidx.push_back(e);
+      }
+    }
+    if (eidx.empty()) continue;
+    u64 want = 0, naive = 0;
+    for (size_t i = 0; i < eidx.size(); ++i) { want = addm(want, mulm(eval_tokens(tokens, lo[i], hi[i], naive), val_const[YP0 + (E - 1 - eidx[i])])); }
+    naive += eidx.size();                                      // one fold multiplication per polynomial
+    tot_naive += naive;
+    for (int mode = 0; mode < 4; ++mode) {
+      GateDag dag; dag.cse = mode & 1; dag.hoist = mode & 2; dag.advice_slot_of_instance = G;
+      for (size_t i = 0; i < eidx.size(); ++i) dag.add(tokens, lo[i], hi[i], eidx[i]);
+      dag.plan();
+      ProgBuilder pb;
+      int prev = -1;
+      for (const GateDag::Group& g : dag.groups) { dag.emit_group(pb, g, prev, [&](uint32_t d) { if (d > E) { printf("y power out of range\n"); exit(1); } return YP0 + d; }); prev = (int)dag.polys[g.first + g.count - 1].e; }
+      if ((uint32_t)prev != E - 1) pb.accmul(YP0 + (E - 1 - (uint32_t)prev));
+      if (pb.max_depth > deepest) deepest = pb.max_depth;
+      if (pb.max_depth > EVAL_STACK) { printf("trial %d mode %d: depth %d\n", trial, mode, pb.max_depth); continue; }   // the library rejects these with an error
+      u64 nm = 0;
+      const u64 got = run_program(pb, nm);
+      if (got != want) { printf("MISMATCH trial %d mode %d\n", trial, mode); return 1; }
+      tot[mode] += nm;
+    }
+  }
+  printf("ok naive %llu plain %llu cse %llu hoist %llu both %llu deepest %d\n", tot_naive, tot[0], tot[1], tot[2], tot[3], deepest);
+  return 0;
+}

@@ -43,6 +43,28 @@ def test_field_ops(field, ctx, oracle_c):
     assert np.array_equal(ar.field_op(ctx, field, "from_u512", wide), co.from_u512(field, wide))
 
 
+@pytest.mark.parametrize("field", [0, 1])
+def test_batch_invert_assigned(field, ctx, oracle_c):
+    """SURVEY 8 f3: Assigned<F> columns (numerator / denominator) -> F, against the restated poly::batch_invert_assigned
+    and against plain big-integer division; Zero, Trivial, zero-denominator and ragged-tail cells included."""
+    from oracle import halo2 as H
+    from oracle.vec import Vec
+    co = oracle_c
+    F = co.FIELDS[field]
+    p = F.p
+    rnd = random.Random(7 + field)
+    for n in (1, 7, 8, 9, 2048 + 3):
+        num = [rnd.randrange(p) for _ in range(n)]
+        den = [rnd.choice([1, 1, 1, 0, 2, p - 1, rnd.randrange(p)]) for _ in range(n)]
+        num[0], den[0] = 0, 1                                   # Assigned::Zero
+        nm, dm = co.to_mont(field, num), co.to_mont(field, den)
+        got = ar.batch_invert_assigned(ctx, field, nm, dm)
+        assert np.array_equal(got, H.batch_invert_assigned(Vec(field), nm, dm))
+        assert co.from_mont(field, got) == [x * F.inv(d) % p for x, d in zip(num, den)]
+    trivial = co.to_mont(field, [rnd.randrange(p) for _ in range(64)])          # a column of Trivial cells comes back unchanged
+    assert np.array_equal(ar.batch_invert_assigned(ctx, field, trivial, co.to_mont(field, [1] * 64)), trivial)
+
+
 @pytest.mark.parametrize("curve", [0, 1])
 def test_curve_ops(curve, ctx, oracle_c):
     co = oracle_c

@@ -195,6 +195,28 @@ def test_sanity_checks_flag_catches_broken_copy_constraint(ctx, monkeypatch):
     pk.close(); params.close()
 
 
+@pytest.mark.parametrize("which", ["shot", "board"])
+def test_quotient_dag_and_tree_programs_agree(ctx, which, monkeypatch):
+    """h(X) compiled as one DAG per tier (shared sub-expressions, hoisted factors: csrc/evalprog.h) and as the
+    reference-shaped one-tree-per-polynomial program give the same proof bytes; the DAG costs fewer multiplications."""
+    from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
+    cs, cfg, asg = (shot_circuit if which == "shot" else board_circuit)(1)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    monkeypatch.setenv("BZ_QUOTIENT_CSE", "0")
+    from battlezips_halo2_b200.plonk import prover as PR
+    from tests.util_prover import VK_REPR
+    pk_tree = PR.ProvingKey(ctx, params, job.ir, job.asg.fixed, job.mapping, VK_REPR)       # programs are compiled at pk creation
+    monkeypatch.delenv("BZ_QUOTIENT_CSE")
+    a, b = _prove(job, pk, [2])[0], _prove(job, pk_tree, [2])[0]
+    assert first_diff(a, b) is None, first_diff(a, b)
+    assert job.verify(a)
+    cost = lambda k: sum(m * p for m, p in k.quotient_muls)
+    assert cost(pk) < cost(pk_tree), (pk.quotient_muls, pk_tree.quotient_muls)
+    print(which, "multiplications per proof in h(X): DAG", cost(pk), "tree", cost(pk_tree), pk.quotient_muls, pk_tree.quotient_muls)
+    pk_tree.close(); pk.close(); params.close()
+
+
 def test_device_proofs_equal_committed_goldens(ctx):
     """The committed oracle goldens (tests/golden/proofs.npz): tiny k = 5, Shot k = 11 and Board k = 12 proofs from the
     device are byte-identical -- no oracle run needed on the GPU box for this comparison (the witness / keys still come

@@ -75,3 +75,17 @@ def test_oracle_reproduces_committed_golden_proofs(tiny):
     job = Job(cs, asg)
     proof = job.oracle_proof(index=0)
     assert proof == bytes(gold["shot_w0_idx0"]) and job.verify(proof)
+
+
+def test_oracle_batch_invert_assigned_is_division():
+    """The restated poly::batch_invert_assigned equals numerator / denominator (0 for a zero denominator) in big integers."""
+    import random
+    from oracle import c_oracle as co, halo2 as H
+    from oracle.vec import Vec
+    for f in (0, 1):
+        F = co.FIELDS[f]
+        p, rnd = F.p, random.Random(f)
+        num = [rnd.randrange(p) for _ in range(200)]
+        den = [rnd.choice([0, 1, 2, p - 1, rnd.randrange(p)]) for _ in range(200)]
+        got = H.batch_invert_assigned(Vec(f), co.to_mont(f, num), co.to_mont(f, den))
+        assert co.from_mont(f, got) == [x * F.inv(d) % p for x, d in zip(num, den)]
