@@ -51,6 +51,10 @@ extern "C" {
     pub fn bz_pk_destroy(pk: *mut bz_pk);
     pub fn bz_pk_num_random(pk: *const bz_pk) -> u32;
     pub fn bz_pk_proof_size(pk: *const bz_pk) -> u32;
+    pub fn bz_pk_quotient_muls(pk: *const bz_pk, tier: u32, points: *mut u32) -> u32;
+    // poly.rs `batch_invert_assigned`: Assigned<F> = numerator / denominator per cell (Zero = (0, 1), Trivial(x) = (x, 1))
+    pub fn bz_batch_invert_assigned(ctx: *mut bz_ctx, field: c_int, numerators: *const c_void, denominators: *const c_void, out: *mut c_void, n: u64) -> c_int;
+    pub fn bz_batch_invert_assigned_dev(ctx: *mut bz_ctx, field: c_int, d_numerators: *const c_void, d_denominators: *const c_void, d_out: *mut c_void, n: u64) -> c_int;
     // poly/commitment.rs `Params::new`, pasta_curves `hash_to_curve`
     pub fn bz_params_new(ctx: *mut bz_ctx, k: u32, curve: c_int, g: *mut c_void, g_lagrange: *mut c_void, w: *mut c_void, u: *mut c_void) -> c_int;
     pub fn bz_hash_to_curve(ctx: *mut bz_ctx, curve: c_int, domain_prefix: *const c_char, messages: *const c_void, msg_len: u32, count: u64, out_affine: *mut c_void) -> c_int;
