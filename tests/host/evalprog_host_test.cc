@@ -15,7 +15,14 @@ static u64 subm(u64 a, u64 b) { return (a + P - b) % P; }
 
 static std::mt19937_64 rng(12345);
 static const int NADV = 6, NFIX = 4, NINST = 2, NCONST = 8, G = NADV;
-static u64 val_adv[NADV + NINST][3], val_fix[NFIX][3], val_const[64];
+static uint32_t g_inst_base = G;
+static int g_max_tmp = -1;
+static u64 val_const[4096], salt = 1;
+static u64 hval(u64 kind, u64 col, long long rot) {           // pseudo-random value of a column cell at the evaluation point
+  u64 z = salt * 0x9E3779B97F4A7C15ull + kind * 0xBF58476D1CE4E5B9ull + col * 0x94D049BB133111EBull + (u64)(rot + 1000) * 0xD6E8FEB86659FD93ull;
+  z ^= z >> 31; z *= 0x7FB5D329728EA185ull; z ^= z >> 27; z *= 0x81DADEF4BC2DD44Dull; z ^= z >> 33;
+  return z % P;
+}
 static std::vector<std::vector<Token>> pool;
 
 static std::vector<Token> gen(int depth) {
@@ -50,9 +57,9 @@ static u64 eval_tokens(const std::vector<Token>& t, uint32_t lo, uint32_t hi, u6
     const Token& k = t[i];
     switch (k.op) {
       case 0: st.push_back(val_const[k.a]); break;
-      case 1: st.push_back(val_adv[k.a][k.b + 1]); break;
-      case 2: st.push_back(val_fix[k.a][k.b + 1]); break;
-      case 3: st.push_back(val_adv[G + k.a][k.b + 1]); break;
+      case 1: st.push_back(hval(0, k.a, k.b)); break;
+      case 2: st.push_back(hval(1, k.a, k.b)); break;
+      case 3: st.push_back(hval(0, g_inst_base + k.a, k.b)); break;
       case 4: st.back() = subm(0, st.back()); break;
       case 5: { u64 r = st.back(); st.pop_back(); st.back() = addm(st.back(), r); break; }
       case 6: { u64 r = st.back(); st.pop_back(); st.back() = mulm(st.back(), r); ++nmul; break; }
@@ -67,8 +74,8 @@ static u64 run_program(const ProgBuilder& pb, u64& nmul) {
   for (uint32_t ins : pb.code) {
     const uint32_t op = ins & 15u, x = (ins >> 4) & 0xfffu, y = ins >> 16;
     switch (op) {
-      case OP_PUSH_P: st[sp++] = val_adv[x][pb.rot_table[y] + 1]; break;
-      case OP_PUSH_S: st[sp++] = val_fix[x][pb.rot_table[y] + 1]; break;
+      case OP_PUSH_P: st[sp++] = hval(0, x, pb.rot_table[y]); break;
+      case OP_PUSH_S: st[sp++] = hval(1, x, pb.rot_table[y]); break;
       case OP_PUSH_C: st[sp++] = val_const[ins >> 4]; break;
       case OP_ADD: --sp; st[sp - 1] = addm(st[sp - 1], st[sp]); break;
       case OP_SUB: --sp; st[sp - 1] = subm(st[sp - 1], st[sp]); break;
@@ -78,7 +85,7 @@ static u64 run_program(const ProgBuilder& pb, u64& nmul) {
       case OP_ADDC: st[sp - 1] = addm(st[sp - 1], val_const[ins >> 4]); break;
       case OP_FOLD: --sp; acc = addm(mulm(acc, val_const[ins >> 4]), st[sp]); ++nmul; break;
       case OP_ACC_MULC: acc = mulm(acc, val_const[ins >> 4]); ++nmul; break;
-      case OP_TEE: if ((ins >> 4) >= (uint32_t)EVAL_TMP) { printf("tmp overflow\n"); exit(1); } tmp[ins >> 4] = st[sp - 1]; break;
+      case OP_TEE: if ((ins >> 4) >= (uint32_t)EVAL_TMP) { printf("tmp overflow\n"); exit(1); } tmp[ins >> 4] = st[sp - 1]; if ((int)(ins >> 4) > g_max_tmp) g_max_tmp = (int)(ins >> 4); break;
       case OP_PUSH_T: st[sp++] = tmp[ins >> 4]; break;
       default: printf("bad op\n"); exit(1);
     }
@@ -88,13 +95,59 @@ static u64 run_program(const ProgBuilder& pb, u64& nmul) {
   return acc;
 }
 
-int main() {
+// file mode: the gate polynomials of a real constraint system, one line per polynomial
+//   "<tier> <e> <ntok> (<op> <a> <b>)*"   preceded by a header line "<E> <instance slot base> <#consts>"
+// prints per tier: polynomials, multiplications as trees / as one DAG, deepest stack, temporaries used
+static int file_mode(const char* path) {
+  FILE* f = fopen(path, "r");
+  if (!f) { printf("cannot open %s\n", path); return 1; }
+  uint32_t E, ibase, nconst;
+  if (fscanf(f, "%u %u %u", &E, &ibase, &nconst) != 3) return 1;
+  g_inst_base = ibase;
+  const uint32_t YP0 = nconst;
+  if (YP0 + E + 1 > 4096) { printf("too many constants\n"); return 1; }
+  struct PolyIn { uint32_t tier, e; std::vector<Token> t; };
+  std::vector<PolyIn> in;
+  for (;;) {
+    PolyIn p; uint32_t nt;
+    if (fscanf(f, "%u %u %u", &p.tier, &p.e, &nt) != 3) break;
+    for (uint32_t i = 0; i < nt; ++i) { Token k; if (fscanf(f, "%u %u %d", &k.op, &k.a, &k.b) != 3) return 1; p.t.push_back(k); }
+    in.push_back(p);
+  }
+  fclose(f);
+  for (uint32_t tier = 0; tier < 3; ++tier) {
+    salt = 77 + tier;
+    for (uint32_t i = 0; i < nconst; ++i) val_const[i] = hval(2, i, 0);
+    const u64 y = hval(3, 0, 0);
+    { u64 p = 1; for (uint32_t d = 0; d <= E; ++d) { val_const[YP0 + d] = p; p = mulm(p, y); } }
+    std::vector<Token> tokens; std::vector<uint32_t> lo, hi, eidx;
+    for (const PolyIn& p : in) if (p.tier == tier) { lo.push_back((uint32_t)tokens.size()); tokens.insert(tokens.end(), p.t.begin(), p.t.end()); hi.push_back((uint32_t)tokens.size()); eidx.push_back(p.e); }
+    if (eidx.empty()) { printf("tier %u polys 0\n", tier); continue; }
+    u64 want = 0, naive = 0;
+    for (size_t i = 0; i < eidx.size(); ++i) want = addm(want, mulm(eval_tokens(tokens, lo[i], hi[i], naive), val_const[YP0 + (E - 1 - eidx[i])]));
+    naive += eidx.size();
+    GateDag dag; dag.advice_slot_of_instance = ibase;
+    for (size_t i = 0; i < eidx.size(); ++i) dag.add(tokens, lo[i], hi[i], eidx[i]);
+    dag.plan();
+    ProgBuilder pb; int prev = -1;
+    for (const GateDag::Group& g : dag.groups) { dag.emit_group(pb, g, prev, [&](uint32_t d) { return YP0 + d; }); prev = (int)dag.polys[g.first + g.count - 1].e; }
+    if ((uint32_t)prev != E - 1) pb.accmul(YP0 + (E - 1 - (uint32_t)prev));
+    if (pb.max_depth > EVAL_STACK) { printf("tier %u: stack depth %d exceeds EVAL_STACK\n", tier, pb.max_depth); return 1; }
+    u64 nm = 0; g_max_tmp = -1;
+    if (run_program(pb, nm) != want) { printf("MISMATCH tier %u\n", tier); return 1; }
+    printf("tier %u polys %zu tree_muls %llu dag_muls %llu depth %d temporaries %d instructions %zu\n", tier, eidx.size(), naive, nm, pb.max_depth, g_max_tmp + 1, pb.code.size());
+  }
+  printf("ok\n");
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1) return file_mode(argv[1]);
   u64 tot_naive = 0, tot[4] = {0, 0, 0, 0};
   int deepest = 0;
   for (int trial = 0; trial < 400; ++trial) {
     pool.clear();
-    for (auto& r : val_adv) for (u64& v : r) v = rng() % P;
-    for (auto& r : val_fix) for (u64& v : r) v = rng() % P;
+    salt = rng();
     for (int i = 0; i < NCONST; ++i) val_const[i] = rng() % P;
     const uint32_t E = 4 + rng() % 30, YP0 = 16;               // constants 16.. : y^0 .. y^E
     const u64 y = rng() % P;
