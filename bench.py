@@ -30,8 +30,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default=os.environ.get("BZ_WORKLOAD", "shot"))
     ap.add_argument("--batch", type=int, default=int(os.environ.get("BZ_BATCH", "64")), help="proofs per step per GPU (shot / board)")
-    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "4")),
-                    help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board)")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("BZ_INFLIGHT", "0")),
+                    help="concurrent prover lanes per GPU (own host thread + CUDA stream each; shot / board); "
+                         "0 = auto: one per host core available to this GPU, between 2 and 6")
     ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
@@ -39,7 +40,14 @@ def parse():
     ap.add_argument("--cpu-sample-log", type=int, default=18)
     ap.add_argument("--no-extras", dest="extras", action="store_false",
                     help="default (shot) run only: skip the compact Board / MSM / NTT sub-benchmarks reported under `extras`")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.inflight <= 0:          # measured on 1xB200 / 16 cores: 4 lanes 3 153, 6 lanes 3 254, 8 lanes 3 286 Shot proofs/s
+        try:
+            cores = len(os.sched_getaffinity(0))
+        except AttributeError:
+            cores = os.cpu_count() or 4
+        args.inflight = max(2, min(6, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", args.gpus)))))
+    return args
 
 
 # ------------------------------------------------------------------------------------------------------
