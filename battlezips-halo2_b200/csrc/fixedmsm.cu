@@ -16,13 +16,17 @@
 namespace bz {
 
 // ---- table construction (one-off per Params) -----------------------------------------------------
+// scratch[d][i] = (d + 1) * base[i] for d < nbk.  The multiples of one point form a chain of mixed additions; the chain is
+// cut into `nseg` segments that start from [seg * len] base[i] (a 32-bit double-and-add), so a 2^11-point URS still fills
+// the GPU: thread = (segment, point), adjacent threads store adjacent points.
 template <class BP>
-__global__ void fb_multiples_kernel(const Affine<BP>* __restrict__ base, uint32_t npts, uint32_t nbk, Xyzz<BP>* __restrict__ scratch) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= npts) return;
+__global__ void fb_multiples_kernel(const Affine<BP>* __restrict__ base, uint32_t npts, uint32_t nbk, uint32_t nseg, Xyzz<BP>* __restrict__ scratch) {
+  const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (uint64_t)npts * nseg) return;
+  const uint32_t i = (uint32_t)(t % npts), seg = (uint32_t)(t / npts), len = nbk / nseg, d0 = seg * len;
   Affine<BP> p = aff_load(base + i);
-  Xyzz<BP> acc = xyzz_identity<BP>();
-  for (uint32_t d = 0; d < nbk; ++d) {
+  Xyzz<BP> acc = d0 ? xyzz_mul_u32(xyzz_from_affine(p), d0) : xyzz_identity<BP>();
+  for (uint32_t d = d0; d < d0 + len; ++d) {
     xyzz_add_mixed(acc, p);
     Xyzz<BP>* o = scratch + (size_t)d * npts + i;
     fe_store(&o->x, acc.x); fe_store(&o->y, acc.y); fe_store(&o->zz, acc.zz); fe_store(&o->zzz, acc.zzz);
@@ -82,8 +86,10 @@ static void fb_build_t(Ctx* ctx, FixedBase& fb, const void* bases_dev) {
   base.alloc((size_t)npts * sizeof(Affine<BP>));
   BZ_CUDA(cudaMemcpyAsync(base.p, bases_dev, (size_t)npts * sizeof(Affine<BP>), cudaMemcpyDeviceToDevice, st));
   const uint64_t per_window = (uint64_t)nbk * npts;
+  uint32_t nseg = 1;                                   // power of two (divides nbk): ~128 K threads, segments of >= 64 additions
+  while (nseg * 2 <= nbk / 64 && (uint64_t)npts * nseg * 2 <= 131072) nseg *= 2;
   for (uint32_t w = 0; w < W; ++w) {
-    fb_multiples_kernel<BP><<<(npts + 63) / 64, 64, 0, st>>>(base.as<Affine<BP>>(), npts, nbk, scratch.as<Xyzz<BP>>());
+    fb_multiples_kernel<BP><<<(unsigned)(((uint64_t)npts * nseg + 63) / 64), 64, 0, st>>>(base.as<Affine<BP>>(), npts, nbk, nseg, scratch.as<Xyzz<BP>>());
     uint64_t nthreads = (per_window + 15) / 16;
     fb_to_affine_kernel<BP, 16><<<(unsigned)((nthreads + 127) / 128), 128, 0, st>>>(
         scratch.as<Xyzz<BP>>(), fb.table.as<Affine<BP>>() + (size_t)w * per_window, per_window);

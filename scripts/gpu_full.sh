@@ -1,0 +1,11 @@
+set -o pipefail
+(time python -m pytest tests -m gpu -x -q) > gpurun_out/full_tests.log 2>&1; tail -4 gpurun_out/full_tests.log
+(time python -c "import __graft_entry__ as g; g.smoke()") > gpurun_out/full_smoke.log 2>&1; tail -3 gpurun_out/full_smoke.log
+(time python bench.py) > gpurun_out/full_bench.log 2>&1; tail -c 600 gpurun_out/full_bench.log
+python - <<'PY'
+import json
+for l in open('gpurun_out/full_bench.log'):
+    if l.startswith('{'):
+        d=json.loads(l); print(round(d['value'],1), round(d['e2e']['value'],1), round(d['ms_per_step'],2), d['config']['workload'][:70], {k:round(v/d['steps'],2) for k,v in d['roofline']['kernel_ms'].items()}, d.get('verified'), d.get('single_proof_ms'))
+        print({k:(v.get('value'),v.get('unit'),v.get('error')) for k,v in d.get('extras',{}).items()})
+PY
