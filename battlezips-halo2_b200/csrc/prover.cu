@@ -289,15 +289,15 @@ API int bz_params_create(bz_ctx* ctx, uint32_t k, int curve, const void* g, cons
     if (!c) {
       const char* e = getenv("BZ_FIXED_WINDOW");
       c = e ? (uint32_t)atoi(e) : 0;
-      if (!c) {   // largest window whose two tables stay under ~150 GB of the 180 GB (k = 11: c = 16, 137 GB; k = 12: c = 15, 146 GB;
+      if (!c) {   // largest window whose two tables stay under 160 GB of the B200's 191 GB (k = 11: c = 16, 138 GB; k = 12: c = 15, 155 GB;
         // k = 13: c = 13, 85 GB) and under 2^31 entries.  Measured on B200, Shot proofs/s: c = 13 -> 2422, 14 -> 2457, 15 -> 2560
         // (17 instead of ~18.8 additions per scalar: the top window of a 255-bit scalar is almost never occupied at c = 15);
         // with 6 lanes: c = 15 -> 3250, c = 16 -> 3324 (16 additions); Board c = 14 -> 15: table MSM time -9 %.
         // The cap also respects what is free right now, so a second Params alive at the same time gets a smaller window.
         size_t free_b = 0, total_b = 0;
         BZ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-        const double cap = std::min(150e9, (double)free_b - 16e9);          // leave room for the batch work areas
-        for (c = std::min(16u, std::max(8u, k + 4)); c > 4; --c) {
+        const double cap = std::min(160e9, (double)free_b - 16e9);          // leave room for the batch work areas
+        for (c = std::min(16u, std::max(8u, k + 5)); c > 4; --c) {
           double entries = (double)((256 + c - 1) / c) * (double)(1u << (c - 1)) * (double)(n + 2);
           if (2.0 * entries * 64.0 <= cap && entries < 2147483648.0) break;
         }

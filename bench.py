@@ -809,6 +809,8 @@ def main():
     if args.workload == "shot" and args.extras:
         if hasattr(wl, "close"):
             wl.close()
+        if os.environ.get("BZ_BENCH_VERBOSE"):
+            print("free / total HBM after closing the headline workload:", torch.cuda.mem_get_info(local_rank), file=sys.stderr)
         names = ["board", "msm", "ntt", "commit"] if world == 1 else ["msm", "commit"]
         for name in names:
             # an extra must never take the headline line down with it; under torchrun every rank takes the same branch
