@@ -13,6 +13,7 @@
 // Fusions: zero-padding + zeta^(i mod 3) coset pre-scale on the first pass (coeff_to_extended),
 // N^-1 and zeta^-(i mod 3) post-scale on the last pass (ifft / extended_to_coeff).
 #include "common.h"
+#include <cstdlib>
 #include "field.cuh"
 
 namespace bz {
@@ -218,7 +219,8 @@ static void ntt_run_t(Ctx* ctx, int field, const Fe<P>* in, Fe<P>* out, int logN
   }
   for (int i = 0; i < 3; ++i) { base.pre[i] = pre[i]; base.post[i] = post[i]; }
 
-  int npass = logN <= 12 ? 1 : (logN <= 20 ? 2 : 3);
+  static const int two_pass_max = [] { const char* e = getenv("BZ_NTT_2PASS_MAX"); return e ? atoi(e) : 20; }();      // A/B knob
+  int npass = logN <= 12 ? 1 : (logN <= two_pass_max ? 2 : 3);
   if (npass == 1) {
     NttPassArgs<P> a = base;
     a.in = in; a.out = out;
