@@ -47,6 +47,7 @@ __attribute__((visibility("default"))) int bz_ctx_create(int device, void* strea
     h->own_stream = true;
   }
   cudaDeviceGetAttribute(&h->c.sm_count, cudaDevAttrMultiProcessorCount, device);
+  { const char* pe = getenv("BZ_FB_PAIRS"); h->c.fb_pairs = pe && atoi(pe) != 0; }
   *out = h;
   return BZ_OK;
 }

@@ -78,6 +78,7 @@ struct Ctx {
   DevBuf stage[6];         // device staging of the host-buffer entry points (kept across calls: no cudaMalloc/cudaFree per call)
   uint64_t kernel_launches = 0;   // counted by every launch site (bench.py's gpu_launches)
   bool profiling = false;
+  bool fb_pairs = false;   // BZ_FB_PAIRS=1 at context creation: pair mode of the table MSM (fixedmsm.cu; measured slower, kept for A/B)
   DevBuf counters;        // [0] = mixed additions done by fixed_msm_kernel while profiling
   std::vector<ProfRec> prof;
   double prof_ms[PROF_NTAGS] = {0};

@@ -217,6 +217,52 @@ def test_quotient_dag_and_tree_programs_agree(ctx, which, monkeypatch):
     pk_tree.close(); pk.close(); params.close()
 
 
+@pytest.mark.parametrize("pairs", ["0", "1"])
+def test_table_msm_degenerate_bases_and_pair_mode_parity(oracle_c, monkeypatch, pairs):
+    """The table MSM in both accumulation modes -- default, and BZ_FB_PAIRS=1 (affine pre-addition of consecutive table points with one shared inversion per thread, fixedmsm.cu) --:
+    same commitments as the oracle's best_multiexp on a URS with repeated, opposite and identity bases (the pairs that must
+    take the complete-addition path), and the Shot golden proof bytes."""
+    import os
+    import battlezips_halo2_b200 as bz
+    from battlezips_halo2_b200.plonk import prover as PR
+    from battlezips_halo2_b200.circuits import shot_circuit
+    from tests.util_prover import VK_REPR
+    from oracle import halo2 as H
+    co = oracle_c
+    monkeypatch.setenv("BZ_FB_PAIRS", pairs)
+    c2 = bz.Context(0)
+    monkeypatch.delenv("BZ_FB_PAIRS")
+    C = co.CURVES[0][0]
+    h = C.hash_to_curve("bz-pairs")
+    k, n = 6, 64
+    pts = [h(bytes([i])) for i in range(n + 2)]
+    pts[1] = pts[0]; pts[2] = C.neg(pts[0]); pts[3] = None; pts[40] = pts[8]; pts[41] = pts[8]
+    g = co.points_to_mont(0, pts[:n])
+    w, u = co.points_to_mont(0, [pts[n]])[0], co.points_to_mont(0, [pts[n + 1]])[0]
+    params = PR.Params(c2, k, g, g, w, u, window_bits=5)
+    rng = np.random.default_rng(5)
+    for trial in range(4):
+        poly = co.from_u512(0, rng.integers(0, 2**63, size=(n, 8), dtype=np.uint64))
+        if trial == 1:
+            poly[:] = poly[0]                                   # equal scalars: equal digits on the repeated bases
+        if trial == 2:
+            poly[4:] = 0
+        blind = co.from_u512(0, rng.integers(0, 2**63, size=(1, 8), dtype=np.uint64))
+        exp = co.to_affine(0, co.best_multiexp(0, np.concatenate([poly, blind]), np.concatenate([g, w[None]])))
+        assert np.array_equal(params.commit(poly, blind[0], lagrange=False), exp[0]), trial
+    params.close()
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "proofs.npz"))
+    cs, _, asg = shot_circuit(0)
+    fx = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"params_vesta_k{asg.k}.npz"))
+    params = PR.Params(c2, asg.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"], window_bits=12)
+    pk = PR.ProvingKey(c2, params, cs.to_ir(), asg.fixed, asg.permutation_mapping(), VK_REPR)
+    advice = np.stack([PR.mont(col) for col in asg.advice])
+    wide = H.splitmix64_wide(0xB200B200B200B200, pk.num_random)
+    proof = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
+    assert proof == bytes(gold["shot_w0_idx0"])
+    pk.close(); params.close(); c2.close()
+
+
 def test_device_proofs_equal_committed_goldens(ctx):
     """The committed oracle goldens (tests/golden/proofs.npz): tiny k = 5, Shot k = 11 and Board k = 12 proofs from the
     device are byte-identical -- no oracle run needed on the GPU box for this comparison (the witness / keys still come
