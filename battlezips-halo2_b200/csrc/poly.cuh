@@ -402,6 +402,46 @@ __global__ void grand_product_finish_kernel(const Fe<P>* __restrict__ pnum, cons
   fe_store(region_ptr<P>(reg, zref, b, n) + i, v);
 }
 
+// All grand products of a proof in one launch (blockIdx.z = product): the first `nsets` products are the permutation sets,
+// chained through z_s[0] = z_{s-1}[u] (u = first unusable row); the others (lookups) start at 1.
+//   z_g[i] = z0_g * pnum_g[i] * sden_g[i] / sden_g[0],   z0_s = prod_{s' < s} pnum_s'[u] * sden_s'[u] / sden_s'[0]
+// The <= 8 inversions a product needs share one Fermat chain (Montgomery's trick, zeros skipped), so a batch pays the
+// inversion latency once instead of once per product.
+struct GpBatchDesc { uint32_t nprod, nsets; PolyRef zref[8]; };
+template <class P>
+__global__ void grand_product_finish_batch_kernel(const Fe<P>* __restrict__ pnum, const Fe<P>* __restrict__ sden, uint64_t prod_stride, uint64_t nd_stride,
+                                                  Regions reg, GpBatchDesc d, uint32_t n, uint32_t u) {
+  __shared__ Fe<P> scale_sh;
+  const uint32_t b = blockIdx.y, g = blockIdx.z;
+  if (threadIdx.x == 0) {
+    const uint32_t g0 = g < d.nsets ? 0u : g;
+    Fe<P> pre[8], s0[8];
+    Fe<P> acc = fe_one<P>();
+    for (uint32_t gp = g0; gp <= g; ++gp) {
+      s0[gp - g0] = fe_load(sden + (uint64_t)gp * prod_stride + (uint64_t)b * nd_stride);
+      pre[gp - g0] = acc;
+      if (!fe_is_zero(s0[gp - g0])) acc = fe_mul(acc, s0[gp - g0]);
+    }
+    Fe<P> inv = fe_inv(acc);
+    Fe<P> z0 = fe_one<P>(), mine = fe_zero<P>();
+    for (uint32_t gp = g + 1; gp-- > g0;) {                       // 1 / sden_gp[0], last product first
+      Fe<P> iv = fe_zero<P>();
+      if (!fe_is_zero(s0[gp - g0])) { iv = fe_mul(inv, pre[gp - g0]); inv = fe_mul(inv, s0[gp - g0]); }
+      if (gp == g) mine = iv;
+      else {
+        const uint64_t at = (uint64_t)gp * prod_stride + (uint64_t)b * nd_stride + u;
+        z0 = fe_mul(z0, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), iv));
+      }
+    }
+    scale_sh = fe_mul(z0, mine);
+  }
+  __syncthreads();
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t at = (uint64_t)g * prod_stride + (uint64_t)b * nd_stride + i;
+  fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale_sh));
+}
+
 // ---- Horner evaluation: one CTA per (query, proof) ---------------------------------------------------
 struct EvalQuery { PolyRef poly; uint32_t point_const; };     // point = consts[b][point_const]
 constexpr int EVALQ_THREADS = 128;

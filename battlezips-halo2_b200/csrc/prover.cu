@@ -243,7 +243,7 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.hcoef.alloc(B * en * E);
   w.hext_low.alloc(B * (en / 2 + en / 4) * E);        // tiers 1 and 2, back to back
   w.hcoef_low.alloc(B * (en / 2) * E);
-  w.nd.alloc(4 * B * n * E);
+  w.nd.alloc(4 * (size_t)std::max<uint32_t>(1, pk.nsets + pk.L) * B * n * E);       // num, den, prefix(num), suffix(den) of every grand product
   w.consts.alloc(B * (size_t)pk.cstride * E);
   w.extras.alloc(B * 64 * 2 * E);
   w.evalout.alloc(B * (pk.evals.size() + pk.point_sets.size() + 8) * E);
@@ -1045,8 +1045,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   // ---- steps 7-9: permutation products, lookup products, random polynomial: one commitment batch
   phase.reset(); phase.reset(new NvtxRange("steps 7-9: grand products, random polynomial"));
   {
-    DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n;
-    for (uint32_t s = 0; s < pk.nsets; ++s) {
+    auto perm_desc = [&](uint32_t s) {
       PermSetDesc d{};
       uint32_t c0 = s * pk.chunk_len, c1 = std::min<uint32_t>(pk.M, c0 + pk.chunk_len);
       d.ncols = c1 - c0;
@@ -1057,6 +1056,43 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         d.sigma_slot[j - c0] = j;
         d.bd_const[j - c0] = pk.C_BD0 + j;
       }
+      return d;
+    };
+    const uint32_t NG = pk.nsets + L;
+    static const bool gp_sequential = [] { const char* e = getenv("BZ_GP_SEQUENTIAL"); return e && atoi(e) != 0; }();     // A/B knob
+    if (NG >= 1 && NG <= 8 && (n + SCAN_TILE - 1) / SCAN_TILE <= 8 && !gp_sequential) {
+      // Shot / Board: all grand products of the batch in lockstep -- fractions, ONE prefix and ONE suffix scan launch over
+      // NG x B arrays, ONE finish launch (a single inversion latency per batch instead of one per product), one copy launch
+      const uint64_t PS = (uint64_t)B * n;
+      DFe* num = (DFe*)w.nd.p; DFe* den = num + NG * PS; DFe* pnum = den + NG * PS; DFe* sden = pnum + NG * PS;
+      GpBatchDesc gd{}; gd.nprod = NG; gd.nsets = pk.nsets;
+      std::vector<CopyDesc> cd;
+      {
+        ProfScope prof(C, PROF_SCAN);
+        for (uint32_t s = 0; s < pk.nsets; ++s) {
+          perm_fraction_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, perm_desc(s), (const DFe*)pk.lval.p + (uint64_t)cs.F * n, (const DFe*)pk.omega_pows.p,
+                                                                            (const DFe*)w.consts.p, pk.cstride, pk.C_BETA, pk.C_GAMMA, num + s * PS, den + s * PS, n);
+          gd.zref[s] = PolyRef{R_VAL, pk.slot_pz(s)};
+          cd.push_back(CopyDesc{PolyRef{R_VAL, pk.slot_pz(s)}, n - bf, pk.r_perm0 + s * (bf + 1), bf});
+        }
+        for (uint32_t l = 0; l < L; ++l) {
+          const uint32_t g = pk.nsets + l;
+          lookup_fraction_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_cin0 + 2 * l}, PolyRef{R_MISC, pk.m_cin0 + 2 * l + 1},
+                                                                              PolyRef{R_VAL, pk.slot_lk(l, 0)}, PolyRef{R_VAL, pk.slot_lk(l, 1)},
+                                                                              (const DFe*)w.consts.p, pk.cstride, pk.C_BETA, pk.C_GAMMA, num + g * PS, den + g * PS, n);
+          gd.zref[g] = PolyRef{R_VAL, pk.slot_lk(l, 2)};
+          cd.push_back(CopyDesc{PolyRef{R_VAL, pk.slot_lk(l, 2)}, n - bf, pk.r_lkz0 + l * (bf + 1), bf});
+        }
+        product_scan_kernel<FpP><<<dim3(1, NG * B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0);
+        product_scan_kernel<FpP><<<dim3(1, NG * B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
+        grand_product_finish_batch_kernel<FpP><<<dim3((n + 127) / 128, B, NG), 128, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
+        C->kernel_launches += NG + 3;
+      }
+      launch_copy(cd, n);
+    } else {
+    DFe* num = (DFe*)w.nd.p; DFe* den = num + (uint64_t)B * n;
+    for (uint32_t s = 0; s < pk.nsets; ++s) {
+      PermSetDesc d = perm_desc(s);
       {
         ProfScope prof(C, PROF_SCAN);
         perm_fraction_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, d, (const DFe*)pk.lval.p + (uint64_t)cs.F * n, (const DFe*)pk.omega_pows.p,
@@ -1078,6 +1114,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       grand_product(PolyRef{R_VAL, pk.slot_lk(l, 2)}, false, PolyRef{R_VAL, 0}, 0);
       std::vector<CopyDesc> cd{CopyDesc{PolyRef{R_VAL, pk.slot_lk(l, 2)}, n - bf, pk.r_lkz0 + l * (bf + 1), bf}};
       launch_copy(cd, n);
+    }
     }
     std::vector<CommitReq> reqs;
     std::vector<std::vector<HFe>> bl(B);
