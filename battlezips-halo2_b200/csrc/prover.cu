@@ -1059,7 +1059,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       return d;
     };
     const uint32_t NG = pk.nsets + L;
-    static const bool gp_sequential = [] { const char* e = getenv("BZ_GP_SEQUENTIAL"); return e && atoi(e) != 0; }();     // A/B knob
+    const bool gp_sequential = [] { const char* e = getenv("BZ_GP_SEQUENTIAL"); return e && atoi(e) != 0; }();     // A/B knob (read per call)
     if (NG >= 1 && NG <= 8 && (n + SCAN_TILE - 1) / SCAN_TILE <= 8 && !gp_sequential) {
       // Shot / Board: all grand products of the batch in lockstep -- fractions, ONE prefix and ONE suffix scan launch over
       // NG x B arrays, ONE finish launch (a single inversion latency per batch instead of one per product), one copy launch

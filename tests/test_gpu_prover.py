@@ -195,6 +195,22 @@ def test_sanity_checks_flag_catches_broken_copy_constraint(ctx, monkeypatch):
     pk.close(); params.close()
 
 
+def test_grand_products_batched_and_sequential_agree(ctx, monkeypatch):
+    """All grand products of a batch in lockstep (one scan / finish launch, one shared inversion) and the one-product-at-a-
+    time path (what large domains use) write the same proof; both equal the oracle's."""
+    from battlezips_halo2_b200.circuits import shot_circuit
+    cs, cfg, asg = shot_circuit(3)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx, window_bits=10)
+    a = _prove(job, pk, [1, 4])
+    monkeypatch.setenv("BZ_GP_SEQUENTIAL", "1")
+    b = _prove(job, pk, [1, 4])
+    monkeypatch.delenv("BZ_GP_SEQUENTIAL")
+    assert a == b
+    assert first_diff(a[1], job.oracle_proof(index=4)) is None
+    pk.close(); params.close()
+
+
 @pytest.mark.parametrize("which", ["shot", "board"])
 def test_quotient_dag_and_tree_programs_agree(ctx, which, monkeypatch):
     """h(X) compiled as one DAG per tier (shared sub-expressions, hoisted factors: csrc/evalprog.h) and as the
