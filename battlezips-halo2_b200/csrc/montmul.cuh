@@ -10,6 +10,11 @@
 // two shifts.  The one-limb right shift is free: the rows swap roles, the odd row is read two registers ahead, and
 // the single stray limb (old E[1]) is merged by the add.cc that opens the next chain.
 //
+// Tried and dropped (round 1): making every chain-ending `addc` consume-and-produce a (mathematically zero) carry, so that
+// ptxas must emit IADD3.X on the ALU pipe instead of IMAD.X on the fma-heavy pipe (30 -> 24 IMAD.X, heavy-pipe issue
+// cycles per multiplication 217 -> 204).  It chains all rows into ONE dependency chain: Shot 3 310 -> 3 171 proofs/s.
+// The independent chains below overlap; the pipe imbalance is the cheaper evil.
+//
 // Every primitive has a host emulation (explicit carry variable) so the exact instruction sequence is unit-tested
 // on the CPU against big-integer arithmetic (tests/test_montmul_host.py) before it ever runs on a GPU.
 #pragma once
