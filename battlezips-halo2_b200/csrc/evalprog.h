@@ -6,7 +6,10 @@
 //   * a sub-expression that occurs several times (the curve equation of the ECC gates, (x_p - x_q), running-sum
 //     differences, ...) is computed once per point and kept in a per-thread temporary (OP_TEE / OP_PUSH_T), and
 //   * consecutive polynomials of one gate that share a factor (normally the selector:  s*e_1, s*e_2, ...) are folded as
-//     acc <- acc*y^G + s*(e_1*y^.. + ... + e_m):  m + 1 multiplications instead of 2m.
+//     acc <- acc*y^G + s*(e_1*y^.. + ... + e_m):  m + 1 multiplications instead of 2m.  The factor is also found through
+//     nested products ((s*a)*e_1, (s*b)*e_2); the remaining factors are re-multiplied and interned, which for the ECC-style
+//     gates exposes many more shared products.  Re-association can also lose sharing, so the caller compiles a tier both
+//     ways and keeps the program with fewer multiplications.
 // Both rewrites compute the same field element at every point (exact arithmetic), so h(X) and the proof bytes do not change.
 // This header has no CUDA dependency: tests/host/evalprog_host_test.cc compiles it with g++ and checks the emitted
 // programs against direct evaluation of the expression trees.
@@ -87,7 +90,7 @@ struct GateDag {
   std::map<std::tuple<uint32_t, uint32_t, int32_t, int, int>, int> index;
   std::vector<Poly> polys;
   std::vector<Group> groups;
-  bool cse = true, hoist = true;
+  bool cse = true, hoist = true, nested = true;      // nested: hoist common factors through nested products as well
   uint32_t advice_slot_of_instance = 0;       // instance column c lives in per-proof slot G + c
   std::vector<int> free_tmp;
 
@@ -122,6 +125,15 @@ struct GateDag {
   }
   void add(const std::vector<Token>& tokens, uint32_t lo, uint32_t hi, uint32_t e) { polys.push_back(Poly{from_tokens(tokens, lo, hi), e}); }
 
+  // the factors of a (nested) product, in emission order
+  std::vector<int> factors(int v) const {
+    std::vector<int> out, st{v};
+    while (!st.empty()) {
+      const int c = st.back(); st.pop_back();
+      if (nodes[c].op == 6) { st.push_back(nodes[c].y); st.push_back(nodes[c].x); } else out.push_back(c);
+    }
+    return out;
+  }
   // children as the emission references them: a + (-b) is emitted as a b SUB, so it references b, not the negation
   void refs(int v, int& c0, int& c1, bool& is_sub) const {
     const Node& n = nodes[v];
@@ -143,7 +155,7 @@ struct GateDag {
     groups.clear();
     for (uint32_t i = 0; i < polys.size();) {
       Group g{i, 1, -1, {}};
-      const Node& r = nodes[polys[i].root];
+      const Node r = nodes[polys[i].root];           // (a copy: interning below may grow `nodes`)
       if (hoist && r.op == 6) {
         std::vector<int> cand = {r.x, r.y};
         uint32_t j = i + 1;
@@ -158,6 +170,35 @@ struct GateDag {
         if (j - i >= 2) {
           g.count = j - i; g.factor = cand[0];
           for (uint32_t p = i; p < j; ++p) { const Node& q = nodes[polys[p].root]; g.rest.push_back(q.x == g.factor ? q.y : q.x); }
+        }
+      }
+      if (hoist && cse && nested && g.factor < 0 && r.op == 6) {
+        // no common DIRECT child: look through nested products -- (s*a)*e_1, (s*b)*e_2 share s.  One common factor (a
+        // leaf if there is one: the selector) is pulled out, the other factors of every polynomial are re-multiplied
+        // (interned, so they are still shared with the rest of the DAG).
+        std::vector<int> cand = factors(polys[i].root);
+        uint32_t j = i + 1;
+        for (; j < polys.size() && nodes[polys[j].root].op == 6; ++j) {
+          const std::vector<int> fj = factors(polys[j].root);
+          std::vector<int> keep;
+          for (int c : cand) if (std::find(fj.begin(), fj.end(), c) != fj.end() && std::find(keep.begin(), keep.end(), c) == keep.end()) keep.push_back(c);
+          if (keep.empty()) break;
+          cand = keep;
+        }
+        if (j - i >= 2) {
+          int f = cand[0];
+          for (int c : cand) if (nodes[c].op <= 3) { f = c; break; }
+          std::vector<int> rest;
+          bool ok = true;
+          for (uint32_t p = i; p < j && ok; ++p) {
+            std::vector<int> fp = factors(polys[p].root);
+            fp.erase(std::find(fp.begin(), fp.end(), f));
+            if (fp.empty()) { ok = false; break; }
+            int prod = fp[0];
+            for (size_t t = 1; t < fp.size(); ++t) prod = intern(6, 0, 0, prod, fp[t]);
+            rest.push_back(prod);
+          }
+          if (ok) { g.count = j - i; g.factor = f; g.rest = rest; }
         }
       }
       groups.push_back(g);

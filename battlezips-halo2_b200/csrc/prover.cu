@@ -159,13 +159,19 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
     // BZ_QUOTIENT_CSE=0: every gate polynomial as its own expression tree (the reference's evaluation order), for A/B runs
     const char* cse_env = getenv("BZ_QUOTIENT_CSE");
     const bool use_dag = !(cse_env && atoi(cse_env) == 0);
-    auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
-      ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
+    auto count_muls = [](const ProgBuilder& pb) {
+      uint32_t m = 0;
+      for (uint32_t ins : pb.code) { const uint32_t op = ins & 15u; m += op == OP_MUL || op == OP_MULC || op == OP_FOLD || op == OP_ACC_MULC || op == OP_MUL_T_STORE; }
+      return m;
+    };
+    // one tier's program; `nested`: look for common factors through nested products too (evalprog.h)
+    auto compile = [&](uint32_t tier, bool nested, ProgBuilder& pb) {
+      pb.scale = 1 << (pk.ext_k - cs.k);
       const uint32_t E = (uint32_t)terms.size();
       auto yp = [&pk](uint32_t d) { return pk.C_YP0 + d; };
       int prev = -1;
       // the gate polynomials of this tier: one DAG (shared sub-expressions once, common factors hoisted; evalprog.h)
-      GateDag dag; dag.advice_slot_of_instance = cs.G;
+      GateDag dag; dag.advice_slot_of_instance = cs.G; dag.nested = nested;
       if (use_dag) {
         for (uint32_t e = 0; e < E; ++e)
           if (terms[e].gate && tier_of(std::max(1u, terms[e].degree)) == tier) dag.add(cs.tokens, terms[e].lo, terms[e].hi, e);
@@ -181,14 +187,22 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
         pb.fold(yp(prev < 0 ? 1u : e - (uint32_t)prev));          // acc = acc * y^(gap) + expr
         prev = (int)e;
       }
-      ninstr = 0;
-      if (prev < 0) return;                                                  // nothing in this tier
+      if (prev < 0) return false;                                            // nothing in this tier
       if ((uint32_t)prev != E - 1) pb.accmul(pk.C_YP0 + (E - 1 - (uint32_t)prev));
       pb.code.push_back(OP_MUL_T_STORE);
+      return true;
+    };
+    auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
+      ProgBuilder pb, pb2;
+      ninstr = 0; pk.q_muls[tier] = 0;
+      if (!compile(tier, true, pb)) return;
+      if (use_dag) {                                                         // re-association can lose sharing: keep the cheaper program
+        compile(tier, false, pb2);
+        if (pb.max_depth > EVAL_STACK || (pb2.max_depth <= EVAL_STACK && count_muls(pb2) < count_muls(pb))) pb = pb2;
+      }
       BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
       ninstr = (uint32_t)pb.code.size();
-      pk.q_muls[tier] = 0;
-      for (uint32_t ins : pb.code) { const uint32_t op = ins & 15u; pk.q_muls[tier] += op == OP_MUL || op == OP_MULC || op == OP_FOLD || op == OP_ACC_MULC || op == OP_MUL_T_STORE; }
+      pk.q_muls[tier] = count_muls(pb);
       BZ_CHECK(ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
       code.alloc(pb.code.size() * 4);
       BZ_CUDA(cudaMemcpy(code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
