@@ -90,11 +90,23 @@ struct GateDag {
   std::map<std::tuple<uint32_t, uint32_t, int32_t, int, int>, int> index;
   std::vector<Poly> polys;
   std::vector<Group> groups;
+  bool sort_rest = false, canon_mul = false;
   bool cse = true, hoist = true, nested = true;      // nested: hoist common factors through nested products as well
   uint32_t advice_slot_of_instance = 0;       // instance column c lives in per-proof slot G + c
   std::vector<int> free_tmp;
 
   int intern(uint32_t op, uint32_t a, int32_t b, int x, int y) {
+    if (canon_mul && op == 6) {                                         // products as sorted left-deep chains of their factors
+      std::vector<int> fl = factors(x), fy = factors(y);
+      fl.insert(fl.end(), fy.begin(), fy.end());
+      std::sort(fl.begin(), fl.end());
+      int prod = fl[0];
+      for (size_t t = 1; t < fl.size(); ++t) prod = intern_raw(6, 0, 0, prod, fl[t]);
+      return prod;
+    }
+    return intern_raw(op, a, b, x, y);
+  }
+  int intern_raw(uint32_t op, uint32_t a, int32_t b, int x, int y) {
     if ((op == 5 || op == 6) && x > y) std::swap(x, y);                // commutative
     auto key = std::make_tuple(op, a, b, x, y);
     if (cse) { auto it = index.find(key); if (it != index.end()) return it->second; }
@@ -194,6 +206,7 @@ struct GateDag {
             std::vector<int> fp = factors(polys[p].root);
             fp.erase(std::find(fp.begin(), fp.end(), f));
             if (fp.empty()) { ok = false; break; }
+            if (sort_rest) std::sort(fp.begin(), fp.end());          // same multiset of factors -> same chain of products
             int prod = fp[0];
             for (size_t t = 1; t < fp.size(); ++t) prod = intern(6, 0, 0, prod, fp[t]);
             rest.push_back(prod);

@@ -164,14 +164,15 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       for (uint32_t ins : pb.code) { const uint32_t op = ins & 15u; m += op == OP_MUL || op == OP_MULC || op == OP_FOLD || op == OP_ACC_MULC || op == OP_MUL_T_STORE; }
       return m;
     };
-    // one tier's program; `nested`: look for common factors through nested products too (evalprog.h)
-    auto compile = [&](uint32_t tier, bool nested, ProgBuilder& pb) {
+    // one tier's program; variant 0: direct common factors only, 1: through nested products too, 2: products as sorted chains
+    // of their factors as well (evalprog.h)
+    auto compile = [&](uint32_t tier, int variant, ProgBuilder& pb) {
       pb.scale = 1 << (pk.ext_k - cs.k);
       const uint32_t E = (uint32_t)terms.size();
       auto yp = [&pk](uint32_t d) { return pk.C_YP0 + d; };
       int prev = -1;
       // the gate polynomials of this tier: one DAG (shared sub-expressions once, common factors hoisted; evalprog.h)
-      GateDag dag; dag.advice_slot_of_instance = cs.G; dag.nested = nested;
+      GateDag dag; dag.advice_slot_of_instance = cs.G; dag.nested = variant >= 1; dag.canon_mul = dag.sort_rest = variant >= 2;
       if (use_dag) {
         for (uint32_t e = 0; e < E; ++e)
           if (terms[e].gate && tier_of(std::max(1u, terms[e].degree)) == tier) dag.add(cs.tokens, terms[e].lo, terms[e].hi, e);
@@ -193,12 +194,13 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       return true;
     };
     auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
-      ProgBuilder pb, pb2;
+      ProgBuilder pb;
       ninstr = 0; pk.q_muls[tier] = 0;
-      if (!compile(tier, true, pb)) return;
-      if (use_dag) {                                                         // re-association can lose sharing: keep the cheaper program
-        compile(tier, false, pb2);
-        if (pb.max_depth > EVAL_STACK || (pb2.max_depth <= EVAL_STACK && count_muls(pb2) < count_muls(pb))) pb = pb2;
+      if (!compile(tier, 0, pb)) return;
+      for (int variant = 1; use_dag && variant <= 2; ++variant) {            // re-association can win or lose sharing: keep the cheapest program
+        ProgBuilder alt;
+        compile(tier, variant, alt);
+        if (alt.max_depth <= EVAL_STACK && (pb.max_depth > EVAL_STACK || count_muls(alt) < count_muls(pb))) pb = alt;
       }
       BZ_CHECK(pb.max_depth <= EVAL_STACK, "gate expression too deep for the evaluator stack");
       ninstr = (uint32_t)pb.code.size();

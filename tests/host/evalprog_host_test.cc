@@ -126,7 +126,7 @@ static int file_mode(const char* path) {
     u64 want = 0, naive = 0;
     for (size_t i = 0; i < eidx.size(); ++i) want = addm(want, mulm(eval_tokens(tokens, lo[i], hi[i], naive), val_const[YP0 + (E - 1 - eidx[i])]));
     naive += eidx.size();
-    GateDag dag; dag.advice_slot_of_instance = ibase;
+    GateDag dag; dag.advice_slot_of_instance = ibase; dag.canon_mul = dag.sort_rest = getenv("BZ_NO_CANON") == nullptr;
     for (size_t i = 0; i < eidx.size(); ++i) dag.add(tokens, lo[i], hi[i], eidx[i]);
     dag.plan();
     ProgBuilder pb; int prev = -1;
@@ -143,7 +143,7 @@ static int file_mode(const char* path) {
 
 int main(int argc, char** argv) {
   if (argc > 1) return file_mode(argv[1]);
-  u64 tot_naive = 0, tot[5] = {0, 0, 0, 0, 0};
+  u64 tot_naive = 0, tot[6] = {0, 0, 0, 0, 0, 0};
   int deepest = 0;
   for (int trial = 0; trial < 400; ++trial) {
     pool.clear();
@@ -172,8 +172,8 @@ int main(int argc, char** argv) {
     for (size_t i = 0; i < eidx.size(); ++i) { want = addm(want, mulm(eval_tokens(tokens, lo[i], hi[i], naive), val_const[YP0 + (E - 1 - eidx[i])])); }
     naive += eidx.size();                                      // one fold multiplication per polynomial
     tot_naive += naive;
-    for (int mode = 0; mode < 5; ++mode) {            // mode 4 = cse + hoist + hoisting through nested products
-      GateDag dag; dag.cse = mode == 4 || (mode & 1); dag.hoist = mode == 4 || (mode & 2); dag.nested = mode == 4; dag.advice_slot_of_instance = G;
+    for (int mode = 0; mode < 6; ++mode) {            // mode 4 = cse + hoist + hoisting through nested products, 5 = 4 + products as sorted chains
+      GateDag dag; dag.cse = mode >= 4 || (mode & 1); dag.hoist = mode >= 4 || (mode & 2); dag.nested = mode >= 4; dag.canon_mul = dag.sort_rest = mode == 5; dag.advice_slot_of_instance = G;
       for (size_t i = 0; i < eidx.size(); ++i) dag.add(tokens, lo[i], hi[i], eidx[i]);
       dag.plan();
       ProgBuilder pb;
@@ -188,6 +188,6 @@ int main(int argc, char** argv) {
       tot[mode] += nm;
     }
   }
-  printf("ok naive %llu plain %llu cse %llu hoist %llu both %llu nested %llu deepest %d\n", tot_naive, tot[0], tot[1], tot[2], tot[3], tot[4], deepest);
+  printf("ok naive %llu plain %llu cse %llu hoist %llu both %llu nested %llu canon %llu deepest %d\n", tot_naive, tot[0], tot[1], tot[2], tot[3], tot[4], tot[5], deepest);
   return 0;
 }
