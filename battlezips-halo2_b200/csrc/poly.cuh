@@ -436,10 +436,13 @@ __global__ void grand_product_finish_batch_kernel(const Fe<P>* __restrict__ pnum
     scale_sh = fe_mul(z0, mine);
   }
   __syncthreads();
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint64_t at = (uint64_t)g * prod_stride + (uint64_t)b * nd_stride + i;
-  fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale_sh));
+  // grid-stride over the rows, so that the launch may use ONE CTA per (proof, product) and the Fermat chain above runs B x G
+  // times per batch instead of once per 128 rows (see the launch site in prover.cu)
+  const Fe<P> scale = scale_sh;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint64_t at = (uint64_t)g * prod_stride + (uint64_t)b * nd_stride + i;
+    fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale));
+  }
 }
 
 // ---- Horner evaluation: one CTA per (query, proof) ---------------------------------------------------
