@@ -408,7 +408,7 @@ __global__ void grand_product_finish_kernel(const Fe<P>* __restrict__ pnum, cons
 // The <= 8 inversions a product needs share one Fermat chain (Montgomery's trick, zeros skipped), so a batch pays the
 // inversion latency once instead of once per product.
 struct GpBatchDesc { uint32_t nprod, nsets; PolyRef zref[8]; };
-template <class P>
+template <class P, bool NARROW>
 __global__ void grand_product_finish_batch_kernel(const Fe<P>* __restrict__ pnum, const Fe<P>* __restrict__ sden, uint64_t prod_stride, uint64_t nd_stride,
                                                   Regions reg, GpBatchDesc d, uint32_t n, uint32_t u) {
   __shared__ Fe<P> scale_sh;
@@ -436,12 +436,17 @@ __global__ void grand_product_finish_batch_kernel(const Fe<P>* __restrict__ pnum
     scale_sh = fe_mul(z0, mine);
   }
   __syncthreads();
-  // grid-stride over the rows, so that the launch may use ONE CTA per (proof, product) and the Fermat chain above runs B x G
-  // times per batch instead of once per 128 rows (see the launch site in prover.cu)
-  const Fe<P> scale = scale_sh;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+  if (!NARROW) {                        // validated geometry: one thread per row, the chain above once per 128 rows
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
     const uint64_t at = (uint64_t)g * prod_stride + (uint64_t)b * nd_stride + i;
-    fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale));
+    fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale_sh));
+  } else {                              // ONE CTA per (proof, product) walks all rows: B x G Fermat chains per batch (launch site in prover.cu)
+    const Fe<P> scale = scale_sh;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint64_t at = (uint64_t)g * prod_stride + (uint64_t)b * nd_stride + i;
+      fe_store(region_ptr<P>(reg, d.zref[g], b, n) + i, fe_mul(fe_mul(fe_load(pnum + at), fe_load(sden + at)), scale));
+    }
   }
 }
 

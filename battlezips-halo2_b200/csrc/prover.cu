@@ -1103,11 +1103,11 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         product_scan_kernel<FpP><<<dim3(1, NG * B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
         // BZ_GP_FINISH_NARROW=1: one CTA per (proof, product), i.e. B x NG Fermat chains per batch instead of one per 128 rows (the
         // r1h launch list shows the 3 072 single-lane chains of the wide geometry costing the fma pipe as much as an IPA-round
-        // MSM).  Written after the round's GPU budget was spent: the kernel is grid-stride and the validated wide geometry
+        // MSM).  Written after the round's GPU budget was spent: the validated wide geometry (template argument false: the code that passed)
         // stays the default until the narrow one has run through the parity suite.
         const bool narrow = [] { const char* e = getenv("BZ_GP_FINISH_NARROW"); return e && atoi(e) != 0; }();
-        if (narrow) grand_product_finish_batch_kernel<FpP><<<dim3(1, B, NG), 256, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
-        else grand_product_finish_batch_kernel<FpP><<<dim3((n + 127) / 128, B, NG), 128, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
+        if (narrow) grand_product_finish_batch_kernel<FpP, true><<<dim3(1, B, NG), 256, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
+        else grand_product_finish_batch_kernel<FpP, false><<<dim3((n + 127) / 128, B, NG), 128, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
         C->kernel_launches += NG + 3;
       }
       launch_copy(cd, n);
