@@ -628,10 +628,15 @@ class ProofWorkload:
         H, op, opk = self._oracle
         nproofs = max(1, steps)
         t = time.perf_counter()
+        phases = {}
         for i in range(nproofs):
             T = H.Blake2bTranscript(0)
-            H.create_proof(op, opk, self.instances_d[0], [self.advice[0][g] for g in range(self.advice.shape[1])], H.Draws(self.wide[i % len(self.wide)]), T)
+            trace = {}
+            H.create_proof(op, opk, self.instances_d[0], [self.advice[0][g] for g in range(self.advice.shape[1])], H.Draws(self.wide[i % len(self.wide)]), T, trace=trace)
+            for name, sec in trace.get("phase_s", {}).items():
+                phases[name] = phases.get(name, 0.0) + 1e3 * sec / nproofs
         dt = (time.perf_counter() - t) / nproofs
+        self.cpu_phases_ms = {k: round(v, 2) for k, v in phases.items()}        # the Amdahl picture of the CPU path
         return 1.0 / dt, (f"{nproofs} {self.which} proof(s) with the restated halo2_proofs 0.2.0 prover (oracle/halo2.py over the C restatement, "
                           f"{co.get_threads()} threads)"), co.get_threads(), dt
 
@@ -660,7 +665,19 @@ def run_reference(args, rank):
         v, sample, cores, dt = wl.cpu(args.cpu_sample_log)
         vals.append(v); dts.append(dt)
     v = float(np.mean(vals))
+    extra = {}
+    if isinstance(wl, ProofWorkload):
+        from oracle import c_oracle as co
+        extra["cpu_phases_ms"] = getattr(wl, "cpu_phases_ms", None)
+        nthreads = co.get_threads()
+        co.set_threads(1)                    # the same proof on one host thread (SURVEY 8d asks for both figures)
+        try:
+            v1, _, _, _ = wl.cpu(args.cpu_sample_log)
+            extra["one_thread"] = {"value": v1, "unit": wl.unit, "phases_ms": getattr(wl, "cpu_phases_ms", None)}
+        finally:
+            co.set_threads(nthreads)
     print(json.dumps({
+        **extra,
         "impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
@@ -781,6 +798,8 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
     if want_cpu:
         v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
         cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
+        if getattr(wl, "cpu_phases_ms", None):
+            cpu["phases_ms"] = wl.cpu_phases_ms          # where the CPU prover spends its time, beside kernel_ms of the GPU arm
     return {
         "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None,

@@ -318,6 +318,14 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     rot_scale = 1 << (dom.extended_k - k)
     T = transcript
     tr = trace if trace is not None else {}
+    import time as _time
+    _clock = {"t": _time.perf_counter(), "name": "setup"}
+    tr["phase_s"] = {}
+
+    def _phase(name):          # wall-clock seconds per protocol phase (bench.py --impl reference reports them)
+        now = _time.perf_counter()
+        tr["phase_s"][_clock["name"]] = tr["phase_s"].get(_clock["name"], 0.0) + now - _clock["t"]
+        _clock["t"], _clock["name"] = now, name
 
     def rnd(m):
         return draws.take(f, m)
@@ -329,6 +337,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     # step 0: vk.hash_into
     T.common_scalar(pk.vk_repr)
 
+    _phase("instance + advice commitments")
     # step 1: instance columns
     instance_values, instance_polys, instance_cosets = [], [], []
     for vals in instances:
@@ -369,6 +378,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         src = {"advice": advice_cosets, "fixed": pk.fixed_cosets, "instance": instance_cosets}[kind][col]
         return np.roll(src, -rot * rot_scale, axis=0) if rot else src
 
+    _phase("lookup permute + commitments")
     # steps 4-5: lookups: compress, permute, commit
     lookups = []
     for lk in ir["lookups"]:
@@ -429,6 +439,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     beta = T.squeeze_challenge()
     gamma = T.squeeze_challenge()
 
+    _phase("grand products + commitments")
     # step 7: permutation argument
     chunk_len = ir["degree"] - 2
     perm_cols = ir["permutation"]
@@ -480,6 +491,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         L["product_coset"] = dom.coeff_to_extended(L["product_poly"])
     tr["lookup_z"] = [L["z"] for L in lookups]
 
+    _phase("random polynomial")
     # step 9: vanishing argument: random polynomial
     random_poly = rnd(n)
     random_blind = rnd1()
@@ -489,6 +501,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     # step 10
     y = T.squeeze_challenge()
 
+    _phase("h(X): coset NTTs + evaluation")
     # step 11: h(X) on the extended coset
     one_minus_lb = V.sub(V.const(1, ext_n), V.add(pk.l_last, pk.l_blind))      # 1 - (l_last + l_blind)
     exprs = []
@@ -544,6 +557,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         h = V.add(V.scale(h, y), e)
     tr["num_expressions"] = len(exprs)
 
+    _phase("h(X): inverse NTT + piece commitments")
     # step 12: divide by t(X), back to coefficients, split, commit pieces
     h = dom.divide_by_vanishing_poly(h)
     h_coeffs = dom.extended_to_coeff(h)
@@ -559,6 +573,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     x = T.squeeze_challenge()
     xn = pow(x, n, p)
 
+    _phase("evaluations")
     # step 14: instance / advice / fixed evaluations
     for col, rot in ir["instance_queries"]:
         T.write_scalar(V.eval_polynomial(instance_polys[col], dom.rotate_omega(x, rot)))
@@ -595,6 +610,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         T.write_scalar(V.eval_polynomial(L["permuted_input_poly"], x_prev))
         T.write_scalar(V.eval_polynomial(L["permuted_table_poly"], x))
 
+    _phase("multiopen")
     # step 19: query list  (id, point, (poly, blind))
     Q = []
     for col, rot in ir["instance_queries"]:
@@ -651,8 +667,10 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     tr["p_poly"] = p_poly
     tr["point_sets"] = point_sets
 
+    _phase("inner product argument")
     # step 21: inner product argument
     ipa_create_proof(params, draws, T, p_poly, p_blind, x3, tr)
+    _phase("done")
 
 
 def ipa_create_proof(params, draws, T, p_poly, p_blind, x3, tr=None):
