@@ -211,6 +211,23 @@ def test_grand_products_batched_and_sequential_agree(ctx, monkeypatch):
     pk.close(); params.close()
 
 
+@pytest.mark.skipif(__import__("os").environ.get("BZ_VALIDATE_PENDING") != "1",
+                    reason="pending validation: the one-CTA-per-product finish geometry was written after round 1's GPU budget was spent")
+def test_grand_product_finish_narrow_geometry(ctx, monkeypatch):
+    """BZ_GP_FINISH_NARROW=1 (one CTA per (proof, product) walks all rows) writes the same proofs as the default geometry."""
+    from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
+    for make in (shot_circuit, board_circuit):
+        cs, cfg, asg = make(2)
+        job = Job(cs, asg)
+        params, pk = job.device_keys(ctx, window_bits=10)
+        a = _prove(job, pk, [0, 5])
+        monkeypatch.setenv("BZ_GP_FINISH_NARROW", "1")
+        b = _prove(job, pk, [0, 5])
+        monkeypatch.delenv("BZ_GP_FINISH_NARROW")
+        assert a == b
+        pk.close(); params.close()
+
+
 @pytest.mark.parametrize("which", ["shot", "board"])
 def test_quotient_dag_and_tree_programs_agree(ctx, which, monkeypatch):
     """h(X) compiled as one DAG per tier (shared sub-expressions, hoisted factors: csrc/evalprog.h) and as the
