@@ -55,7 +55,8 @@ def parse():
 # 71 IMAD.WIDE.U32(.X) at HALF rate (measured: bz_imad_wide_peak = 0.455 x bz_imad_peak) = 142, plus 25 IMAD.HI + 11 IMAD +
 # 18 IMAD.X at full rate = 54  ->  196  (cuobjdump -sass of fe_mul_raw)
 FMA_PER_MUL = 196
-NCU_DRAM_BYTES_PER_ADD = 129.8      # profiles/r1d_ncu_full_summary.csv, fb_accumulate_kernel
+NCU_DRAM_BYTES_PER_ADD = 136.6      # profiles/r1h_ncu_full_summary.csv, fb_accumulate_kernel at c = 16: (278.3 + 8.5) MB per IPA-round launch of
+                                    # 128 MSMs x 1 026 scalars x 16 windows = 2.10 M mixed additions (r1d, c = 14: 129.8)
 
 
 def set_sync_policy(args, local_rank):
