@@ -60,7 +60,7 @@ def batch_invert_assigned(ctx, field, numerators, denominators):
     return out
 
 
-_FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "from_u512": 4, "from_mont": 5, "to_mont": 6, "neg": 7, "sqr": 8}
+_FIELD_OPS = {"mul": 0, "add": 1, "sub": 2, "inv": 3, "from_u512": 4, "from_mont": 5, "to_mont": 6, "neg": 7, "sqr": 8, "inv_gcd": 9}
 
 
 def field_op(ctx, field, op, a, b=None):

@@ -258,7 +258,7 @@ __attribute__((visibility("default"))) int bz_imad_peak(bz_ctx* ctx, double* ima
 __attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n) {
   BZ_TRY(ctx, {
     BZ_CHECK(field == 0 || field == 1, "bad field id");
-    BZ_CHECK(op >= 0 && op <= 8, "bad op");
+    BZ_CHECK(op >= 0 && op <= 9, "bad op");
     size_t in_sz = op == 4 ? 64 : 32;
     bz::DevBuf da, db, dout;
     da.alloc(n * in_sz + 32); db.alloc(n * 32 + 32); dout.alloc(n * 32 + 32);

@@ -26,6 +26,7 @@ __global__ void field_op_kernel(int op, const uint32_t* __restrict__ a, const ui
       case 5: r = fe_from_mont(x); break;
       case 6: r = fe_to_mont(x); break;
       case 7: r = fe_neg(x); break;
+      case 9: r = fe_inv_gcd(x); break;
       default: r = fe_sqr(x); break;
     }
   }

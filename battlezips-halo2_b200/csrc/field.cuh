@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 #include "montmul.cuh"
+#include "gcdinv.h"
 
 namespace bz {
 
@@ -228,6 +229,20 @@ template <class P> __device__ __noinline__ Fe<P> fe_inv(const Fe<P>& a) {
   e[0] = 0xffffffffu;   // m - 2: limb0 is 1 -> borrow through: (m1..): 1 - 2 = -1 mod 2^32 with borrow from limb 1
   e[1] = P::M1 - 1u;
   return fe_pow<P>(a, e);
+}
+
+// Inversion by the binary GCD of gcdinv.h (0 -> 0):  (aR)^-1 = a^-1 R^-1, and two Montgomery multiplications by R^2 give a^-1 R.
+// ALU-pipe work instead of a Fermat chain on the fma pipe; reachable through bz_field_op op 9 only until it has been through
+// the GPU parity suite (written after round 1's GPU budget was spent; tests/test_gcdinv_host.py checks the core on the CPU).
+template <class P> __device__ __noinline__ Fe<P> fe_inv_gcd(const Fe<P>& a) {
+  uint32_t p[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = mod_limb<P>(i);
+  gcdinv::inverse(r, a.l, p);
+  Fe<P> x;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x.l[i] = r[i];
+  return fe_to_mont<P>(fe_to_mont<P>(x));
 }
 
 // 256-bit vector load/store of one element (sm_100a has 256-bit global accesses; two 128-bit halves

@@ -77,7 +77,7 @@ int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes);
 /* ---- ff::Field / group ops on host slices (pasta_curves semantics; used by the parity suite and by the
  * shim for the few scalar-sized steps it does not want to do on the CPU) ------------------------------ */
 /* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 over the slice (ff::BatchInvert: Montgomery trick, 0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
- *     6 canonical -> Montgomery, 7 -a, 8 a^2 */
+ *     6 canonical -> Montgomery, 7 -a, 8 a^2, 9 a^-1 element-wise by binary GCD (gcdinv.h; pending GPU validation) */
 int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
 /* poly::batch_invert_assigned (U: halo2_proofs 0.2.0 src/poly.rs `batch_invert_assigned`, called by create_proof on the
  * advice columns a circuit assigned as Assigned<F>; reference call path R:src/circuits/shot.rs:921 -> create_proof):

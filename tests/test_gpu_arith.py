@@ -43,6 +43,19 @@ def test_field_ops(field, ctx, oracle_c):
     assert np.array_equal(ar.field_op(ctx, field, "from_u512", wide), co.from_u512(field, wide))
 
 
+@pytest.mark.skipif(__import__("os").environ.get("BZ_VALIDATE_PENDING") != "1",
+                    reason="pending validation: fe_inv_gcd was written after round 1's GPU budget was spent (CPU-checked only)")
+@pytest.mark.parametrize("field", [0, 1])
+def test_binary_gcd_inverse_on_device(field, ctx, oracle_c):
+    co = oracle_c
+    F = co.FIELDS[field]
+    rnd = random.Random(55 + field)
+    a = _edge_and_random(F, rnd, 700) + [1 << 32, 1 << 64, (1 << 254) % F.p]
+    am = co.to_mont(field, a)
+    assert co.from_mont(field, ar.field_op(ctx, field, "inv_gcd", am)) == [F.inv(x) for x in a]
+    assert np.array_equal(ar.field_op(ctx, field, "inv_gcd", am), ar.field_op(ctx, field, "inv", am))
+
+
 @pytest.mark.parametrize("field", [0, 1])
 def test_batch_invert_assigned(field, ctx, oracle_c):
     """SURVEY 8 f3: Assigned<F> columns (numerator / denominator) -> F, against the restated poly::batch_invert_assigned
