@@ -1,7 +1,7 @@
 # Round 2, first GPU call: validate what round 1 wrote after its GPU budget was spent, then A/B it.
 #   gpurun --timeout 900 -- 'bash scripts/validate_pending.sh'
 set -o pipefail
-BZ_VALIDATE_PENDING=1 python -m pytest tests/test_gpu_prover.py -x -q -k narrow_geometry 2>&1 | tail -3
+BZ_VALIDATE_PENDING=1 python -m pytest tests/test_gpu_prover.py tests/test_gpu_arith.py -x -q -k "narrow_geometry or binary_gcd" 2>&1 | tail -3
 for nm in 0 1; do
   BZ_GP_FINISH_NARROW=$nm python bench.py --no-extras > gpurun_out/pending_narrow$nm.log 2>&1
 done
