@@ -22,6 +22,24 @@ sys.path.insert(0, ROOT)
 import numpy as np
 
 
+def box_gpus(args):
+    """GPUs this process can see on the box (no CUDA context is created): torch's device count, else CUDA_VISIBLE_DEVICES /
+    /dev/nvidia<N>, else the launch size."""
+    try:
+        import torch
+        n = torch.cuda.device_count()
+        if n > 0:
+            return n
+    except Exception:      # noqa: BLE001
+        pass
+    import glob
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis is not None and vis.strip():
+        return max(1, len([v for v in vis.split(",") if v.strip()]))
+    n = len(glob.glob("/dev/nvidia[0-9]*"))
+    return max(1, n or int(os.environ.get("LOCAL_WORLD_SIZE", args.gpus)))
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -46,7 +64,9 @@ def parse():
             cores = len(os.sched_getaffinity(0))
         except AttributeError:
             cores = os.cpu_count() or 4
-        args.inflight = max(2, min(6, cores // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", args.gpus)))))
+        # the share of the box's cores one GPU gets -- from the GPUs the BOX has, not from --gpus, so that every N of a
+        # scaling run on one box uses the same lanes x batch per GPU (weak scaling: per-GPU work fixed)
+        args.inflight = max(2, min(6, cores // box_gpus(args)))
     return args
 
 
