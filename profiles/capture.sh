@@ -3,6 +3,8 @@
 #   bash profiles/capture.sh <tag>      -> gpurun_out/<tag>_*.{csv,ncu-rep,log}
 # Every ncu pass runs only after the same command has exited 0 without ncu.
 set -u
+# NOTE: consider `export BZ_FIXED_WINDOW=14` for the --set full passes: ncu saves / restores all allocated device memory between
+# replay passes, and the default c = 16 tables are 138 GB (r1h took 21 minutes instead of 7).
 TAG=${1:-r1}
 OUT=gpurun_out
 CMD="python bench.py --no-extras --batch 64 --inflight 1 --steps 2 --warmup 3"
