@@ -26,11 +26,18 @@ __global__ void field_op_kernel(int op, const uint32_t* __restrict__ a, const ui
       case 5: r = fe_from_mont(x); break;
       case 6: r = fe_to_mont(x); break;
       case 7: r = fe_neg(x); break;
-      case 9: r = fe_inv_gcd(x); break;
       default: r = fe_sqr(x); break;
     }
   }
   fe_store(out + i, r);
+}
+
+// op 9: element-wise inversion by binary GCD (gcdinv.h) -- its own kernel, so that field_op_kernel stays the validated code
+template <class P>
+__global__ void field_inv_gcd_kernel(const Fe<P>* __restrict__ a, Fe<P>* __restrict__ out, uint64_t n) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  fe_store(out + i, fe_inv_gcd(fe_load(a + i)));
 }
 
 // ff::BatchInvert: Montgomery's trick over RUN consecutive elements per thread, zeros skipped (0 -> 0);
@@ -137,6 +144,13 @@ void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, voi
     return;
   }
   unsigned blocks = (unsigned)((n + 127) / 128);
+  if (op == 9) {
+    if (field == 0) field_inv_gcd_kernel<FpP><<<blocks, 128, 0, ctx->stream>>>((const Fe<FpP>*)a, (Fe<FpP>*)out, n);
+    else field_inv_gcd_kernel<FqP><<<blocks, 128, 0, ctx->stream>>>((const Fe<FqP>*)a, (Fe<FqP>*)out, n);
+    ctx->kernel_launches++;
+    BZ_CUDA(cudaGetLastError());
+    return;
+  }
   if (field == 0) field_op_kernel<FpP><<<blocks, 128, 0, ctx->stream>>>(op, (const uint32_t*)a, (const uint32_t*)b, (Fe<FpP>*)out, n);
   else field_op_kernel<FqP><<<blocks, 128, 0, ctx->stream>>>(op, (const uint32_t*)a, (const uint32_t*)b, (Fe<FqP>*)out, n);
   ctx->kernel_launches++;
