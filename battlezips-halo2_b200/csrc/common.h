@@ -34,6 +34,19 @@ struct Error : std::runtime_error {
     if (!(cond)) throw ::bz::Error(-1, std::string(msg));    \
   } while (0)
 
+// cudaFuncSetAttribute and occupancy queries act on the CURRENT device's copy of a kernel: a process that opens contexts on
+// several GPUs (bz_ctx_create(device, ...)) must repeat them per device.  One instance per call site; `fn` runs once per device.
+constexpr int BZ_MAX_DEVICES = 64;
+struct PerDeviceOnce {
+  std::mutex m;
+  uint64_t done = 0;
+  template <class F> void run(int device, F&& fn) {
+    std::lock_guard<std::mutex> g(m);
+    if (device < 0 || device >= BZ_MAX_DEVICES) { fn(); return; }
+    if (!((done >> device) & 1)) { fn(); done |= 1ull << device; }
+  }
+};
+
 // device buffer owned by a context (freed with it)
 struct DevBuf {
   void* p = nullptr;

@@ -445,9 +445,11 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
   cudaStream_t st = ctx->stream;
   if (!ctx->counters.p) { ctx->counters.alloc(64); BZ_CUDA(cudaMemsetAsync(ctx->counters.p, 0, 64, st)); }
   const uint32_t list_stride = fb.npts * fb.W;                          // worst case: every digit non-zero
-  static int ctas_per_sm = 0, ctas_per_sm_pairs = 0;          // per template instantiation; several prover lanes (host threads) may race to set it
-  static std::once_flag once;
-  std::call_once(once, [] {
+  static int ctas_dev[BZ_MAX_DEVICES], ctas_pairs_dev[BZ_MAX_DEVICES];   // per template instantiation and device; several prover lanes (host threads) may race to set them
+  static PerDeviceOnce once;
+  const int dev = ctx->device >= 0 && ctx->device < BZ_MAX_DEVICES ? ctx->device : 0;
+  once.run(ctx->device, [dev] {
+    int ctas_per_sm = 0, ctas_per_sm_pairs = 0;
     cudaFuncSetAttribute(fb_accumulate_pairs_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FB_MAX_MSM + 1) * 4));
     cudaFuncSetAttribute(fb_pair_prefix_kernel<BP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((FB_MAX_MSM + 1) * 4));
     int vp = 0;
@@ -462,7 +464,11 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
     cudaFuncSetAttribute(fb_fold_kernel<BP, false, FB_FOLD_THREADS_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
     cudaFuncSetAttribute(fb_fold_kernel<BP, true, FB_FOLD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
     cudaFuncSetAttribute(fb_fold_kernel<BP, false, FB_FOLD_THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize, fold_smem);
+    // BZ_FB_CTAS_PER_SM: fewer resident CTAs of the accumulate wave than fit (A/B: leaves registers for the other prover lanes' kernels)
+    if (const char* e = getenv("BZ_FB_CTAS_PER_SM")) { const int v2 = atoi(e); if (v2 >= 1 && v2 < ctas_per_sm) ctas_per_sm = v2; }
+    ctas_dev[dev] = ctas_per_sm; ctas_pairs_dev[dev] = ctas_per_sm_pairs;
   });
+  const int ctas_per_sm = ctas_dev[dev], ctas_per_sm_pairs = ctas_pairs_dev[dev];
   // pair mode needs 32 B of prefix storage per table point: only for launches whose worst case stays under 1 GB
   const bool pairs = ctx->fb_pairs && (uint64_t)std::min<uint32_t>(n_msm, FB_MAX_MSM) * list_stride <= (1ull << 25);
   const uint32_t acc_ctas = (uint32_t)ctx->sm_count * (uint32_t)(pairs ? ctas_per_sm_pairs : ctas_per_sm), acc_threads = acc_ctas * FB_THREADS;

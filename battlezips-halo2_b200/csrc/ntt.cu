@@ -187,8 +187,8 @@ template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t
     while ((a.k_limit << a.zero_stages) < (1u << a.logL)) ++a.zero_stages;
   size_t smem = (size_t)tile * 32;
   int threads = tile >= 4096 ? 512 : (tile >= 512 ? 256 : (tile >= 64 ? (int)tile / 2 : 32));
-  static std::once_flag once[2];
-  std::call_once(once[P::ID], [] { cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
+  static PerDeviceOnce once;            // per template instantiation
+  once.run(ctx->device, [] { cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
   dim3 grid((unsigned)(nlines >> a.logT), (unsigned)batch, (unsigned)batch2);
   ProfScope prof(ctx, PROF_NTT_PASS);
   ntt_pass_kernel<P><<<grid, threads, smem, ctx->stream>>>(a);

@@ -974,8 +974,8 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, 4, cudaMemcpyDeviceToHost, st));
     } else if (device_permute) {
       // device: sort / permute (U: lookup/prover.rs::permute_expression_pair), one CTA per (lookup, proof)
-      static std::once_flag once;
-      std::call_once(once, [] { cudaFuncSetAttribute(lookup_permute_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lookup_permute_smem(LKP_MAX_N)); });
+      static PerDeviceOnce once;
+      once.run(C->device, [] { cudaFuncSetAttribute(lookup_permute_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lookup_permute_smem(LKP_MAX_N)); });
       std::vector<LookupPermDesc> pd;
       for (uint32_t l = 0; l < L; ++l)
         pd.push_back(LookupPermDesc{PolyRef{R_MISC, pk.m_cin0 + 2 * l}, PolyRef{R_MISC, pk.m_cin0 + 2 * l + 1}, PolyRef{R_VAL, pk.slot_lk(l, 0)}, PolyRef{R_VAL, pk.slot_lk(l, 1)}});
@@ -1191,8 +1191,8 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     a.pbase = (const DFe*)w.coset.p; a.pstride = (uint64_t)pk.NS * en; a.sbase = (const DFe*)pk.shcoset.p;
     a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
     a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
-    static std::once_flag once;
-    std::call_once(once, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+    static PerDeviceOnce once;
+    once.run(C->device, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
     {
       ProfScope prof(C, PROF_QUOTIENT);
       eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr[0] * 4, st>>>(a);

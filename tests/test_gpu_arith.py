@@ -43,8 +43,6 @@ def test_field_ops(field, ctx, oracle_c):
     assert np.array_equal(ar.field_op(ctx, field, "from_u512", wide), co.from_u512(field, wide))
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BZ_VALIDATE_PENDING") != "1",
-                    reason="pending validation: fe_inv_gcd was written after round 1's GPU budget was spent (CPU-checked only)")
 @pytest.mark.parametrize("field", [0, 1])
 def test_binary_gcd_inverse_on_device(field, ctx, oracle_c):
     co = oracle_c

@@ -211,8 +211,6 @@ def test_grand_products_batched_and_sequential_agree(ctx, monkeypatch):
     pk.close(); params.close()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("BZ_VALIDATE_PENDING") != "1",
-                    reason="pending validation: the one-CTA-per-product finish geometry was written after round 1's GPU budget was spent")
 def test_grand_product_finish_narrow_geometry(ctx, monkeypatch):
     """BZ_GP_FINISH_NARROW=1 (one CTA per (proof, product) walks all rows) writes the same proofs as the default geometry."""
     from battlezips_halo2_b200.circuits import shot_circuit, board_circuit

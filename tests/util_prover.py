@@ -42,16 +42,42 @@ def tiny_circuit(k=5):
     return cs, asg
 
 
+def device_urs_checked(ctx, k):
+    """Large k: the oracle's Python Params::new would take minutes, so both sides use the URS that Params::new on the
+    device returns (bit-exact against the oracle fixtures for k <= 13, tests/test_gpu_params.py) after re-checking it
+    here with oracle arithmetic: sampled g[i] against the oracle hash-to-curve, w and u, and the two Lagrange-basis
+    identities  sum_i g_lagrange[i] = g[0]  and  sum_i omega^i g_lagrange[i] = g[1]  (1 and X in the Lagrange basis)."""
+    from battlezips_halo2_b200 import arithmetic as ar
+    urs = ar.params_new(ctx, k, curve=0)
+    n = 1 << k
+    C = co.CURVES[0][0]
+    h = C.hash_to_curve("Halo2-Parameters")
+    for i in (0, 1, n // 3, n - 1):
+        assert co.points_from_mont(0, urs["g"][i][None, :])[0] == h(b"\x00" + i.to_bytes(4, "little"))
+    assert co.points_from_mont(0, urs["w"][None, :])[0] == h(b"\x01") and co.points_from_mont(0, urs["u"][None, :])[0] == h(b"\x02")
+    F = co.FIELDS[0]
+    om = pow(F.root_of_unity, 1 << (32 - k), F.p)
+    ones = np.repeat(co.to_mont(0, [1]), n, axis=0)
+    pw = [1] * n
+    for i in range(1, n):
+        pw[i] = pw[i - 1] * om % F.p
+    assert np.array_equal(co.to_affine(0, co.best_multiexp(0, ones, urs["g_lagrange"]))[0], urs["g"][0])
+    assert np.array_equal(co.to_affine(0, co.best_multiexp(0, co.to_mont(0, pw), urs["g_lagrange"]))[0], urs["g"][1])
+    return H.Params(k, 0, urs["g"], urs["g_lagrange"], urs["w"], urs["u"])
+
+
 class Job:
     """Everything both sides need for one circuit: IR, oracle pk, witness arrays, RNG words."""
 
-    def __init__(self, cs, asg, seed=0xB200B200B200B200):
+    def __init__(self, cs, asg, seed=0xB200B200B200B200, params_from_device=None):
         self.cs, self.asg, self.k = cs, asg, asg.k
         self.ir = cs.to_ir()
         fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"params_vesta_k{self.k}.npz")
         if os.path.exists(fixture):          # URS fixtures made by tests/golden/make_params.py (oracle Params::new)
             d = np.load(fixture)
             self.oparams = H.Params(self.k, 0, d["g"], d["g_lagrange"], d["w"], d["u"])
+        elif params_from_device is not None:
+            self.oparams = device_urs_checked(params_from_device, self.k)
         else:
             self.oparams = H.Params.new(self.k, 0)
         self.mapping = asg.permutation_mapping()
