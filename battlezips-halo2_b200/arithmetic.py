@@ -142,3 +142,78 @@ def params_read(ctx, data, curve=0):
     if (st == 2).any():
         raise ValueError("Params::read: invalid point encoding")
     return k, {"g": pts[:n].copy(), "g_lagrange": pts[n:2 * n].copy(), "w": pts[2 * n].copy(), "u": pts[2 * n + 1].copy()}
+
+
+# ---- fine-grained prover arithmetic (include/bzhalo2.h "Fine-grained prover arithmetic") -------------------
+def _ptr_array(arrs):
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64) for a in arrs]
+    ptrs = (ctypes.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    return arrs, ptrs
+
+
+def _scalar(x):
+    return np.ascontiguousarray(x, dtype=np.uint64).reshape(4)
+
+
+def eval_polynomials(ctx, field, polys, points):
+    """arithmetic::eval_polynomial for many (poly, point) pairs: polys = list of (n,4) arrays, points = (count,4)."""
+    keep, ptrs = _ptr_array(polys)
+    points = np.ascontiguousarray(points, dtype=np.uint64).reshape(-1, 4)
+    assert len(points) == len(keep)
+    out = np.zeros((len(keep), 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_eval_many(ctx.h, field, len(keep[0]) if keep else 0, len(keep), ptrs, _np_ptr(points), _np_ptr(out)))
+    return out
+
+
+def kate_division(ctx, field, a, point):
+    """arithmetic::kate_division(a, b) -> n - 1 coefficients."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4)
+    out = np.zeros((len(a) - 1, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_kate_div(ctx.h, field, len(a), _np_ptr(a), _np_ptr(_scalar(point)), _np_ptr(out)))
+    return out
+
+
+def axpy(ctx, field, acc, x, poly):
+    """acc * x + poly (returned; multiopen's accumulation step)."""
+    acc = np.ascontiguousarray(acc, dtype=np.uint64).reshape(-1, 4).copy()
+    poly = np.ascontiguousarray(poly, dtype=np.uint64).reshape(-1, 4)
+    assert len(acc) == len(poly)
+    ctx._check(ctx.lib.bz_axpy(ctx.h, field, len(acc), _np_ptr(acc), _np_ptr(_scalar(x)), _np_ptr(poly)))
+    return acc
+
+
+def divide_by_vanishing_poly(ctx, field, a, k, extended_k):
+    """EvaluationDomain::divide_by_vanishing_poly on 2^extended_k extended-Lagrange values (returned)."""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4).copy()
+    assert len(a) == 1 << extended_k
+    ctx._check(ctx.lib.bz_divide_by_vanishing(ctx.h, field, k, extended_k, _np_ptr(a)))
+    return a
+
+
+def permutation_product(ctx, field, k, values, sigmas, beta, gamma, delta_omega0, z0):
+    """permutation::Argument::commit for one column set -> z (n,4) before blinding."""
+    vk, vp = _ptr_array(values)
+    sk, sp = _ptr_array(sigmas)
+    out = np.zeros((1 << k, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_perm_product(ctx.h, field, k, len(vk), vp, sp, _np_ptr(_scalar(beta)), _np_ptr(_scalar(gamma)),
+                                       _np_ptr(_scalar(delta_omega0)), _np_ptr(_scalar(z0)), _np_ptr(out)))
+    return out
+
+
+def lookup_permute(ctx, field, k, usable_rows, compressed_input, compressed_table):
+    """lookup::permute_expression_pair -> (permuted_input, permuted_table), rows >= usable_rows zero."""
+    ci = np.ascontiguousarray(compressed_input, dtype=np.uint64).reshape(-1, 4)
+    ct = np.ascontiguousarray(compressed_table, dtype=np.uint64).reshape(-1, 4)
+    assert len(ci) == len(ct) == 1 << k
+    a, s = np.zeros_like(ci), np.zeros_like(ci)
+    ctx._check(ctx.lib.bz_lookup_permute(ctx.h, field, k, usable_rows, _np_ptr(ci), _np_ptr(ct), _np_ptr(a), _np_ptr(s)))
+    return a, s
+
+
+def lookup_product(ctx, field, k, compressed_input, compressed_table, permuted_input, permuted_table, beta, gamma):
+    """lookup::Permuted::commit_product -> z (n,4) before blinding."""
+    arrs = [np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, 4) for a in (compressed_input, compressed_table, permuted_input, permuted_table)]
+    assert all(len(a) == 1 << k for a in arrs)
+    out = np.zeros((1 << k, 4), dtype=np.uint64)
+    ctx._check(ctx.lib.bz_lookup_product(ctx.h, field, k, *[_np_ptr(a) for a in arrs], _np_ptr(_scalar(beta)), _np_ptr(_scalar(gamma)), _np_ptr(out)))
+    return out

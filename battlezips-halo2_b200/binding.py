@@ -89,6 +89,20 @@ def load_library():
         "bz_hash_to_curve": (i32, [vp, i32, ctypes.c_char_p, vp, u32, u64, vp]),
         "bz_batch_invert_assigned": (i32, [vp, i32, vp, vp, vp, u64]),
         "bz_batch_invert_assigned_dev": (i32, [vp, i32, vp, vp, vp, u64]),
+        "bz_perm_product": (i32, [vp, i32, u32, u32, ctypes.POINTER(vp), ctypes.POINTER(vp), vp, vp, vp, vp, vp]),
+        "bz_lookup_permute": (i32, [vp, i32, u32, u32, vp, vp, vp, vp]),
+        "bz_lookup_product": (i32, [vp, i32, u32, vp, vp, vp, vp, vp, vp, vp]),
+        "bz_divide_by_vanishing": (i32, [vp, i32, u32, u32, vp]),
+        "bz_pk_quotient": (i32, [vp, vp, vp, vp, vp, vp, vp, vp]),
+        "bz_pk_num_poly_slots": (u32, [vp]),
+        "bz_eval_many": (i32, [vp, i32, u64, u32, ctypes.POINTER(vp), vp, vp]),
+        "bz_kate_div": (i32, [vp, i32, u64, vp, vp, vp]),
+        "bz_axpy": (i32, [vp, i32, u64, vp, vp, vp]),
+        "bz_ipa_begin": (i32, [vp, vp, vp, vp, ctypes.POINTER(vp)]),
+        "bz_ipa_round": (i32, [vp, vp, vp, vp, vp, vp, vp]),
+        "bz_ipa_fold": (i32, [vp, vp, vp, vp]),
+        "bz_ipa_finish": (i32, [vp, vp, vp]),
+        "bz_ipa_destroy": (None, [vp]),
     }
     declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",
                           "bz_pk_num_random", "bz_pk_proof_size", "bz_pk_quotient_muls", "bz_create_proofs", "bz_pk_create_from_assembly", "bz_pk_vk_commitments", "bz_verify_proofs", "bz_params_commit_batch_dev"}     # bound in plonk/prover.py

@@ -16,6 +16,7 @@ Ctx::~Ctx() {}
 
 
 #define BZ_TRY(ctx_, ...)                                    \
+  if (!(ctx_)) return BZ_ERR_INVALID;                        \
   try {                                                      \
     cudaSetDevice((ctx_)->c.device);                         \
     __VA_ARGS__;                                             \
@@ -41,10 +42,19 @@ __attribute__((visibility("default"))) int bz_ctx_create(int device, void* strea
   bz_ctx* h = new (std::nothrow) bz_ctx();
   if (!h) return BZ_ERR_INVALID;
   h->c.device = device;
+  int prio_lo = 0, prio_hi = 0;          // numerically lowest = highest priority
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char* se = getenv("BZ_SPLIT_STREAMS");
+  const bool split = se && atoi(se) != 0;
   if (stream) h->c.stream = (cudaStream_t)stream;
   else {
-    if (cudaStreamCreateWithFlags(&h->c.stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return BZ_ERR_CUDA; }
+    if (cudaStreamCreateWithPriority(&h->c.stream, cudaStreamNonBlocking, split ? prio_hi : prio_lo) != cudaSuccess) { delete h; return BZ_ERR_CUDA; }
     h->own_stream = true;
+  }
+  if (split) {
+    if (cudaStreamCreateWithPriority(&h->c.big, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->c.ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->c.ev_join, cudaEventDisableTiming) != cudaSuccess) { delete h; return BZ_ERR_CUDA; }
   }
   cudaDeviceGetAttribute(&h->c.sm_count, cudaDevAttrMultiProcessorCount, device);
   { const char* pe = getenv("BZ_FB_PAIRS"); h->c.fb_pairs = pe && atoi(pe) != 0; }
@@ -57,6 +67,7 @@ __attribute__((visibility("default"))) void bz_ctx_destroy(bz_ctx* ctx) {
   cudaSetDevice(ctx->c.device);
   cudaStreamSynchronize(ctx->c.stream);
   for (void* p : ctx->allocs) cudaFree(p);
+  if (ctx->c.big) { cudaStreamSynchronize(ctx->c.big); cudaStreamDestroy(ctx->c.big); cudaEventDestroy(ctx->c.ev_fork); cudaEventDestroy(ctx->c.ev_join); }
   if (ctx->own_stream) cudaStreamDestroy(ctx->c.stream);
   delete ctx;
 }
@@ -259,6 +270,10 @@ __attribute__((visibility("default"))) int bz_field_op(bz_ctx* ctx, int field, i
   BZ_TRY(ctx, {
     BZ_CHECK(field == 0 || field == 1, "bad field id");
     BZ_CHECK(op >= 0 && op <= 9, "bad op");
+    if (!n) return BZ_OK;
+    BZ_CHECK(a && out, "null argument");
+    BZ_CHECK(op > 2 || b, "binary field op without a second operand");
+    BZ_CHECK(n <= (1ull << 32), "field op: slice too long");
     size_t in_sz = op == 4 ? 64 : 32;
     bz::DevBuf da, db, dout;
     da.alloc(n * in_sz + 32); db.alloc(n * 32 + 32); dout.alloc(n * 32 + 32);
@@ -340,6 +355,8 @@ __attribute__((visibility("default"))) int bz_point_sum_dev(bz_ctx* ctx, int cur
 __attribute__((visibility("default"))) int bz_batch_normalize_dev(bz_ctx* ctx, int curve, const void* d_jac, void* d_affine, uint64_t n) {
   BZ_TRY(ctx, {
     BZ_CHECK(curve == 0 || curve == 1, "bad curve id");
+    BZ_CHECK(n < (1ull << 32), "batch_normalize: too many points");
+    BZ_CHECK(n == 0 || (d_jac && d_affine), "null argument");
     bz::jac_to_affine_run(&ctx->c, curve, d_jac, d_affine, (uint32_t)n);
   });
 }

@@ -97,8 +97,33 @@ struct Ctx {
   double prof_ms[PROF_NTAGS] = {0};
   uint64_t prof_count[PROF_NTAGS] = {0};
 
+  // Throughput kernels (table-MSM accumulation, h(X), NTT passes) go to a second, LOWEST-priority stream so that the
+  // latency-bound kernels of the other prover lanes (folds, scans, Horner evaluations: a few CTAs each) are dispatched ahead
+  // of a big kernel's pending CTAs instead of queueing behind its last wave (BigKernelScope below; null = one stream).
+  cudaStream_t big = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
   const bzh::Field& field(int f) const { return f == 0 ? fp : fq; }
   ~Ctx();
+};
+
+// Launch the kernels issued inside the scope on ctx->big, ordered after everything already on ctx->stream and before
+// everything issued to it afterwards (two event edges; no host synchronisation).
+struct BigKernelScope {
+  Ctx* c; cudaStream_t s;
+  explicit BigKernelScope(Ctx* ctx) : c(ctx), s(ctx->stream) {
+    if (!c->big) return;
+    cudaEventRecord(c->ev_fork, c->stream);
+    cudaStreamWaitEvent(c->big, c->ev_fork, 0);
+    s = c->big;
+  }
+  ~BigKernelScope() {
+    if (!c->big) return;
+    cudaEventRecord(c->ev_join, c->big);
+    cudaStreamWaitEvent(c->stream, c->ev_join, 0);
+  }
+  BigKernelScope(const BigKernelScope&) = delete;
+  BigKernelScope& operator=(const BigKernelScope&) = delete;
 };
 
 // NVTX range (header-only nvtx3; a no-op unless a profiler is attached): prover phases and kernel classes show up by name

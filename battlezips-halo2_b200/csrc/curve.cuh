@@ -120,7 +120,7 @@ template <class BP> __device__ __forceinline__ Xyzz<BP> jac_to_xyzz(const Jac<BP
 template <class BP> __device__ __forceinline__ Affine<BP> xyzz_to_affine(const Xyzz<BP>& a) {
   Affine<BP> r;
   if (xyzz_is_identity(a)) { r.x = fe_zero<BP>(); r.y = fe_zero<BP>(); return r; }
-  Fe<BP> zi = fe_inv(a.zzz);                 // 1/z^3
+  Fe<BP> zi = fe_inv_gcd(a.zzz);             // 1/z^3 (binary GCD: the callers run this on one lane per point)
   Fe<BP> zi2 = fe_mul(fe_sqr(zi), a.zz);     // z^-6 * z^2 ... = z^-4? no: see below
   // zz = z^2, zzz = z^3: 1/zz = zzz^-2 * zz^2 = z^-6 * z^4 = z^-2
   zi2 = fe_mul(zi2, a.zz);

@@ -232,8 +232,7 @@ template <class P> __device__ __noinline__ Fe<P> fe_inv(const Fe<P>& a) {
 }
 
 // Inversion by the binary GCD of gcdinv.h (0 -> 0):  (aR)^-1 = a^-1 R^-1, and two Montgomery multiplications by R^2 give a^-1 R.
-// ALU-pipe work instead of a Fermat chain on the fma pipe; reachable through bz_field_op op 9 only until it has been through
-// the GPU parity suite (written after round 1's GPU budget was spent; tests/test_gcdinv_host.py checks the core on the CPU).
+// ALU-pipe work instead of a Fermat chain on the fma pipe (data-dependent loops: meant for single-lane, latency-bound call sites).
 template <class P> __device__ __noinline__ Fe<P> fe_inv_gcd(const Fe<P>& a) {
   uint32_t p[8], r[8];
 #pragma unroll

@@ -498,8 +498,10 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
         field_op_run(ctx, BP::ID, 3, totals, nullptr, inv_totals, acc_threads);
         fb_accumulate_pairs_kernel<BP><<<acc_ctas, FB_THREADS, smem, st>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, pre, inv_totals, partial, cnt);
         ctx->kernel_launches += 1;
-      } else
-        fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, st>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
+      } else {
+        BigKernelScope bigs(ctx);
+        fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, bigs.s>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
+      }
       // fold: offsets + one XYZZ slot per thread in dynamic shared memory; wide CTAs when only a few MSMs are in flight
       const bool wide = nm < 48;
       const size_t fsm = (((size_t)nm + 1 + 31) & ~size_t(31)) * 4 + (size_t)(wide ? FB_FOLD_THREADS_WIDE : FB_FOLD_THREADS) * sizeof(Xyzz<BP>);

@@ -3,9 +3,11 @@
 // multiplications (~77 K instructions, half of them on the fma-heavy pipe every kernel of this library is bound by, and
 // 130 - 180 us of latency on a lone warp); this routine needs ~30 K instructions, practically all of them on the ALU pipe
 // (which sits at ~33 %), so the inversions inside the grand-product finish, the batch-inversion kernels, the table build
-// and the table MSM's pair mode stop competing with the multiplications.  It is NOT wired into any
-// kernel yet: it was written after round 1's GPU budget was spent and is only verified on the CPU
-// (tests/test_gcdinv_host.py runs this very code, compiled for the host, against big-integer inverses).
+// and the table MSM's pair mode stop competing with the multiplications.  Used through `fe_inv_gcd`
+// (field.cuh) wherever ONE lane inverts while the rest of its warp waits: the grand-product finish, XYZZ / Jacobian ->
+// affine, and `bz_field_op` op 9.  Checked on the CPU (tests/test_gcdinv_host.py runs this very code, compiled for the
+// host, against big-integer inverses) and on the device against the Fermat chain and the oracle
+// (tests/test_gpu_arith.py::test_binary_gcd_inverse_on_device, green on B200 in round 2).
 //
 // Invariants:  b * a = u  and  c * a = v  (mod p), u and v odd after the shifts; gcd(u, v) = 1, so the loop ends with
 // u = v = 1 and b = a^-1.  Trailing zeros are removed all at once: because p = 1 (mod 2^32), p^-1 = 1 (mod 2^k) for k <= 32,

@@ -242,7 +242,7 @@ __global__ void jac_to_affine_kernel(const Jac<BP>* __restrict__ in, Affine<BP>*
   Affine<BP> r;
   if (fe_is_zero(p.z)) { r.x = fe_zero<BP>(); r.y = fe_zero<BP>(); }
   else {
-    Fe<BP> zi = fe_inv(p.z), zi2 = fe_sqr(zi);
+    Fe<BP> zi = fe_inv_gcd(p.z), zi2 = fe_sqr(zi);
     r.x = fe_mul(p.x, zi2);
     r.y = fe_mul(p.y, fe_mul(zi2, zi));
   }

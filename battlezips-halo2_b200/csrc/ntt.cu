@@ -191,7 +191,8 @@ template <class P> static void launch_pass(Ctx* ctx, NttPassArgs<P>& a, uint64_t
   once.run(ctx->device, [] { cudaFuncSetAttribute(ntt_pass_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024); });
   dim3 grid((unsigned)(nlines >> a.logT), (unsigned)batch, (unsigned)batch2);
   ProfScope prof(ctx, PROF_NTT_PASS);
-  ntt_pass_kernel<P><<<grid, threads, smem, ctx->stream>>>(a);
+  BigKernelScope bigs(ctx);
+  ntt_pass_kernel<P><<<grid, threads, smem, bigs.s>>>(a);
   ctx->kernel_launches++;
   BZ_CUDA(cudaGetLastError());
 }

@@ -391,7 +391,7 @@ __global__ void grand_product_finish_kernel(const Fe<P>* __restrict__ pnum, cons
   __shared__ Fe<P> scale_sh;
   const uint32_t b = blockIdx.y;
   if (threadIdx.x == 0) {
-    Fe<P> inv = fe_inv(fe_load(sden + (uint64_t)b * nd_stride));
+    Fe<P> inv = fe_inv_gcd(fe_load(sden + (uint64_t)b * nd_stride));     // one lane, pure latency: binary GCD (ALU pipe) instead of a Fermat chain
     if (has_z0) inv = fe_mul(inv, fe_load(region_ptr<P>(reg, z0ref, b, n) + z0_index));
     scale_sh = inv;
   }
@@ -422,7 +422,7 @@ __global__ void grand_product_finish_batch_kernel(const Fe<P>* __restrict__ pnum
       pre[gp - g0] = acc;
       if (!fe_is_zero(s0[gp - g0])) acc = fe_mul(acc, s0[gp - g0]);
     }
-    Fe<P> inv = fe_inv(acc);
+    Fe<P> inv = fe_inv_gcd(acc);
     Fe<P> z0 = fe_one<P>(), mine = fe_zero<P>();
     for (uint32_t gp = g + 1; gp-- > g0;) {                       // 1 / sden_gp[0], last product first
       Fe<P> iv = fe_zero<P>();

@@ -261,17 +261,19 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.hcoef_low.alloc(B * (en / 2) * E);
   w.nd.alloc(4 * (size_t)std::max<uint32_t>(1, pk.nsets + pk.L) * B * n * E);       // num, den, prefix(num), suffix(den) of every grand product
   w.consts.alloc(B * (size_t)pk.cstride * E);
-  w.extras.alloc(B * 64 * 2 * E);
+  // commitment requests per proof in one call: advice columns, 2 per lookup, grand products, the h pieces (or 2 IPA terms)
+  const size_t max_req = std::max<size_t>(std::max<size_t>(pk.cs.G, pk.cs.I), std::max<size_t>(std::max<size_t>(2 * pk.L, pk.nsets + pk.L), std::max<size_t>(pk.qdeg, 2)));
+  w.extras.alloc(B * max_req * 2 * E);
   w.evalout.alloc(B * (pk.evals.size() + pk.point_sets.size() + 8) * E);
-  w.commits.alloc(B * 64 * 128);
-  w.ptrs.alloc(B * 64 * 2 * sizeof(void*));
+  w.commits.alloc(B * max_req * 128);
+  w.ptrs.alloc(B * max_req * 2 * sizeof(void*));
   w.descs.alloc(64 * 1024);
   w.adv_in.alloc(1);
   w.lk_sorted.alloc(std::max<size_t>(1, (size_t)B * pk.L * n * E));
   w.lk_err.alloc(64);
   if (!w.h_err) BZ_CUDA(cudaMallocHost(&w.h_err, 64));
   if (w.h_pinned) cudaFreeHost(w.h_pinned);
-  w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(64 * 128, (pk.evals.size() + 16) * E)), 1 << 20);
+  w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(max_req * 128, (pk.evals.size() + 16) * E)), 1 << 20);
   BZ_CUDA(cudaMallocHost(&w.h_pinned, w.h_pinned_bytes));
   w.batch = B;
 }
@@ -875,13 +877,58 @@ struct Prover {
     C->kernel_launches++;
   }
 
+  void compute_h();
   void run(const void* instances, const uint32_t* instance_lens, uint32_t instance_stride, const void* advice, const void* rand_wide, uint8_t* proofs);
 };
+
+// steps 11-12 up to the coefficients of h(X): w.coset (all slots) + the per-proof constants -> w.hcoef[b][0 .. ext_n)
+// (the quotient program, the fused division by t(X), the inverse NTTs of the three degree tiers)
+void Prover::compute_h() {
+    EvalArgs<FpP> a{};
+    a.code = (const uint32_t*)pk.q_code[0].p; a.n_instr = pk.q_ninstr[0]; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot[0].p;
+    a.pbase = (const DFe*)w.coset.p; a.pstride = (uint64_t)pk.NS * en; a.sbase = (const DFe*)pk.shcoset.p;
+    a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
+    a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
+    static PerDeviceOnce once;
+    once.run(C->device, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+    {
+      ProfScope prof(C, PROF_QUOTIENT);
+      BigKernelScope bigs(C);
+      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr[0] * 4, bigs.s>>>(a);
+      C->kernel_launches++;
+      DFe* low_out = (DFe*)w.hext_low.p;
+      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {      // lower-degree terms: every 2^t-th extended point
+        if (!pk.q_ninstr[t]) continue;
+        EvalArgs<FpP> al = a;
+        al.code = (const uint32_t*)pk.q_code[t].p; al.n_instr = pk.q_ninstr[t]; al.rot = (const int32_t*)pk.q_rot[t].p;
+        al.stride_log = t; al.out = low_out; al.ostride = en >> t;
+        eval_program_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, pk.q_ninstr[t] * 4, bigs.s>>>(al);
+        C->kernel_launches++;
+        low_out += (size_t)B * (en >> t);
+      }
+    }
+    NttFusion fu; fu.post_mode = 3;
+    ntt_run(C, 0, w.hext.p, w.hcoef.p, pk.ext_k, true, B, fu);
+    {
+      const DFe* low_in = (const DFe*)w.hext_low.p;
+      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {
+        if (!pk.q_ninstr[t]) continue;
+        ntt_run(C, 0, low_in, w.hcoef_low.p, pk.ext_k - t, true, B, fu);
+        ProfScope prof(C, PROF_POLY);
+        add_low_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, 0, st>>>((DFe*)w.hcoef.p, en, (const DFe*)w.hcoef_low.p, en >> t);
+        C->kernel_launches++;
+        low_in += (size_t)B * (en >> t);
+      }
+    }
+}
 
 void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t instance_stride, const void* advice, const void* rand_wide, uint8_t* proofs) {
   const CircuitCopy& cs = pk.cs;
   const uint32_t G = cs.G, I = cs.I, L = pk.L, bf = cs.bf, usable = pk.usable;
-  for (uint32_t i = 0; i < I; ++i) if (instance_lens[i] > usable) throw Error(BZ_ERR_INVALID, "Error::InstanceTooLarge");
+  for (uint32_t i = 0; i < I; ++i) {
+    if (instance_lens[i] > usable) throw Error(BZ_ERR_INVALID, "Error::InstanceTooLarge");
+    BZ_CHECK(instance_lens[i] <= instance_stride, "instance_lens[i] exceeds instance_stride");
+  }
   // ---- per-proof host state
   for (uint32_t b = 0; b < B; ++b) {
     ps[b].out = proofs + (size_t)b * pk.proof_size;
@@ -1101,11 +1148,10 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         }
         product_scan_kernel<FpP><<<dim3(1, NG * B), SCAN_THREADS, 0, st>>>(num, pnum, n, n, 0);
         product_scan_kernel<FpP><<<dim3(1, NG * B), SCAN_THREADS, 0, st>>>(den, sden, n, n, 1);
-        // BZ_GP_FINISH_NARROW=1: one CTA per (proof, product), i.e. B x NG Fermat chains per batch instead of one per 128 rows (the
-        // r1h launch list shows the 3 072 single-lane chains of the wide geometry costing the fma pipe as much as an IPA-round
-        // MSM).  Written after the round's GPU budget was spent: the validated wide geometry (template argument false: the code that passed)
-        // stays the default until the narrow one has run through the parity suite.
-        const bool narrow = [] { const char* e = getenv("BZ_GP_FINISH_NARROW"); return e && atoi(e) != 0; }();
+        // One CTA per (proof, product), i.e. B x NG inversions per batch instead of one per 128 rows (the r1h launch list shows
+        // the 3 072 single-lane chains of the wide geometry costing the fma pipe as much as an IPA-round MSM; r2 A/B on B200:
+        // scan scope 5.77 -> 2.78 ms per 5 x 64 proofs, Shot 3 469 -> 3 600 proofs/s).  BZ_GP_FINISH_NARROW=0 selects the wide geometry.
+        const bool narrow = [] { const char* e = getenv("BZ_GP_FINISH_NARROW"); return !(e && atoi(e) == 0); }();
         if (narrow) grand_product_finish_batch_kernel<FpP, true><<<dim3(1, B, NG), 256, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
         else grand_product_finish_batch_kernel<FpP, false><<<dim3((n + 127) / 128, B, NG), 128, 0, st>>>(pnum, sden, PS, n, reg, gd, n, n - (bf + 1));
         C->kernel_launches += NG + 3;
@@ -1186,41 +1232,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   // ---- steps 11-12: h(X)
   phase.reset(); phase.reset(new NvtxRange("steps 11-13: h(X), pieces"));
   {
-    EvalArgs<FpP> a{};
-    a.code = (const uint32_t*)pk.q_code[0].p; a.n_instr = pk.q_ninstr[0]; a.logN = pk.ext_k; a.rot = (const int32_t*)pk.q_rot[0].p;
-    a.pbase = (const DFe*)w.coset.p; a.pstride = (uint64_t)pk.NS * en; a.sbase = (const DFe*)pk.shcoset.p;
-    a.consts = (const DFe*)w.consts.p; a.cstride = pk.cstride;
-    a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
-    static PerDeviceOnce once;
-    once.run(C->device, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
-    {
-      ProfScope prof(C, PROF_QUOTIENT);
-      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr[0] * 4, st>>>(a);
-      C->kernel_launches++;
-      DFe* low_out = (DFe*)w.hext_low.p;
-      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {      // lower-degree terms: every 2^t-th extended point
-        if (!pk.q_ninstr[t]) continue;
-        EvalArgs<FpP> al = a;
-        al.code = (const uint32_t*)pk.q_code[t].p; al.n_instr = pk.q_ninstr[t]; al.rot = (const int32_t*)pk.q_rot[t].p;
-        al.stride_log = t; al.out = low_out; al.ostride = en >> t;
-        eval_program_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, pk.q_ninstr[t] * 4, st>>>(al);
-        C->kernel_launches++;
-        low_out += (size_t)B * (en >> t);
-      }
-    }
-    NttFusion fu; fu.post_mode = 3;
-    ntt_run(C, 0, w.hext.p, w.hcoef.p, pk.ext_k, true, B, fu);
-    {
-      const DFe* low_in = (const DFe*)w.hext_low.p;
-      for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {
-        if (!pk.q_ninstr[t]) continue;
-        ntt_run(C, 0, low_in, w.hcoef_low.p, pk.ext_k - t, true, B, fu);
-        ProfScope prof(C, PROF_POLY);
-        add_low_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, 0, st>>>((DFe*)w.hcoef.p, en, (const DFe*)w.hcoef_low.p, en >> t);
-        C->kernel_launches++;
-        low_in += (size_t)B * (en >> t);
-      }
-    }
+    compute_h();
     std::vector<CommitReq> reqs;
     std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(pk.qdeg));
     for (uint32_t i = 0; i < pk.qdeg; ++i) reqs.push_back({PolyRef{R_HCOEF, i}, false});
@@ -1440,3 +1452,147 @@ extern "C" API int bz_create_proofs(bz_ctx* ctx, bz_pk* pkh, uint32_t batch, con
     pr.run(instances, instance_lens, instance_stride, advice, rand_wide, (uint8_t*)proofs);
   });
 }
+
+// ======================================================================================================
+// Fine-grained entry points bound to a ProvingKey / Params (SURVEY 8b minimum export set): what a patched
+// plonk/vanishing/prover.rs and poly/commitment/prover.rs would call one-for-one.  Host buffers, synchronous.
+// ======================================================================================================
+extern "C" {
+
+// vanishing::Argument::construct up to h(X)'s coefficients (U: halo2_proofs 0.2.0 src/plonk/vanishing/prover.rs `construct`,
+// src/plonk/prover.rs the `h_poly` expression list, src/poly/domain.rs `divide_by_vanishing_poly` + `extended_to_coeff`).
+API int bz_pk_quotient(bz_ctx* ctx, bz_pk* pkh, const void* polys, const void* theta, const void* beta, const void* gamma, const void* y, void* out_h) {
+  if (!ctx) return BZ_ERR_INVALID;
+  PV_TRY(ctx, {
+    BZ_CHECK(pkh && polys && theta && beta && gamma && y && out_h, "null argument");
+    PkImpl& pk = pkh->p;
+    ensure_work(C, pk, 1);
+    Prover pr(C, pk, 1);
+    const bzh::Field& F = C->fp;
+    ProofState& ps = pr.ps[0];
+    ps.consts.assign(pk.cstride, F.zero());
+    for (uint32_t i = 0; i < pk.NC; ++i) ps.consts[i] = pk.cs.consts[i];
+    ps.consts[pk.C_ONE] = F.one();
+    HFe th, be, ga, yy;
+    memcpy(th.l, theta, 32); memcpy(be.l, beta, 32); memcpy(ga.l, gamma, 32); memcpy(yy.l, y, 32);
+    ps.consts[pk.C_THETA] = th; ps.consts[pk.C_BETA] = be; ps.consts[pk.C_GAMMA] = ga; ps.consts[pk.C_Y] = yy;
+    HFe bd = be;
+    for (uint32_t j = 0; j < pk.M; ++j) { ps.consts[pk.C_BD0 + j] = bd; bd = F.mul(bd, F.delta()); }
+    HFe yp = F.one();
+    for (uint32_t g = 0; g <= pk.n_exprs; ++g) { ps.consts[pk.C_YP0 + g] = yp; yp = F.mul(yp, yy); }
+    pr.upload_consts();
+    BZ_CUDA(cudaMemcpyAsync(pr.w.poly.p, polys, (size_t)pk.NS * pk.n * 32, cudaMemcpyHostToDevice, pr.st));
+    pr.to_coset(0, pk.NS);
+    pr.compute_h();
+    BZ_CUDA(cudaMemcpyAsync(out_h, pr.w.hcoef.p, (size_t)pk.qdeg * pk.n * 32, cudaMemcpyDeviceToHost, pr.st));
+    BZ_CUDA(cudaStreamSynchronize(pr.st));
+  });
+}
+API uint32_t bz_pk_num_poly_slots(const bz_pk* pk) { return pk ? pk->p.NS : 0; }
+
+}  // extern "C"
+
+// ---- inner product argument, round by round (U: halo2_proofs 0.2.0 src/poly/commitment/prover.rs `create_proof`) ----
+struct bz_ipa {
+  bz::ParamsImpl* params = nullptr;
+  uint32_t n = 0, k = 0, round = 0;
+  bz::DevBuf vec;        // 5 x n scalars: p', b, coef (challenge products over the ORIGINAL g), scalars of L, scalars of R
+  bz::DevBuf consts;     // z, u, u^-1, x3
+  bz::DevBuf rnd;        // l_rand, r_rand
+  bz::DevBuf extras;     // [2][2] extra scalars of the two MSMs (w: blind, u: z <p', b>)
+  bz::DevBuf ptrs, out, msm_in, msm_jac;
+  bz::Regions reg;
+};
+
+extern "C" {
+
+API int bz_ipa_begin(bz_ctx* ctx, bz_params* params, const void* p_prime, const void* x3, bz_ipa** out) {
+  if (!ctx) return BZ_ERR_INVALID;
+  PV_TRY(ctx, {
+    BZ_CHECK(params && p_prime && x3 && out, "null argument");
+    *out = nullptr;
+    std::unique_ptr<bz_ipa> h(new bz_ipa());
+    h->params = &params->p; h->n = params->p.n; h->k = params->p.k;
+    BZ_CHECK(params->p.curve == 0, "ipa: only the Vesta commitment curve is wired up");
+    const size_t n = h->n;
+    cudaStream_t st = C->stream;
+    h->vec.alloc(5 * n * 32); h->consts.alloc(8 * 32); h->rnd.alloc(2 * 32); h->extras.alloc(4 * 32); h->ptrs.alloc(4 * sizeof(void*)); h->out.alloc(2 * 128);
+    memset(&h->reg, 0, sizeof(h->reg));
+    h->reg.base[R_MISC] = h->vec.p; h->reg.stride[R_MISC] = 0;
+    BZ_CUDA(cudaMemcpyAsync(h->vec.p, p_prime, n * 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemsetAsync(h->consts.p, 0, 8 * 32, st));
+    BZ_CUDA(cudaMemcpyAsync((DFe*)h->consts.p + 3, x3, 32, cudaMemcpyHostToDevice, st));
+    powers_kernel<FpP><<<dim3((unsigned)((n + 127) / 128), 1), 128, 0, st>>>(h->reg, (uint32_t)n, PolyRef{R_MISC, 1}, (const DFe*)h->consts.p, 8, 3);
+    fill_kernel<FpP><<<dim3((unsigned)((n + 127) / 128), 1), 128, 0, st>>>(h->reg, n, PolyRef{R_MISC, 2}, (uint32_t)n, dfe(C->fp.one()));
+    C->kernel_launches += 2;
+    void* ptrs[4] = {(DFe*)h->vec.p + 3 * n, (DFe*)h->vec.p + 4 * n, (DFe*)h->extras.p, (DFe*)h->extras.p + 2};
+    BZ_CUDA(cudaMemcpyAsync(h->ptrs.p, ptrs, sizeof(ptrs), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    *out = h.release();
+  });
+}
+
+// L_j and R_j of the current round (affine, 64 B each): <p'_hi, G'_lo> + [z <p'_hi, b_lo>] U + [l_rand] W and the mirror image
+API int bz_ipa_round(bz_ctx* ctx, bz_ipa* ipa, const void* z, const void* l_rand, const void* r_rand, void* out_l_affine, void* out_r_affine) {
+  if (!ctx) return BZ_ERR_INVALID;
+  PV_TRY(ctx, {
+    BZ_CHECK(ipa && z && l_rand && r_rand && out_l_affine && out_r_affine, "null argument");
+    BZ_CHECK(ipa->round < ipa->k, "ipa: all rounds done");
+    cudaStream_t st = C->stream;
+    const uint32_t n = ipa->n, half = 1u << (ipa->k - ipa->round - 1);
+    BZ_CUDA(cudaMemcpyAsync(ipa->consts.p, z, 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(ipa->rnd.p, l_rand, 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->rnd.p + 1, r_rand, 32, cudaMemcpyHostToDevice, st));
+    ipa_scalars_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 2}, PolyRef{R_MISC, 3}, PolyRef{R_MISC, 4});
+    ipa_inner_kernel<FpP><<<1, IPA_THREADS, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 1}, (const DFe*)ipa->consts.p, 8, 0,
+                                                    (const DFe*)ipa->rnd.p, 0, 0, 1, (DFe*)ipa->extras.p);
+    C->kernel_launches += 2;
+    ParamsImpl& pr = *ipa->params;
+    if (pr.use_tables) fixed_msm_run(C, pr.fb_g, (const void* const*)ipa->ptrs.p, n, (const void* const*)((void**)ipa->ptrs.p + 2), 2, 16, ipa->out.p, false);
+    else {
+      // extras are [blind (w), z <p', b> (u)] in the order of g || w || u
+      ipa->msm_in.ensure((size_t)(n + 2) * 32); ipa->msm_jac.ensure(2 * 96);
+      for (int j = 0; j < 2; ++j) {
+        BZ_CUDA(cudaMemcpyAsync(ipa->msm_in.p, (DFe*)ipa->vec.p + (size_t)(3 + j) * n, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
+        BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->msm_in.p + n, (DFe*)ipa->extras.p + 2 * j, 64, cudaMemcpyDeviceToDevice, st));
+        msm_run(C, pr.curve, ipa->msm_in.p, pr.g_w_u.p, n + 2, (char*)ipa->msm_jac.p + (size_t)j * 96, 0);
+      }
+      jac_to_affine_run(C, pr.curve, ipa->msm_jac.p, ipa->out.p, 2);
+    }
+    BZ_CUDA(cudaMemcpyAsync(out_l_affine, ipa->out.p, 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaMemcpyAsync(out_r_affine, (char*)ipa->out.p + 64, 64, cudaMemcpyDeviceToHost, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+  });
+}
+
+// p'_lo += u^-1 p'_hi, b_lo += u b_hi, G'_lo += [u] G'_hi (kept as challenge products over the original generators)
+API int bz_ipa_fold(bz_ctx* ctx, bz_ipa* ipa, const void* u, const void* u_inv) {
+  if (!ctx) return BZ_ERR_INVALID;
+  PV_TRY(ctx, {
+    BZ_CHECK(ipa && u && u_inv, "null argument");
+    BZ_CHECK(ipa->round < ipa->k, "ipa: all rounds done");
+    cudaStream_t st = C->stream;
+    const uint32_t n = ipa->n, half = 1u << (ipa->k - ipa->round - 1);
+    BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->consts.p + 1, u, 32, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->consts.p + 2, u_inv, 32, cudaMemcpyHostToDevice, st));
+    ipa_fold_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 1}, PolyRef{R_MISC, 2}, (const DFe*)ipa->consts.p, 8, 1, 2);
+    C->kernel_launches++;
+    BZ_CUDA(cudaStreamSynchronize(st));
+    ipa->round++;
+  });
+}
+
+// c = p'[0] after the last round; releases the state
+API int bz_ipa_finish(bz_ctx* ctx, bz_ipa* ipa, void* out_c) {
+  if (!ctx) return BZ_ERR_INVALID;
+  PV_TRY(ctx, {
+    BZ_CHECK(ipa && out_c, "null argument");
+    std::unique_ptr<bz_ipa> own(ipa);
+    BZ_CHECK(ipa->round == ipa->k, "ipa: rounds missing");
+    BZ_CUDA(cudaMemcpyAsync(out_c, ipa->vec.p, 32, cudaMemcpyDeviceToHost, C->stream));
+    BZ_CUDA(cudaStreamSynchronize(C->stream));
+  });
+}
+API void bz_ipa_destroy(bz_ipa* ipa) { delete ipa; }
+
+}  // extern "C"

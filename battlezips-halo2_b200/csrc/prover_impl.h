@@ -170,6 +170,7 @@ struct bz_pk { bz::PkImpl p; };
 static inline bz::Ctx* ctx_of(bz_ctx* c) { return &c->c; }
 
 #define PV_TRY(ctx_, ...)                                     \
+  if (!(ctx_)) return BZ_ERR_INVALID;                         \
   bz::Ctx* C = ctx_of(ctx_);                                  \
   try {                                                       \
     cudaSetDevice(C->device);                                 \

@@ -410,6 +410,7 @@ extern "C" API int bz_verify_proofs(bz_ctx* ctx, bz_pk* pkh, uint32_t batch, con
     BZ_CHECK(pkh && proofs && results && batch >= 1, "null argument");
     PkImpl& pk = pkh->p;
     BZ_CHECK(pk.cs.I == 0 || (instances && instance_lens), "instances missing");
+    for (uint32_t i = 0; i < pk.cs.I; ++i) BZ_CHECK(instance_lens[i] <= instance_stride, "instance_lens[i] exceeds instance_stride");
     if (pk.vk_fixed_comm.size() + pk.vk_perm_comm.size() != (size_t)(pk.cs.F + pk.M) * 8) {
       int rc = bz_pk_vk_commitments(ctx, pkh, nullptr, nullptr);
       if (rc != BZ_OK) return rc;

@@ -104,6 +104,31 @@ class Params:
         as_ptr = lambda p: p if isinstance(p, ctypes.c_void_p) else ctypes.c_void_p(int(p))
         self.ctx._check(self.ctx.lib.bz_params_commit_batch_dev(self.ctx.h, self.h, 1 if lagrange else 0, as_ptr(d_polys), as_ptr(d_blinds), count, as_ptr(d_out)))
 
+    def ipa_open(self, p_prime, x3, z, rounds):
+        """poly::commitment::create_proof's folding loop through bz_ipa_begin / round / fold / finish.  rounds = k callables
+        or tuples (l_rand, r_rand, u_of(L, R)) -- u_of maps the round's affine (L, R) to (u, u_inv) (the transcript side).
+        Returns ([(L, R)], c)."""
+        lib, ctx = self.ctx.lib, self.ctx
+        sc = lambda v: np.ascontiguousarray(v, dtype=np.uint64).reshape(4)
+        p_prime = np.ascontiguousarray(p_prime, dtype=np.uint64).reshape(-1, 4)
+        h = ctypes.c_void_p()
+        ctx._check(lib.bz_ipa_begin(ctx.h, self.h, _np_ptr(p_prime), _np_ptr(sc(x3)), ctypes.byref(h)))
+        out = []
+        try:
+            for l_rand, r_rand, u_of in rounds:
+                L, R = np.zeros(8, dtype=np.uint64), np.zeros(8, dtype=np.uint64)
+                ctx._check(lib.bz_ipa_round(ctx.h, h, _np_ptr(sc(z)), _np_ptr(sc(l_rand)), _np_ptr(sc(r_rand)), _np_ptr(L), _np_ptr(R)))
+                u, u_inv = u_of(L, R)
+                ctx._check(lib.bz_ipa_fold(ctx.h, h, _np_ptr(sc(u)), _np_ptr(sc(u_inv))))
+                out.append((L, R))
+            c = np.zeros(4, dtype=np.uint64)
+            ctx._check(lib.bz_ipa_finish(ctx.h, h, _np_ptr(c)))
+            h = None
+        finally:
+            if h:
+                lib.bz_ipa_destroy(h)
+        return out, c
+
     def close(self):
         if self.h:
             self.ctx.lib.bz_params_destroy(self.h)
@@ -213,6 +238,7 @@ class ProvingKey:
             mp = np.ascontiguousarray(np.array(mapping, dtype=np.uint32).reshape(-1, 2)) if len(mapping) else np.zeros((1, 2), np.uint32)
             ctx._check(ctx.lib.bz_pk_create_from_assembly(ctx.h, params.h, ctypes.byref(circ), _np_ptr(fixed), _np_ptr(mp), ctypes.byref(h)))
         self.h = h
+        self.degree = ir["degree"]
         self.num_random = ctx.lib.bz_pk_num_random(h)
         self.proof_size = ctx.lib.bz_pk_proof_size(h)
         # (multiplications per point, points) of every h(X) evaluation tier: the quotient kernel's algorithmic work
@@ -227,6 +253,19 @@ class ProvingKey:
         fc, pc = np.zeros((max(F, 1), 8), dtype=np.uint64), np.zeros((max(M, 1), 8), dtype=np.uint64)
         self.ctx._check(self.ctx.lib.bz_pk_vk_commitments(self.ctx.h, self.h, _np_ptr(fc), _np_ptr(pc)))
         return fc[:F], pc[:M]
+
+    def quotient(self, polys, theta, beta, gamma, y):
+        """vanishing::Argument::construct up to h(X)'s coefficients (bz_pk_quotient): polys = (slots, n, 4) coefficient
+        forms in the order advice, instance, per lookup (A', S', Z), permutation z; challenges as (4,) Montgomery limbs.
+        Returns ((degree - 1) * n, 4)."""
+        lib = self.ctx.lib
+        slots = lib.bz_pk_num_poly_slots(self.h)
+        polys = np.ascontiguousarray(polys, dtype=np.uint64).reshape(slots, -1, 4)
+        n = polys.shape[1]
+        out = np.zeros(((self.degree - 1) * n, 4), dtype=np.uint64)
+        sc = [np.ascontiguousarray(v, dtype=np.uint64).reshape(4) for v in (theta, beta, gamma, y)]
+        self.ctx._check(lib.bz_pk_quotient(self.ctx.h, self.h, _np_ptr(polys), *[_np_ptr(v) for v in sc], _np_ptr(out)))
+        return out
 
     def close(self):
         if self.h:

@@ -77,7 +77,7 @@ int bz_d2h(bz_ctx* ctx, void* host, const void* dptr, size_t bytes);
 /* ---- ff::Field / group ops on host slices (pasta_curves semantics; used by the parity suite and by the
  * shim for the few scalar-sized steps it does not want to do on the CPU) ------------------------------ */
 /* op: 0 a*b, 1 a+b, 2 a-b, 3 a^-1 over the slice (ff::BatchInvert: Montgomery trick, 0 -> 0), 4 from_u512 (a = n x 64 B little-endian), 5 Montgomery -> canonical,
- *     6 canonical -> Montgomery, 7 -a, 8 a^2, 9 a^-1 element-wise by binary GCD (gcdinv.h; pending GPU validation) */
+ *     6 canonical -> Montgomery, 7 -a, 8 a^2, 9 a^-1 element-wise by binary GCD (gcdinv.h; same values as op 3) */
 int bz_field_op(bz_ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);
 /* poly::batch_invert_assigned (U: halo2_proofs 0.2.0 src/poly.rs `batch_invert_assigned`, called by create_proof on the
  * advice columns a circuit assigned as Assigned<F>; reference call path R:src/circuits/shot.rs:921 -> create_proof):
@@ -225,6 +225,58 @@ int bz_create_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instanc
  * Point decompression, the instance commitments, compute_s and the final multi-scalar check run on the device. */
 int bz_verify_proofs(bz_ctx* ctx, bz_pk* pk, uint32_t batch, const void* instances, const uint32_t* instance_lens,
                      uint32_t instance_stride, const void* proofs, uint32_t proof_len, uint8_t* results);
+
+/* ==================================================================================================
+ * Fine-grained prover arithmetic (SURVEY 8b "minimum export set"): one call per inner loop of halo2_proofs 0.2.0, what a
+ * patched plonk/permutation/prover.rs, plonk/lookup/prover.rs, plonk/vanishing/prover.rs, poly/domain.rs,
+ * poly/multiopen/prover.rs, poly/commitment/prover.rs and arithmetic.rs bind one-for-one when the whole-proof call
+ * (bz_create_proofs) is not used.  All buffers are HOST memory in pasta's in-memory Montgomery form; the calls are
+ * synchronous.  They run the same kernels as bz_create_proofs with a batch of one.
+ * ================================================================================================== */
+/* permutation::Argument::commit, the body for ONE column set (U: src/plonk/permutation/prover.rs): n = 2^k rows,
+ * values[j] / sigmas[j] = the set's ncols (<= 8, i.e. cs degree <= 10) columns and their sigma columns (Lagrange values),
+ * delta_omega0 = DELTA^(index of the set's first column), z0 = last_z of the previous set (ONE for the first).
+ * out_z[0] = z0, out_z[i+1] = out_z[i] * prod_j (v_j[i] + delta_omega0 DELTA^j omega^i beta + gamma) / (v_j[i] + beta sigma_j[i] + gamma);
+ * the caller overwrites the last `blinding_factors` rows and reads last_z = z[n - blinding_factors - 1] like upstream. */
+int bz_perm_product(bz_ctx* ctx, int field, uint32_t k, uint32_t ncols, const void* const* values, const void* const* sigmas,
+                    const void* beta, const void* gamma, const void* delta_omega0, const void* z0, void* out_z);
+/* lookup::Argument::commit_permuted -> permute_expression_pair (U: src/plonk/lookup/prover.rs): the theta-compressed input
+ * and table expressions (n scalars each); rows [0, usable_rows) are permuted (A' sorted, S' aligned; App. A step 5), rows
+ * above come back zero for the caller's blinding.  BZ_ERR_SYNTHESIS = an input value is missing from the table
+ * (Error::ConstraintSystemFailure). */
+int bz_lookup_permute(bz_ctx* ctx, int field, uint32_t k, uint32_t usable_rows, const void* compressed_input,
+                      const void* compressed_table, void* out_permuted_input, void* out_permuted_table);
+/* lookup::Permuted::commit_product: z[0] = 1, z[i+1] = z[i] (A[i] + beta)(S[i] + gamma) / ((A'[i] + beta)(S'[i] + gamma)); n scalars out */
+int bz_lookup_product(bz_ctx* ctx, int field, uint32_t k, const void* compressed_input, const void* compressed_table,
+                      const void* permuted_input, const void* permuted_table, const void* beta, const void* gamma, void* out_z);
+/* EvaluationDomain::divide_by_vanishing_poly (U: src/poly/domain.rs): a[i] *= t_evaluations[i mod 2^(extended_k - k)], in place,
+ * a = 2^extended_k scalars in the extended Lagrange basis */
+int bz_divide_by_vanishing(bz_ctx* ctx, int field, uint32_t k, uint32_t extended_k, void* a);
+/* vanishing::Argument::construct up to the coefficients of h(X) (U: src/plonk/vanishing/prover.rs, the expression list of
+ * src/plonk/prover.rs; App. A steps 11-12): polys = bz_pk_num_poly_slots(pk) x n coefficients in the order advice[0..G),
+ * instance[0..I), per lookup (A', S', Z), permutation z per set; out_h = (degree - 1) * n coefficients (the pieces, in order) */
+int bz_pk_quotient(bz_ctx* ctx, bz_pk* pk, const void* polys, const void* theta, const void* beta, const void* gamma,
+                   const void* y, void* out_h);
+uint32_t bz_pk_num_poly_slots(const bz_pk* pk);
+/* arithmetic::eval_polynomial for `count` (polynomial, point) pairs in one launch: polys[i] = n coefficients, points = count scalars */
+int bz_eval_many(bz_ctx* ctx, int field, uint64_t n, uint32_t count, const void* const* polys, const void* points, void* out);
+/* arithmetic::kate_division(a, point): a = n coefficients, out_q = n - 1 coefficients of a(X) / (X - point), remainder dropped */
+int bz_kate_div(bz_ctx* ctx, int field, uint64_t n, const void* a, const void* point, void* out_q);
+/* acc = acc * x + poly over n coefficients (multiopen's q_set / q' / P accumulation, the fold of the h pieces) */
+int bz_axpy(bz_ctx* ctx, int field, uint64_t n, void* acc, const void* x, const void* poly);
+/* poly::commitment::create_proof, the folding loop (U: src/poly/commitment/prover.rs).  The caller (transcript side) keeps
+ * S, xi, z and the blinds; the device keeps p', b and G' (as challenge products over the original generators).
+ *   bz_ipa_begin : p_prime = n coefficients of P' = P + xi S with p'(x3) already subtracted from the constant term; b = powers of x3
+ *   bz_ipa_round : L_j, R_j (affine, 64 B) for the current round, with the caller's blinds l_rand, r_rand and challenge z
+ *   bz_ipa_fold  : the round's folds by u_j (and its inverse)
+ *   bz_ipa_finish: c = p'[0] after the k-th fold; frees the state (bz_ipa_destroy frees it early) */
+typedef struct bz_ipa bz_ipa;
+int bz_ipa_begin(bz_ctx* ctx, bz_params* params, const void* p_prime, const void* x3, bz_ipa** out);
+int bz_ipa_round(bz_ctx* ctx, bz_ipa* ipa, const void* z, const void* l_rand, const void* r_rand, void* out_l_affine,
+                 void* out_r_affine);
+int bz_ipa_fold(bz_ctx* ctx, bz_ipa* ipa, const void* u, const void* u_inv);
+int bz_ipa_finish(bz_ctx* ctx, bz_ipa* ipa, void* out_c);
+void bz_ipa_destroy(bz_ipa* ipa);
 
 #ifdef __cplusplus
 }

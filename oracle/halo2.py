@@ -369,6 +369,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
 
     # step 3
     theta = T.squeeze_challenge()
+    tr["challenges"] = {"theta": theta}
 
     def lagrange_leaf(kind, col, rot):
         src = {"advice": advice_values, "fixed": pk.fixed_values, "instance": instance_values}[kind][col]
@@ -434,10 +435,13 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         L["permuted_input_coset"] = dom.coeff_to_extended(L["permuted_input_poly"])
         L["permuted_table_coset"] = dom.coeff_to_extended(L["permuted_table_poly"])
         lookups.append(L)
+    tr["lookups"] = lookups
 
     # step 6
     beta = T.squeeze_challenge()
     gamma = T.squeeze_challenge()
+    tr["challenges"].update(beta=beta, gamma=gamma)
+    tr["perm_sets"] = []
 
     _phase("grand products + commitments")
     # step 7: permutation argument
@@ -453,6 +457,8 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
 
     for s0 in range(0, len(perm_cols), chunk_len):
         cols = perm_cols[s0:s0 + chunk_len]
+        tr["perm_sets"].append({"values": [col_values(kind, col) for kind, col in cols], "sigmas": [pk.perm_values[s0 + j] for j in range(len(cols))],
+                                "delta_omega0": deltaomega, "z0": last_z})
         modified = V.const(1, n)
         for j, (kind, col) in enumerate(cols):
             t = V.add(V.add_const(V.scale(pk.perm_values[s0 + j], beta), gamma), col_values(kind, col))
@@ -463,6 +469,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
             modified = V.mul(modified, t)
             deltaomega = deltaomega * V.F.delta % p
         z = V.running_product(last_z, modified)
+        tr["perm_sets"][-1]["z_unblinded"] = z.copy()
         z[n - bf:] = rnd(bf)
         last_z = V.int1(z[n - (bf + 1)])
         blind = rnd1()
@@ -480,6 +487,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
         prod = V.mul(prod, V.add_const(L["compressed_input"], beta))
         prod = V.mul(prod, V.add_const(L["compressed_table"], gamma))
         z_full = V.running_product(1, np.concatenate([prod, V.zeros(1)]))      # z[0]=1, z[i]=prod of first i
+        L["z_unblinded"] = z_full[:n].copy()
         z = np.concatenate([z_full[:n - bf], rnd(bf)])
         assert len(z) == n
         L["product_blind"] = rnd1()
@@ -500,6 +508,9 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
 
     # step 10
     y = T.squeeze_challenge()
+    tr["challenges"]["y"] = y
+    tr["polys"] = (advice_polys + instance_polys + [q for L in lookups for q in (L["permuted_input_poly"], L["permuted_table_poly"], L["product_poly"])]
+                   + [s_["poly"] for s_ in sets])          # the slot order of bz_pk_quotient
 
     _phase("h(X): coset NTTs + evaluation")
     # step 11: h(X) on the extended coset
@@ -559,7 +570,9 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
 
     _phase("h(X): inverse NTT + piece commitments")
     # step 12: divide by t(X), back to coefficients, split, commit pieces
+    tr["h_extended_before_division"] = h
     h = dom.divide_by_vanishing_poly(h)
+    tr["h_extended"] = h
     h_coeffs = dom.extended_to_coeff(h)
     h_pieces = [h_coeffs[i * n:(i + 1) * n] for i in range(dom.quotient_poly_degree)]
     h_blinds = [rnd1() for _ in h_pieces]
@@ -572,6 +585,7 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     # step 13
     x = T.squeeze_challenge()
     xn = pow(x, n, p)
+    tr["challenges"]["x"] = x
 
     _phase("evaluations")
     # step 14: instance / advice / fixed evaluations
@@ -638,6 +652,8 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     # step 20: multiopen
     x1 = T.squeeze_challenge()
     x2 = T.squeeze_challenge()
+    tr["challenges"].update(x1=x1, x2=x2)
+    tr["queries"] = Q
     cmap, point_sets = construct_intermediate_sets(Q)
     q_polys = [None] * len(point_sets)
     q_blinds = [0] * len(point_sets)
@@ -660,6 +676,8 @@ def create_proof(params, pk, instances, advice, draws, transcript, trace=None):
     for qp in q_polys:
         T.write_scalar(V.eval_polynomial(qp, x3))
     x4 = T.squeeze_challenge()
+    tr["challenges"].update(x3=x3, x4=x4)
+    tr["q_polys"], tr["q_prime"] = q_polys, q_prime
     p_poly, p_blind = q_prime, q_prime_blind
     for qp, qb in zip(q_polys, q_blinds):
         p_poly = V.add(V.scale(p_poly, x4), qp)
@@ -691,6 +709,8 @@ def ipa_create_proof(params, draws, T, p_poly, p_blind, x3, tr=None):
     v = V.eval_polynomial(p_prime, x3)
     p_prime[0] = V.m((V.int1(p_prime[0]) - v) % p)
     fblind = (s_blind * xi + p_blind) % p
+    if tr is not None:
+        tr["ipa"] = {"p_prime": p_prime.copy(), "x3": x3, "z": z, "xi": xi, "rounds": []}
     b = V.powers(1, x3, n)
     g_prime = params.g.copy()
     u_w = np.stack([params.u, params.w])
@@ -719,11 +739,14 @@ def ipa_create_proof(params, draws, T, p_poly, p_blind, x3, tr=None):
         g_prime = g_prime[:half]
         fblind = (fblind + l_rand * u_inv + r_rand * u_j) % p
         rounds.append((l_pt, r_pt, u_j))
+        if tr is not None:
+            tr["ipa"]["rounds"].append({"L": l_pt, "R": r_pt, "u": u_j, "l_rand": l_rand, "r_rand": r_rand})
     c = V.int1(p_prime[0])
     T.write_scalar(c)
     T.write_scalar(fblind)
     if tr is not None:
         tr["ipa_rounds"] = rounds
+        tr["ipa"]["c"] = c
 
 
 # ------------------------------------------------------------------------------------------------------
