@@ -37,6 +37,66 @@ constexpr int EVAL_TMP = 24;
 // 0 const(a) 1 advice(a = column, b = rotation) 2 fixed 3 instance 4 neg 5 add 6 mul 7 scale by const(a)
 struct Token { uint32_t op, a; int32_t b; };
 
+// Fixed-only sub-expressions of the gate polynomials.  After keygen's selector compression every use of a simple selector is
+// q * prod_{i != r} (i - q): up to 8 multiplications per use, all over one fixed column.  A maximal sub-expression built from
+// constants and fixed queries at rotation 0 that contains a product is split off as a DERIVED column -- evaluated once per
+// proving key on the extended coset -- and the gate polynomial queries it like a fixed column in slot base_slot + j.
+// Same value at every point, so h(X) does not change.  `degree` keeps the true degree for the evaluation tiers.
+struct DerivedColumn { std::vector<Token> tokens; uint32_t degree; };
+inline void split_fixed_subexpressions(const std::vector<Token>& tokens, const std::vector<uint32_t>& gate_off, uint32_t base_slot, bool enabled,
+                                       std::vector<DerivedColumn>& derived, std::vector<Token>& qtokens, std::vector<uint32_t>& qgate_off) {
+  struct Node { Token t; int x = -1, y = -1; bool fixed_only = false, has_mul = false; uint32_t degree = 0; };
+  std::map<std::vector<uint32_t>, uint32_t> index;
+  derived.clear(); qtokens.clear(); qgate_off.assign(1, 0u);
+  for (size_t g = 0; g + 1 < gate_off.size(); ++g) {
+    std::vector<Node> nodes;
+    std::vector<int> st;
+    for (uint32_t t = gate_off[g]; t < gate_off[g + 1]; ++t) {
+      Node n; n.t = tokens[t];
+      switch (n.t.op) {
+        case 0: n.fixed_only = true; break;
+        case 2: n.fixed_only = n.t.b == 0; n.degree = 1; break;
+        case 1: case 3: n.degree = 1; break;
+        case 4: case 7: { BZ_EP_CHECK(!st.empty(), "bad expression"); n.x = st.back(); st.pop_back(); const Node& c = nodes[n.x]; n.fixed_only = c.fixed_only; n.has_mul = c.has_mul; n.degree = c.degree; break; }
+        case 5: case 6: {
+          BZ_EP_CHECK(st.size() >= 2, "bad expression");
+          n.y = st.back(); st.pop_back(); n.x = st.back(); st.pop_back();
+          const Node &a = nodes[n.x], &b = nodes[n.y];
+          n.fixed_only = a.fixed_only && b.fixed_only; n.has_mul = a.has_mul || b.has_mul || n.t.op == 6;
+          n.degree = n.t.op == 5 ? std::max(a.degree, b.degree) : a.degree + b.degree;
+          break;
+        }
+        default: BZ_EP_CHECK(false, "bad token op");
+      }
+      nodes.push_back(n);
+      st.push_back((int)nodes.size() - 1);
+    }
+    BZ_EP_CHECK(st.size() == 1, "bad expression");
+    struct Walk {
+      const std::vector<Node>& nodes; std::map<std::vector<uint32_t>, uint32_t>& index; std::vector<DerivedColumn>& derived; std::vector<Token>& out;
+      uint32_t base_slot; bool enabled;
+      void flat(int v, std::vector<Token>& o) const { const Node& n = nodes[v]; if (n.x >= 0) flat(n.x, o); if (n.y >= 0) flat(n.y, o); o.push_back(n.t); }
+      void emit(int v) {
+        const Node& n = nodes[v];
+        if (enabled && n.fixed_only && n.has_mul && n.degree >= 2) {
+          std::vector<Token> sub; flat(v, sub);
+          std::vector<uint32_t> key;
+          for (const Token& k : sub) { key.push_back(k.op); key.push_back(k.a); key.push_back((uint32_t)k.b); }
+          auto it = index.find(key);
+          if (it == index.end()) { it = index.emplace(key, (uint32_t)derived.size()).first; derived.push_back(DerivedColumn{sub, n.degree}); }
+          out.push_back(Token{2, base_slot + it->second, 0});
+          return;
+        }
+        if (n.x >= 0) emit(n.x);
+        if (n.y >= 0) emit(n.y);
+        out.push_back(n.t);
+      }
+    } walk{nodes, index, derived, qtokens, base_slot, enabled};
+    walk.emit(st.back());
+    qgate_off.push_back((uint32_t)qtokens.size());
+  }
+}
+
 inline uint32_t enc(uint32_t op, uint32_t x = 0, uint32_t y = 0) { return op | (x << 4) | (y << 16); }
 inline uint32_t encc(uint32_t op, uint32_t idx) { return op | (idx << 4); }
 

@@ -29,9 +29,9 @@ template <class P> __global__ void sigma_from_mapping_kernel(const uint32_t* __r
 }
 
 // emit one expression (postfix tokens [lo,hi)); advice -> per-proof slot col, instance -> slot G + col, fixed -> shared slot col
-static void emit_expr(ProgBuilder& pb, const CircuitCopy& cs, uint32_t lo, uint32_t hi) {
+static void emit_tokens(ProgBuilder& pb, const CircuitCopy& cs, const std::vector<Token>& tokens, uint32_t lo, uint32_t hi) {
   for (uint32_t t = lo; t < hi; ++t) {
-    const Token& k = cs.tokens[t];
+    const Token& k = tokens[t];
     switch (k.op) {
       case 0: pb.pc(k.a); break;
       case 1: pb.pp(k.a, k.b); break;
@@ -45,6 +45,13 @@ static void emit_expr(ProgBuilder& pb, const CircuitCopy& cs, uint32_t lo, uint3
     }
   }
 }
+static void emit_expr(ProgBuilder& pb, const CircuitCopy& cs, uint32_t lo, uint32_t hi) { emit_tokens(pb, cs, cs.tokens, lo, hi); }
+
+static void derive_fixed_subexpressions(PkImpl& pk) {
+  const char* env = getenv("BZ_QUOTIENT_DERIVED");            // =0: evaluate the compressed selector products per point (A/B)
+  split_fixed_subexpressions(pk.cs.tokens, pk.cs.gate_off, pk.cs.F + pk.M + 5, !(env && atoi(env) == 0), pk.derived, pk.qtokens, pk.qgate_off);
+}
+
 static void emit_compressed(ProgBuilder& pb, const CircuitCopy& cs, const std::vector<std::pair<uint32_t, uint32_t>>& exprs, uint32_t c_theta) {
   for (size_t e = 0; e < exprs.size(); ++e) {
     if (e > 0) pb.mulc(c_theta);
@@ -94,13 +101,15 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
   {
     struct Term { uint32_t degree; std::function<void(ProgBuilder&)> emit; bool gate = false; uint32_t lo = 0, hi = 0; };
     std::vector<Term> terms;
-    auto expr_degree = [&](uint32_t lo, uint32_t hi) {
+    const uint32_t derived_base = cs.F + pk.M + 5;
+    auto degree_of = [&](const std::vector<Token>& tokens, uint32_t lo, uint32_t hi) {
       std::vector<uint32_t> st;
       for (uint32_t t = lo; t < hi; ++t) {
-        const Token& k = cs.tokens[t];
+        const Token& k = tokens[t];
         switch (k.op) {
           case 0: st.push_back(0); break;
-          case 1: case 2: case 3: st.push_back(1); break;
+          case 2: st.push_back(k.a >= derived_base ? pk.derived[k.a - derived_base].degree : 1u); break;
+          case 1: case 3: st.push_back(1); break;
           case 4: case 7: break;
           case 5: { uint32_t r = st.back(); st.pop_back(); st.back() = std::max(st.back(), r); break; }
           case 6: { uint32_t r = st.back(); st.pop_back(); st.back() += r; break; }
@@ -109,11 +118,13 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       }
       return st.back();
     };
+    auto expr_degree = [&](uint32_t lo, uint32_t hi) { return degree_of(cs.tokens, lo, hi); };
     auto compressed_degree = [&](const std::vector<std::pair<uint32_t, uint32_t>>& es) { uint32_t d = 0; for (auto& r : es) d = std::max(d, expr_degree(r.first, r.second)); return d; };
     const int last_rot = -((int)cs.bf + 1);
-    for (size_t g = 0; g + 1 < cs.gate_off.size(); ++g) {
-      const uint32_t lo = cs.gate_off[g], hi = cs.gate_off[g + 1];
-      terms.push_back({expr_degree(lo, hi), [&cs, lo, hi](ProgBuilder& pb) { emit_expr(pb, cs, lo, hi); }, true, lo, hi});
+    for (size_t g = 0; g + 1 < pk.qgate_off.size(); ++g) {
+      const uint32_t lo = pk.qgate_off[g], hi = pk.qgate_off[g + 1];
+      BZ_CHECK(degree_of(pk.qtokens, lo, hi) == expr_degree(cs.gate_off[g], cs.gate_off[g + 1]), "internal: derived columns changed a gate's degree");
+      terms.push_back({degree_of(pk.qtokens, lo, hi), [&cs, &pk, lo, hi](ProgBuilder& pb) { emit_tokens(pb, cs, pk.qtokens, lo, hi); }, true, lo, hi});
     }
     if (pk.nsets) {
       terms.push_back({2, [&pk](ProgBuilder& pb) { pb.pc(pk.C_ONE); pb.pp(pk.slot_pz(0), 0); pb.sub(); pb.ps(shslot_l0(pk), 0); pb.mul(); }});          // l0 * (1 - z_0)
@@ -175,7 +186,7 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       GateDag dag; dag.advice_slot_of_instance = cs.G; dag.nested = variant >= 1; dag.canon_mul = dag.sort_rest = variant >= 2;
       if (use_dag) {
         for (uint32_t e = 0; e < E; ++e)
-          if (terms[e].gate && tier_of(std::max(1u, terms[e].degree)) == tier) dag.add(cs.tokens, terms[e].lo, terms[e].hi, e);
+          if (terms[e].gate && tier_of(std::max(1u, terms[e].degree)) == tier) dag.add(pk.qtokens, terms[e].lo, terms[e].hi, e);
         dag.plan();
         for (const GateDag::Group& g : dag.groups) {
           dag.emit_group(pb, g, prev, yp);
@@ -489,8 +500,10 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
       C->kernel_launches += 2;
       BZ_CUDA(cudaStreamSynchronize(st));
     }
+    derive_fixed_subexpressions(pk);
+    const uint32_t ND = (uint32_t)pk.derived.size();
     pk.shpoly.alloc((size_t)std::max(1u, FM) * n * 32);
-    pk.shcoset.alloc((size_t)(FM + 5) * en * 32);
+    pk.shcoset.alloc((size_t)(FM + 5 + ND) * en * 32);
     NttFusion inv; inv.post_mode = 1;
     NttFusion ext; ext.n_in = pk.ext_k > cs.k ? n : 0; ext.pre_zeta = true;
     if (FM) {
@@ -512,6 +525,27 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
     }
     geometric_kernel<FpP><<<(en + 127) / 128, 128, 0, st>>>((DFe*)pk.shcoset.p + (size_t)(FM + 4) * en, dfe(F.zeta()), dfe(pk.ext_omega), en);
     C->kernel_launches += 1;
+    if (ND) {  // derived shared columns: the fixed-only sub-expressions of the gates on the extended coset, once per key
+      ProgBuilder pb; pb.scale = 1 << (pk.ext_k - cs.k);
+      for (uint32_t j = 0; j < ND; ++j) { emit_tokens(pb, cs, pk.derived[j].tokens, 0, (uint32_t)pk.derived[j].tokens.size()); pb.store(j); }
+      BZ_CHECK(pb.max_depth <= EVAL_STACK, "fixed sub-expression too deep for the evaluator stack");
+      BZ_CHECK(pb.code.size() * 4 <= 96 * 1024, "fixed sub-expression program too large for shared memory");
+      DevBuf d_code, d_rot, d_consts;
+      d_code.alloc(pb.code.size() * 4); d_rot.alloc(std::max<size_t>(1, pb.rot_table.size()) * 4); d_consts.alloc(std::max<size_t>(1, cs.consts.size()) * 32);
+      BZ_CUDA(cudaMemcpyAsync(d_code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice, st));
+      if (!pb.rot_table.empty()) BZ_CUDA(cudaMemcpyAsync(d_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice, st));
+      if (!cs.consts.empty()) BZ_CUDA(cudaMemcpyAsync(d_consts.p, cs.consts.data(), cs.consts.size() * 32, cudaMemcpyHostToDevice, st));
+      EvalArgs<FpP> a{};
+      a.code = (const uint32_t*)d_code.p; a.n_instr = (uint32_t)pb.code.size(); a.logN = pk.ext_k; a.rot = (const int32_t*)d_rot.p;
+      a.pbase = nullptr; a.pstride = 0; a.sbase = (const DFe*)pk.shcoset.p; a.consts = (const DFe*)d_consts.p; a.cstride = 0;
+      a.out = (DFe*)pk.shcoset.p + (size_t)(FM + 5) * en; a.ostride = 0; a.tev = nullptr; a.tn = 1;
+      static PerDeviceOnce once;
+      once.run(C->device, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+      eval_program_kernel<FpP><<<dim3((en + 127) / 128, 1), 128, pb.code.size() * 4, st>>>(a);
+      C->kernel_launches++;
+      BZ_CUDA(cudaGetLastError());
+      BZ_CUDA(cudaStreamSynchronize(st));
+    }
     {  // t_evaluations
       uint32_t tn = 1u << (pk.ext_k - cs.k);
       HFe orig = F.pow_u64(F.zeta(), n), step = F.pow_u64(pk.ext_omega, n), cur = orig;

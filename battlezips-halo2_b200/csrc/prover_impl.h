@@ -75,6 +75,13 @@ struct PkImpl {
   DevBuf lk_code, lk_rot, q_code[Q_TIERS], q_rot[Q_TIERS];
   uint32_t lk_ninstr = 0, q_ninstr[Q_TIERS] = {0, 0, 0}, q_muls[Q_TIERS] = {0, 0, 0};
   uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
+  // Gate polynomials as h(X) evaluates them: every maximal sub-expression over fixed columns and constants only that contains
+  // a product (after keygen's selector compression: q * prod_{i != r} (i - q), up to 8 multiplications per use) is evaluated
+  // ONCE per proving key on the extended coset and kept as a derived shared column (shcoset slot F + M + 5 + j); the gate
+  // polynomial queries it like a fixed column.  Same values at every point, so h(X) is unchanged.
+  std::vector<DerivedColumn> derived;
+  std::vector<Token> qtokens;
+  std::vector<uint32_t> qgate_off;
   // const table layout
   uint32_t C_ONE, C_THETA, C_BETA, C_GAMMA, C_Y, C_X, C_XN, C_X1, C_X2, C_X3, C_X4, C_XI, C_Z, C_U, C_UINV, C_BD0, C_ROT0, C_YP0, cstride;
   std::vector<int> rots;                 // distinct rotations of all queries (+1, -1, last)

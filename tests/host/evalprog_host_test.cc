@@ -24,6 +24,10 @@ static u64 hval(u64 kind, u64 col, long long rot) {           // pseudo-random v
   return z % P;
 }
 static std::vector<std::vector<Token>> pool;
+// derived columns (split_fixed_subexpressions): shared slots >= g_derived_base hold the value of their sub-expression
+static uint32_t g_derived_base = 0xffffffffu;
+static std::vector<u64> g_derived;
+static u64 sval(uint32_t slot, long long rot) { return slot >= g_derived_base ? g_derived[slot - g_derived_base] : hval(1, slot, rot); }
 
 static std::vector<Token> gen(int depth) {
   if (!pool.empty() && depth < 4 && rng() % 10 < 3) return pool[rng() % pool.size()];
@@ -58,7 +62,7 @@ static u64 eval_tokens(const std::vector<Token>& t, uint32_t lo, uint32_t hi, u6
     switch (k.op) {
       case 0: st.push_back(val_const[k.a]); break;
       case 1: st.push_back(hval(0, k.a, k.b)); break;
-      case 2: st.push_back(hval(1, k.a, k.b)); break;
+      case 2: st.push_back(sval(k.a, k.b)); break;
       case 3: st.push_back(hval(0, g_inst_base + k.a, k.b)); break;
       case 4: st.back() = subm(0, st.back()); break;
       case 5: { u64 r = st.back(); st.pop_back(); st.back() = addm(st.back(), r); break; }
@@ -75,7 +79,7 @@ static u64 run_program(const ProgBuilder& pb, u64& nmul) {
     const uint32_t op = ins & 15u, x = (ins >> 4) & 0xfffu, y = ins >> 16;
     switch (op) {
       case OP_PUSH_P: st[sp++] = hval(0, x, pb.rot_table[y]); break;
-      case OP_PUSH_S: st[sp++] = hval(1, x, pb.rot_table[y]); break;
+      case OP_PUSH_S: st[sp++] = sval(x, pb.rot_table[y]); break;
       case OP_PUSH_C: st[sp++] = val_const[ins >> 4]; break;
       case OP_ADD: --sp; st[sp - 1] = addm(st[sp - 1], st[sp]); break;
       case OP_SUB: --sp; st[sp - 1] = subm(st[sp - 1], st[sp]); break;
@@ -126,6 +130,14 @@ static int file_mode(const char* path) {
     u64 want = 0, naive = 0;
     for (size_t i = 0; i < eidx.size(); ++i) want = addm(want, mulm(eval_tokens(tokens, lo[i], hi[i], naive), val_const[YP0 + (E - 1 - eidx[i])]));
     naive += eidx.size();
+    // what the library does before compiling: fixed-only sub-expressions (compressed selectors) become derived columns
+    std::vector<DerivedColumn> derived; std::vector<Token> qtokens; std::vector<uint32_t> goff{0}, qoff;
+    for (size_t i = 0; i < eidx.size(); ++i) goff.push_back(hi[i]);
+    g_derived_base = 0xffffffffu; g_derived.clear();
+    split_fixed_subexpressions(tokens, goff, 2000, getenv("BZ_NO_DERIVED") == nullptr, derived, qtokens, qoff);
+    { u64 dm = 0; std::vector<u64> vals; for (const DerivedColumn& d : derived) vals.push_back(eval_tokens(d.tokens, 0, (uint32_t)d.tokens.size(), dm)); g_derived = vals; g_derived_base = 2000; }
+    tokens = qtokens;
+    for (size_t i = 0; i < eidx.size(); ++i) { lo[i] = qoff[i]; hi[i] = qoff[i + 1]; }
     GateDag dag; dag.advice_slot_of_instance = ibase; dag.canon_mul = dag.sort_rest = getenv("BZ_NO_CANON") == nullptr;
     for (size_t i = 0; i < eidx.size(); ++i) dag.add(tokens, lo[i], hi[i], eidx[i]);
     dag.plan();
@@ -135,7 +147,8 @@ static int file_mode(const char* path) {
     if (pb.max_depth > EVAL_STACK) { printf("tier %u: stack depth %d exceeds EVAL_STACK\n", tier, pb.max_depth); return 1; }
     u64 nm = 0; g_max_tmp = -1;
     if (run_program(pb, nm) != want) { printf("MISMATCH tier %u\n", tier); return 1; }
-    printf("tier %u polys %zu tree_muls %llu dag_muls %llu depth %d temporaries %d instructions %zu\n", tier, eidx.size(), naive, nm, pb.max_depth, g_max_tmp + 1, pb.code.size());
+    printf("tier %u polys %zu tree_muls %llu dag_muls %llu depth %d temporaries %d instructions %zu derived %zu\n", tier, eidx.size(), naive, nm, pb.max_depth, g_max_tmp + 1, pb.code.size(), derived.size());
+    g_derived_base = 0xffffffffu;
   }
   printf("ok\n");
   return 0;

@@ -65,16 +65,16 @@ def _dump_gates(cs, path):
 def test_gate_dag_compiler_on_the_shot_and_board_constraint_systems(tmp_path):
     """The real gate sets: the compiled programs are correct, fit the evaluator's stack (EVAL_STACK) and temporaries
     (EVAL_TMP), and the DAG saves multiplications in the tier that is evaluated on every point of the extended coset."""
-    from battlezips_halo2_b200.circuits import shot, board
+    from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
     exe = str(tmp_path / "evalprog_host_test")
     subprocess.run(["g++", "-O1", "-std=c++17", "-o", exe, os.path.join(HERE, "host", "evalprog_host_test.cc")], check=True)
-    for name, mod, npolys in (("shot", shot, 75), ("board", board, 129)):
-        cs, _ = mod.configure()
+    for name, make, npolys in (("shot", shot_circuit, 82), ("board", board_circuit, 141)):
+        cs = make(0)[0]                              # after selector compression: what keygen hands the device
         path = str(tmp_path / f"{name}.gates")
         assert _dump_gates(cs, path) == npolys
         out = subprocess.run([exe, path], capture_output=True, text=True).stdout.strip().splitlines()
         assert out[-1] == "ok", out
         rows = [dict(zip(l.split()[0::2], map(int, l.split()[1::2]))) for l in out[:-1]]
         print(name, rows)
-        assert rows[0]["dag_muls"] < 0.55 * rows[0]["tree_muls"] and rows[1]["dag_muls"] < 0.55 * rows[1]["tree_muls"]
+        assert rows[0]["dag_muls"] < 0.4 * rows[0]["tree_muls"] and rows[0]["derived"] >= 10          # compressed selectors leave the per-point program
         assert sum(r["dag_muls"] for r in rows) < sum(r["tree_muls"] for r in rows)

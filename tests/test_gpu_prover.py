@@ -61,7 +61,7 @@ def test_shot_proof_bytes_match_oracle(ctx):
     cs, cfg, asg = shot_circuit(0)
     job = Job(cs, asg)
     params, pk = job.device_keys(ctx)
-    assert pk.proof_size == 4672 and pk.num_random == 4238
+    assert pk.proof_size == 4000 and pk.num_random == 4238
     proofs = _prove(job, pk, [0, 7])
     for idx, proof in zip([0, 7], proofs):
         exp = job.oracle_proof(index=idx)
