@@ -41,6 +41,9 @@ def _declared_exports():
 EXPORTS = _declared_exports()
 
 
+ALLGATHER_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t)
+
+
 def load_library():
     """dlopen the CUDA library; fails loudly when it has not been built (no fallback path exists)."""
     global _lib
@@ -103,6 +106,9 @@ def load_library():
         "bz_ipa_fold": (i32, [vp, vp, vp, vp]),
         "bz_ipa_finish": (i32, [vp, vp, vp]),
         "bz_ipa_destroy": (None, [vp]),
+        "bz_quotient_program": (i32, [vp, u32, vp, u32, ctypes.POINTER(u32), vp, u32, ctypes.POINTER(u32), ctypes.POINTER(u64)]),
+        "bz_pk_quotient_generated": (i32, [vp, u32]),
+        "bz_ctx_set_sharding": (i32, [vp, u32, u32, vp, vp, ctypes.c_size_t, ALLGATHER_FN, vp]),
     }
     declared_elsewhere = {"bz_params_create", "bz_params_destroy", "bz_params_commit", "bz_pk_create", "bz_pk_destroy",
                           "bz_pk_num_random", "bz_pk_proof_size", "bz_pk_quotient_muls", "bz_create_proofs", "bz_pk_create_from_assembly", "bz_pk_vk_commitments", "bz_verify_proofs", "bz_params_commit_batch_dev"}     # bound in plonk/prover.py
@@ -155,6 +161,7 @@ class Context:
             raise BzError(rc, "bz_ctx_create failed (no CUDA device / driver?) -- the product has no CPU fallback")
         self.h = h
         self.device = device
+        self.stream_handle = stream
 
     def _check(self, rc):
         if rc != 0:
@@ -170,6 +177,33 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def set_sharding(self, rank, world, group=None, capacity=1 << 16):
+        """One large proof across `world` GPUs (bz_ctx_set_sharding): the exchange buffers are torch CUDA tensors and the
+        all-gather is torch.distributed's (NCCL), issued on the stream this context was created on (torch's current stream is
+        thread-local, and bz_create_proofs may be called from a worker thread)."""
+        if world <= 1:
+            self._check(self.lib.bz_ctx_set_sharding(self.h, 0, 1, None, None, 0, ALLGATHER_FN(0), None))
+            self._shard = None
+            return
+        import torch
+        import torch.distributed as dist
+        assert self.stream_handle, "sharding needs a context created on a caller-owned (torch) stream"
+        send = torch.zeros(capacity, dtype=torch.uint8, device=f"cuda:{self.device}")
+        recv = torch.zeros(capacity * world, dtype=torch.uint8, device=f"cuda:{self.device}")
+        stream = torch.cuda.ExternalStream(self.stream_handle, device=f"cuda:{self.device}")
+
+        def exchange(_user, nbytes):
+            try:
+                with torch.cuda.stream(stream):
+                    dist.all_gather_into_tensor(recv[: world * nbytes], send[:nbytes], group=group)
+                return 0
+            except Exception:      # noqa: BLE001  (reported through the C status code)
+                return -1
+        cb = ALLGATHER_FN(exchange)
+        self._shard = (send, recv, cb)          # keep the buffers and the callback alive
+        self._check(self.lib.bz_ctx_set_sharding(self.h, rank, world, ctypes.c_void_p(send.data_ptr()), ctypes.c_void_p(recv.data_ptr()),
+                                                 capacity, cb, None))
 
     def sync(self):
         self._check(self.lib.bz_sync(self.h))

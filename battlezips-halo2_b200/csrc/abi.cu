@@ -72,6 +72,17 @@ __attribute__((visibility("default"))) void bz_ctx_destroy(bz_ctx* ctx) {
   delete ctx;
 }
 
+__attribute__((visibility("default"))) int bz_ctx_set_sharding(bz_ctx* ctx, uint32_t rank, uint32_t world, void* d_send, void* d_recv, size_t capacity_per_rank,
+                                                               bz_allgather_fn exchange, void* user) {
+  BZ_TRY(ctx, {
+    BZ_CHECK(world >= 1 && rank < world, "bad rank / world");
+    BZ_CHECK(world == 1 || (d_send && d_recv && exchange && capacity_per_rank >= 96), "sharding needs exchange buffers and a callback");
+    bz::Ctx& c = ctx->c;
+    c.shard_rank = rank; c.shard_world = world; c.shard_send = d_send; c.shard_recv = d_recv; c.shard_cap = capacity_per_rank;
+    c.shard_exchange = exchange; c.shard_user = user;
+  });
+}
+
 __attribute__((visibility("default"))) const char* bz_last_error(bz_ctx* ctx) { return ctx ? ctx->c.last_error.c_str() : "null context"; }
 __attribute__((visibility("default"))) uint64_t bz_kernel_launches(bz_ctx* ctx) { return ctx ? ctx->c.kernel_launches : 0; }
 

@@ -103,6 +103,13 @@ struct Ctx {
   cudaStream_t big = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
+  // One large proof across the GPUs of a box (bz_ctx_set_sharding): every rank runs the same create_proof; the MSMs
+  // of a commitment batch are dealt out by column, or split by point range when there are fewer MSMs than ranks, and the
+  // 96-byte Jacobian results are exchanged by the caller's all-gather (NCCL) on this context's stream.
+  uint32_t shard_rank = 0, shard_world = 1;
+  void* shard_send = nullptr; void* shard_recv = nullptr; size_t shard_cap = 0;
+  int (*shard_exchange)(void*, size_t) = nullptr; void* shard_user = nullptr;
+
   const bzh::Field& field(int f) const { return f == 0 ? fp : fq; }
   ~Ctx();
 };

@@ -3,55 +3,76 @@
 // The reference algorithm (per-thread chunks, unsigned ceil(ln n)-bit windows, serial buckets) is
 // NOT followed: the result is a group element, canonical after to_affine, so any evaluation order
 // is bit-exact.  Here: signed-digit windows (2^(c-1) buckets per window),
-// counting sort of (window, bucket) keys with L2 atomics, one accumulator per bucket in XYZZ
+// counting sort of (window, bucket) keys with L2 atomics (hand-written: histogram, scan, scatter -- no library sort), one accumulator per bucket in XYZZ
 // coordinates (8M+2S mixed additions, complete formulas), chunk-parallel running-sum reduction
 // per window and a final Horner over the windows.  Everything is integer-pipe work (IMAD); the
 // only HBM traffic is 32 B/scalar + 64 B/point gathers.
 #include "common.h"
 #include "curve.cuh"
-#include <cub/device/device_radix_sort.cuh>
 
 namespace bz {
 
-// ---- 1. signed-digit decomposition: key = window * nb + (|digit| - 1) (W * nb for a zero digit), value = point
-// index | sign << 31 ---------------------------------------------------------------------------------------------
-template <class SP>
-__global__ void msm_digits_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W,
-                                  uint32_t nb, uint32_t* __restrict__ keys, uint32_t* __restrict__ vals) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  Fe<SP> s = fe_from_mont(fe_load(scalars + i));
+// ---- 1. counting sort of the non-zero signed digits by (window, bucket).  The key of a digit is  window * nb + (|digit| - 1),
+// its value the point index with the sign in bit 31.  Two passes over the scalars recompute the digits (one Montgomery
+// multiplication per scalar) instead of materialising and radix-sorting W * n (key, value) pairs:
+//   msm_hist_kernel     counts[key]++                      msm_scan_kernel (below)   offsets = exclusive scan of counts
+//   msm_scatter_kernel  sorted[offsets[key] + slot] = value, slot handed out by an atomic cursor per bucket
+// Lanes of a warp that hit the same bucket (witness-like scalars: a fifth of all scalars equal 1) are combined with
+// __match_any_sync, so a hot bucket costs one atomic per warp instead of 32 serialised ones.  The order inside a bucket is
+// whatever the atomics give; the bucket's SUM does not depend on it.
+template <class SP, class F>
+__device__ __forceinline__ void msm_for_each_digit(const Fe<SP>& canonical, uint32_t c, uint32_t W, uint32_t nb, F&& f) {
   uint32_t carry = 0;
   const uint32_t half = 1u << (c - 1), full = 1u << c;
   for (uint32_t w = 0; w < W; ++w) {
-    uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
+    const uint32_t bit = w * c, limb = bit >> 5, sh = bit & 31;
     uint32_t raw = 0;
     if (limb < 8) {
-      raw = s.l[limb] >> sh;
-      if (sh + c > 32 && limb + 1 < 8) raw |= s.l[limb + 1] << (32 - sh);
+      raw = canonical.l[limb] >> sh;
+      if (sh + c > 32 && limb + 1 < 8) raw |= canonical.l[limb + 1] << (32 - sh);
       raw &= full - 1;
     }
-    uint32_t v = raw + carry;
-    bool neg = v > half;
-    uint32_t d = neg ? full - v : v;
+    const uint32_t v = raw + carry;
+    const bool neg = v > half;
+    const uint32_t d = neg ? full - v : v;
     carry = neg ? 1u : 0u;
-    keys[(size_t)w * n + i] = d ? (w * nb + d - 1) : W * nb;    // zero digits: sentinel key = #buckets, sinks to the end
-    vals[(size_t)w * n + i] = i | (neg ? 0x80000000u : 0u);
+    f(d ? w * nb + d - 1 : 0xffffffffu, neg);          // every lane calls f for every window (warp-synchronous inside)
   }
 }
 
-// bucket boundaries in the sorted key array: offsets[b] = lower_bound(b), counts[b] = lower_bound(b + 1) - offsets[b]
-__global__ void msm_bounds_kernel(const uint32_t* __restrict__ sorted_keys, uint32_t items, uint32_t total_buckets,
-                                  uint32_t* __restrict__ offsets, uint32_t* __restrict__ counts) {
-  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= total_buckets) return;
-  uint32_t lo = 0, hi = items;
-  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < b) lo = mid + 1; else hi = mid; }
-  uint32_t start = lo;
-  hi = items;
-  while (lo < hi) { uint32_t mid = (lo + hi) >> 1; if (sorted_keys[mid] < b + 1) lo = mid + 1; else hi = mid; }
-  offsets[b] = start;
-  counts[b] = lo - start;
+template <class SP>
+__global__ void __launch_bounds__(256) msm_hist_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb, uint32_t* __restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  Fe<SP> s = fe_zero<SP>();
+  if (i < n) s = fe_from_mont(fe_load(scalars + i));
+  msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool) {
+    // uniform scalars: 32 distinct keys per warp, one atomic each.  Only when neighbouring lanes collide (skewed scalars) is the
+    // warp's traffic to a bucket combined -- __match_any_sync costs one step per distinct key, too slow for the common case
+    const bool dup = key != 0xffffffffu && key == __shfl_xor_sync(0xffffffffu, key, 1);
+    if (__any_sync(0xffffffffu, dup)) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      if (key != 0xffffffffu && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
+    } else if (key != 0xffffffffu) atomicAdd(&counts[key], 1u);
+  });
+}
+
+template <class SP>
+__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
+                                                          uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  Fe<SP> s = fe_zero<SP>();
+  if (i < n) s = fe_from_mont(fe_load(scalars + i));
+  msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool neg) {
+    const bool dup = key != 0xffffffffu && key == __shfl_xor_sync(0xffffffffu, key, 1);
+    if (__any_sync(0xffffffffu, dup)) {
+      const uint32_t peers = __match_any_sync(0xffffffffu, key);
+      const uint32_t leader = (uint32_t)(__ffs((int)peers) - 1);
+      uint32_t base = 0;
+      if (key != 0xffffffffu && lane == leader) base = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if (key != 0xffffffffu) sorted[base + __popc(peers & ((1u << lane) - 1u))] = i | (neg ? 0x80000000u : 0u);
+    } else if (key != 0xffffffffu) sorted[atomicAdd(&cursor[key], 1u)] = i | (neg ? 0x80000000u : 0u);
+  });
 }
 
 // ---- 2. exclusive scan of bucket counts over all windows (single CTA; W*nb <= 2^21) ------------
@@ -249,17 +270,22 @@ __global__ void jac_to_affine_kernel(const Jac<BP>* __restrict__ in, Affine<BP>*
   fe_store(&out[i].x, r.x); fe_store(&out[i].y, r.y);
 }
 
+// Window size by a cost model in mixed additions: W(c) * (n + 2.8 * 2^(c-1)) -- one mixed addition per non-zero digit plus two
+// full additions (14 instead of 10 multiplications each) per bucket in the running-sum reduction -- over the windows whose top
+// digit is either empty or holds at least c/2 real bits of the 255-bit scalar (a top window of a few bits would pile all points
+// into a handful of buckets).  A point-range shard of a large MSM (multi-GPU split) picks the window for ITS n.
 static uint32_t pick_window(uint32_t n) {
-  uint32_t lg = 0;
-  while ((1ull << (lg + 1)) <= n) ++lg;
-  int c = (int)lg - 2;
-  if (c < 4) c = 4;
-  if (c > 16) c = 16;
-  // avoid windows whose top digit has only a few significant bits of the 255-bit scalar (all points would pile into
-  // a handful of buckets): require the last window to hold >= c/2 real bits or none
   auto top_bits = [](int cc) { int W = (256 + cc - 1) / cc; return 255 - (W - 1) * cc; };
-  while (c > 4) { int tb = top_bits(c); if (tb <= 0 || tb >= c / 2) break; --c; }
-  return (uint32_t)c;
+  uint32_t best = 4;
+  double best_cost = 1e300;
+  for (int c = 4; c <= 16; ++c) {
+    const int tb = top_bits(c);
+    if (c > 4 && tb > 0 && tb < c / 2) continue;
+    const double W = (256 + c - 1) / c;
+    const double cost = W * ((double)n + 2.8 * (double)(1u << (c - 1)));
+    if (cost < best_cost) { best_cost = cost; best = (uint32_t)c; }
+  }
+  return best;
 }
 
 template <class BP, class SP>
@@ -281,25 +307,18 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   const uint32_t items = (uint32_t)items64;
   uint32_t splits = nb >= 4096 ? nb / 2048 : 1;                  // CTAs per window in the reduction
   // scratch layout
-  size_t temp_bytes = 0;
-  cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                  (uint32_t*)nullptr, (int)items, 0, 32, st);
   uint32_t max_segs = (uint32_t)(items64 / SEG + total);
-  ctx->scratch[0].ensure((size_t)items * 4 * 2);                  // keys, vals
-  ctx->scratch[1].ensure((size_t)items * 4 * 2 + temp_bytes + 256);   // sorted keys, sorted vals, cub temp
+  ctx->scratch[0].ensure((size_t)items * 4);                      // point indices grouped by (window, bucket)
   const uint32_t max_large = (uint32_t)(items64 / (SEG * FOLD_SERIAL_MAX) + 1);
-  ctx->scratch[2].ensure((size_t)total * 4 * 4 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4);
+  ctx->scratch[2].ensure((size_t)total * 4 * 5 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4);
   ctx->scratch[3].ensure((size_t)(total + W * splits + W + max_segs) * sizeof(Xyzz<BP>));
-  uint32_t* keys = ctx->scratch[0].as<uint32_t>();
-  uint32_t* vals = keys + items;
-  uint32_t* skeys = ctx->scratch[1].as<uint32_t>();
-  uint32_t* sorted = skeys + items;
-  void* cub_temp = (void*)(((uintptr_t)(sorted + items) + 255) & ~(uintptr_t)255);
+  uint32_t* sorted = ctx->scratch[0].as<uint32_t>();
   uint32_t* counts = ctx->scratch[2].as<uint32_t>();
   uint32_t* offsets = counts + total;
   uint32_t* nseg = offsets + total;
   uint32_t* segoff = nseg + total;
-  uint32_t* seg_bucket = segoff + total;
+  uint32_t* cursor = segoff + total;
+  uint32_t* seg_bucket = cursor + total;
   uint32_t* large_count = seg_bucket + max_segs;
   uint32_t* large_list = large_count + 4;
   Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
@@ -308,12 +327,11 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   Xyzz<BP>* partial = wsums + W;
 
   { ProfScope p(ctx, PROF_MSM_DIGITS);
-    msm_digits_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, keys, vals); }
+    BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)total * 4, st));
+    msm_hist_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, counts); }
   { ProfScope p(ctx, PROF_MSM_SORT);
-    // radix sort of (bucket key, point) pairs over just the bits a key can have
-    int end_bit = 1; while ((1u << end_bit) <= total) ++end_bit;
-    cub::DeviceRadixSort::SortPairs(cub_temp, temp_bytes, (const uint32_t*)keys, skeys, (const uint32_t*)vals, sorted, (int)items, 0, end_bit, st);
-    msm_bounds_kernel<<<(total + 255) / 256, 256, 0, st>>>(skeys, items, total, offsets, counts);
+    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
+    msm_scatter_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, cursor, sorted);
     BZ_CUDA(cudaMemsetAsync(large_count, 0, 16, st));
     msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg, large_count, large_list, max_large);
     msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*scratch copy, overwritten below*/, total);

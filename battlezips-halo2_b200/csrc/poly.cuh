@@ -235,7 +235,7 @@ __global__ void __launch_bounds__(LKP_THREADS) lookup_permute_kernel(Regions reg
     }
     bool ok = lo < usable;
     if (ok) { const uint4* q = reinterpret_cast<const uint4*>(T + lo); ok = key_eq(q[0], q[1], a0, a1); }
-    if (ok) removed[lo] = 1; else atomicOr(err, 1u);    // Error::ConstraintSystemFailure: input not in the table
+    if (ok) removed[lo] = 1; else atomicOr(err + b, 1u);    // Error::ConstraintSystemFailure: input not in the table (one error word per proof)
   }
   __syncthreads();
   for (uint32_t i = tid; i < n; i += LKP_THREADS) removed[i] = (i < usable && !removed[i]) ? 1u : 0u;    // now: "kept"
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(LKP_THREADS) lookup_permute_kernel(Regions reg
   }
   __syncthreads();
   const uint32_t n_rep = block_exclusive_scan(repeat, n, wsum);
-  if (n_rep != n_left) { if (tid == 0) atomicOr(err, 2u); return; }
+  if (n_rep != n_left) { if (tid == 0) atomicOr(err + b, 2u); return; }
   // 4. S'
   for (uint32_t i = tid; i < usable; i += LKP_THREADS) {
     const uint32_t nxt = (i + 1 < n) ? repeat[i + 1] : n_rep;

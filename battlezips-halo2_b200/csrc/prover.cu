@@ -73,7 +73,7 @@ static void push_column(ProgBuilder& pb, const PkImpl& pk, std::pair<uint32_t, u
   else pb.pp(pk.slot_inst(col.second), 0);
 }
 
-static void build_programs(Ctx* ctx, PkImpl& pk) {
+static void build_programs(PkImpl& pk) {
   const CircuitCopy& cs = pk.cs;
   // ---- lookup compression on the Lagrange domain: outputs 2l (input), 2l+1 (table)
   {
@@ -84,13 +84,8 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
     }
     BZ_CHECK(pb.max_depth <= EVAL_STACK, "lookup expression too deep for the evaluator stack");
     pk.lk_ninstr = (uint32_t)pb.code.size();
-    if (pk.lk_ninstr) {
-      pk.lk_code.alloc(pb.code.size() * 4);
-      BZ_CUDA(cudaMemcpy(pk.lk_code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
-      if (pb.rot_table.empty()) pb.rot_table.push_back(0);
-      pk.lk_rot.alloc(pb.rot_table.size() * 4);
-      BZ_CUDA(cudaMemcpy(pk.lk_rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
-    }
+    if (pb.rot_table.empty()) pb.rot_table.push_back(0);
+    pk.h_lk_code = pb.code; pk.h_lk_rot = pb.rot_table;
   }
   // ---- h(X) on the extended coset:  N(X) = sum_e y^(E-1-e) expr_e(X),  h = N / t.
   // Every expr_e of a satisfying witness vanishes on the whole domain, so it is divisible by t(X) = X^n - 1 on its own and
@@ -204,9 +199,9 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       pb.code.push_back(OP_MUL_T_STORE);
       return true;
     };
-    auto build = [&](uint32_t tier, DevBuf& code, DevBuf& rot, uint32_t& ninstr) {
+    auto build = [&](uint32_t tier, uint32_t& ninstr) {
       ProgBuilder pb;
-      ninstr = 0; pk.q_muls[tier] = 0;
+      ninstr = 0; pk.q_muls[tier] = 0; pk.h_q_code[tier].clear(); pk.h_q_rot[tier].clear();
       if (!compile(tier, 0, pb)) return;
       for (int variant = 1; use_dag && variant <= 2; ++variant) {            // re-association can win or lose sharing: keep the cheapest program
         ProgBuilder alt;
@@ -217,14 +212,25 @@ static void build_programs(Ctx* ctx, PkImpl& pk) {
       ninstr = (uint32_t)pb.code.size();
       pk.q_muls[tier] = count_muls(pb);
       BZ_CHECK(ninstr * 4 <= 96 * 1024, "quotient program too large for shared memory");
-      code.alloc(pb.code.size() * 4);
-      BZ_CUDA(cudaMemcpy(code.p, pb.code.data(), pb.code.size() * 4, cudaMemcpyHostToDevice));
       if (pb.rot_table.empty()) pb.rot_table.push_back(0);
-      rot.alloc(pb.rot_table.size() * 4);
-      BZ_CUDA(cudaMemcpy(rot.p, pb.rot_table.data(), pb.rot_table.size() * 4, cudaMemcpyHostToDevice));
+      pk.h_q_code[tier] = pb.code; pk.h_q_rot[tier] = pb.rot_table;
     };
-    for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) build(t, pk.q_code[t], pk.q_rot[t], pk.q_ninstr[t]);
+    for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) build(t, pk.q_ninstr[t]);
     BZ_CHECK(pk.q_ninstr[0] > 0, "internal: no full-degree term in h(X)");
+  }
+}
+
+// programs -> device; the circuit-specialised straight-line kernel of a tier is looked up by the hash of its program
+static void upload_programs(PkImpl& pk) {
+  auto up = [](DevBuf& d, const void* src, size_t bytes) { if (bytes) { d.alloc(bytes); BZ_CUDA(cudaMemcpy(d.p, src, bytes, cudaMemcpyHostToDevice)); } };
+  up(pk.lk_code, pk.h_lk_code.data(), pk.h_lk_code.size() * 4);
+  up(pk.lk_rot, pk.h_lk_rot.data(), pk.h_lk_rot.size() * 4);
+  const char* env = getenv("BZ_QUOTIENT_GENERATED");            // =0: always the interpreter (A/B)
+  const bool use_gen = !(env && atoi(env) == 0);
+  for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) {
+    up(pk.q_code[t], pk.h_q_code[t].data(), pk.h_q_code[t].size() * 4);
+    up(pk.q_rot[t], pk.h_q_rot[t].data(), pk.h_q_rot[t].size() * 4);
+    pk.q_gen[t] = use_gen && pk.q_ninstr[t] ? find_generated_quotient(program_hash(pk.h_q_code[t], pk.h_q_rot[t])) : nullptr;
   }
 }
 
@@ -273,7 +279,7 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.nd.alloc(4 * (size_t)std::max<uint32_t>(1, pk.nsets + pk.L) * B * n * E);       // num, den, prefix(num), suffix(den) of every grand product
   w.consts.alloc(B * (size_t)pk.cstride * E);
   // commitment requests per proof in one call: advice columns, 2 per lookup, grand products, the h pieces (or 2 IPA terms)
-  const size_t max_req = std::max<size_t>(std::max<size_t>(pk.cs.G, pk.cs.I), std::max<size_t>(std::max<size_t>(2 * pk.L, pk.nsets + pk.L), std::max<size_t>(pk.qdeg, 2)));
+  const size_t max_req = std::max<size_t>((size_t)pk.cs.G + pk.cs.I, std::max<size_t>(std::max<size_t>(2 * pk.L, pk.nsets + pk.L), std::max<size_t>(pk.qdeg, 2)));
   w.extras.alloc(B * max_req * 2 * E);
   w.evalout.alloc(B * (pk.evals.size() + pk.point_sets.size() + 8) * E);
   w.commits.alloc(B * max_req * 128);
@@ -281,8 +287,9 @@ static void ensure_work(Ctx* ctx, PkImpl& pk, uint32_t B) {
   w.descs.alloc(64 * 1024);
   w.adv_in.alloc(1);
   w.lk_sorted.alloc(std::max<size_t>(1, (size_t)B * pk.L * n * E));
-  w.lk_err.alloc(64);
-  if (!w.h_err) BZ_CUDA(cudaMallocHost(&w.h_err, 64));
+  w.lk_err.alloc((size_t)B * 4 + 64);
+  if (w.h_err) cudaFreeHost(w.h_err);
+  BZ_CUDA(cudaMallocHost(&w.h_err, (size_t)B * 4 + 64));
   if (w.h_pinned) cudaFreeHost(w.h_pinned);
   w.h_pinned_bytes = std::max<size_t>(B * std::max<size_t>(2 * n * E * std::max<uint32_t>(1, pk.L), std::max<size_t>(max_req * 128, (pk.evals.size() + 16) * E)), 1 << 20);
   BZ_CUDA(cudaMallocHost(&w.h_pinned, w.h_pinned_bytes));
@@ -423,6 +430,151 @@ API uint32_t bz_pk_quotient_muls(const bz_pk* pk, uint32_t tier, uint32_t* point
   return pk->p.q_muls[tier];
 }
 
+// Everything of keygen_pk's image that needs no GPU: the flattened constraint system, domain constants, the layouts of the per-proof
+// constants / randomness / polynomial slots, the query and evaluation lists, the multiopen structure and the compiled programs.
+// (Also what bz_quotient_program runs at build time to emit the circuit-specialised kernels.)
+static void pk_host_setup(const bzh::Field& F, PkImpl& pk, const bz_circuit* cin) {
+  CircuitCopy& cs = pk.cs;
+  cs.k = cin->k; cs.G = cin->num_advice; cs.F = cin->num_fixed; cs.I = cin->num_instance; cs.degree = cin->degree; cs.bf = cin->blinding_factors;
+  for (uint32_t i = 0; i < cin->n_advice_queries; ++i) cs.aq.push_back({cin->advice_queries[2 * i], cin->advice_queries[2 * i + 1]});
+  for (uint32_t i = 0; i < cin->n_fixed_queries; ++i) cs.fq.push_back({cin->fixed_queries[2 * i], cin->fixed_queries[2 * i + 1]});
+  for (uint32_t i = 0; i < cin->n_instance_queries; ++i) cs.iq.push_back({cin->instance_queries[2 * i], cin->instance_queries[2 * i + 1]});
+  for (uint32_t i = 0; i < cin->n_perm_columns; ++i) cs.perm.push_back({cin->perm_columns[2 * i], cin->perm_columns[2 * i + 1]});
+  cs.consts.resize(cin->n_constants);
+  if (cin->n_constants) memcpy(cs.consts.data(), cin->constants, (size_t)cin->n_constants * 32);
+  cs.tokens.resize(cin->n_tokens);
+  for (uint32_t i = 0; i < cin->n_tokens; ++i) cs.tokens[i] = Token{cin->tokens[i].op, cin->tokens[i].a, cin->tokens[i].b};
+  cs.gate_off.assign(cin->gate_poly_offsets, cin->gate_poly_offsets + cin->n_gate_polys + 1);
+  {
+    uint32_t e = 0;
+    for (uint32_t l = 0; l < cin->n_lookups; ++l) {
+      CircuitCopy::Lookup lk;
+      for (uint32_t j = 0; j < cin->lookup_input_counts[l]; ++j, ++e) lk.inputs.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
+      for (uint32_t j = 0; j < cin->lookup_table_counts[l]; ++j, ++e) lk.tables.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
+      cs.lookups.push_back(lk);
+    }
+  }
+  {
+    uint64_t raw[4]; memcpy(raw, cin->vk_transcript_repr, 32);
+    cs.vk_repr = F.from_raw(raw);
+  }
+  BZ_CHECK(cs.degree >= 3, "cs degree must be >= 3");
+  pk.n = 1u << cs.k;
+  pk.qdeg = cs.degree - 1;
+  pk.ext_k = cs.k;
+  while ((1ull << pk.ext_k) < (uint64_t)pk.n * pk.qdeg) ++pk.ext_k;
+  pk.ext_n = 1u << pk.ext_k;
+  pk.M = (uint32_t)cs.perm.size(); pk.L = (uint32_t)cs.lookups.size();
+  pk.chunk_len = cs.degree - 2;
+  pk.nsets = pk.M ? (pk.M + pk.chunk_len - 1) / pk.chunk_len : 0;
+  pk.NS = cs.G + cs.I + 3 * pk.L + pk.nsets;
+  pk.NC = (uint32_t)cs.consts.size();
+  pk.usable = pk.n - (cs.bf + 1);
+  BZ_CHECK(pk.chunk_len <= 8, "permutation chunk too wide");
+  // domain constants
+  pk.ext_omega = F.root_of_unity();
+  for (uint32_t i = pk.ext_k; i < 32; ++i) pk.ext_omega = F.sqr(pk.ext_omega);
+  pk.omega = pk.ext_omega;
+  for (uint32_t i = cs.k; i < pk.ext_k; ++i) pk.omega = F.sqr(pk.omega);
+  pk.omega_inv = F.inv(pk.omega);
+  const uint32_t n = pk.n;
+  derive_fixed_subexpressions(pk);
+  // ---- const table layout
+  uint32_t c = pk.NC;
+  pk.C_ONE = c++; pk.C_THETA = c++; pk.C_BETA = c++; pk.C_GAMMA = c++; pk.C_Y = c++; pk.C_X = c++; pk.C_XN = c++;
+  pk.C_X1 = c++; pk.C_X2 = c++; pk.C_X3 = c++; pk.C_X4 = c++; pk.C_XI = c++; pk.C_Z = c++; pk.C_U = c++; pk.C_UINV = c++;
+  pk.C_BD0 = c; c += pk.M;
+  {
+    std::set<int> rs;
+    for (auto& q : cs.aq) rs.insert(q.second);
+    for (auto& q : cs.fq) rs.insert(q.second);
+    for (auto& q : cs.iq) rs.insert(q.second);
+    rs.insert(0); rs.insert(1); rs.insert(-1); rs.insert(-((int)cs.bf + 1));
+    pk.C_ROT0 = c;
+    for (int r : rs) { pk.rots.push_back(r); pk.rot_const[r] = c++; }
+  }
+  pk.n_exprs = cin->n_gate_polys + (pk.nsets ? 2 + (pk.nsets - 1) + pk.nsets : 0) + 5 * pk.L;
+  pk.C_YP0 = c; c += pk.n_exprs + 1;          // y^0 .. y^E
+  pk.cstride = c;
+  // ---- randomness layout
+  uint32_t r = 0;
+  pk.r_adv_rows = r; r += cs.G * (cs.bf + 1);
+  pk.r_adv_blind = r; r += cs.G;
+  pk.r_lk0 = r; r += pk.L * (2 * (cs.bf + 1) + 2);
+  pk.r_perm0 = r; r += pk.nsets * (cs.bf + 1);
+  pk.r_lkz0 = r; r += pk.L * (cs.bf + 1);
+  pk.r_randpoly = r; r += n;
+  pk.r_rand_blind = r; r += 1;
+  pk.r_hblind = r; r += pk.qdeg;
+  pk.r_qprime = r; r += 1;
+  pk.r_spoly = r; r += n;
+  pk.r_sblind = r; r += 1;
+  pk.r_ipa = r; r += 2 * cs.k;
+  pk.R = r;
+  // ---- MISC slots
+  uint32_t m = 0;
+  pk.m_cin0 = m; m += 2 * pk.L;
+  pk.m_hpoly = m++;
+  // ---- queries.  blind slots: advice[G], lookup (A',S',Z)[3L], perm[nsets], h, random
+  auto b_adv = [&](uint32_t g) { return (int)g; };
+  auto b_lk = [&](uint32_t l, uint32_t w) { return (int)(cs.G + 3 * l + w); };
+  auto b_pz = [&](uint32_t s) { return (int)(cs.G + 3 * pk.L + s); };
+  const int b_h = (int)(cs.G + 3 * pk.L + pk.nsets), b_rand = b_h + 1;
+  pk.nblinds = b_rand + 1;
+  const int last_rot = -((int)cs.bf + 1);
+  // positions in the proof's evaluation list (same order as the `ev(...)` pushes below; steps 14-18)
+  const int e_adv0 = (int)cs.iq.size(), e_fix0 = e_adv0 + (int)cs.aq.size(), e_rand = e_fix0 + (int)cs.fq.size(), e_sig0 = e_rand + 1;
+  const int e_perm0 = e_sig0 + (int)pk.M;
+  auto e_perm = [&](uint32_t s2) { return e_perm0 + 3 * (int)s2; };                     // z, z_next, (z_last: all but the last set)
+  const int e_lk0 = e_perm0 + (pk.nsets ? 3 * (int)pk.nsets - 1 : 0);
+  for (size_t i = 0; i < cs.iq.size(); ++i) add_query(pk, cid_inst + cs.iq[i].first, cs.iq[i].second, PolyRef{R_POLY, pk.slot_inst(cs.iq[i].first)}, 0, 0, (int)i);
+  for (size_t i = 0; i < cs.aq.size(); ++i) add_query(pk, cid_adv + cs.aq[i].first, cs.aq[i].second, PolyRef{R_POLY, (uint32_t)cs.aq[i].first}, 1, b_adv(cs.aq[i].first), e_adv0 + (int)i);
+  for (uint32_t s2 = 0; s2 < pk.nsets; ++s2) {
+    add_query(pk, cid_pz + s2, 0, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2));
+    add_query(pk, cid_pz + s2, 1, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2) + 1);
+  }
+  for (int s2 = (int)pk.nsets - 2; s2 >= 0; --s2) add_query(pk, cid_pz + s2, last_rot, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2) + 2);
+  for (uint32_t l = 0; l < pk.L; ++l) {
+    const int e = e_lk0 + 5 * (int)l;                                                   // z, z_next, a, a_inv, s
+    add_query(pk, cid_lk + 3 * l + 2, 0, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2), e);
+    add_query(pk, cid_lk + 3 * l + 0, 0, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0), e + 2);
+    add_query(pk, cid_lk + 3 * l + 1, 0, PolyRef{R_POLY, pk.slot_lk(l, 1)}, 1, b_lk(l, 1), e + 4);
+    add_query(pk, cid_lk + 3 * l + 0, -1, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0), e + 3);
+    add_query(pk, cid_lk + 3 * l + 2, 1, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2), e + 1);
+  }
+  for (size_t i = 0; i < cs.fq.size(); ++i) add_query(pk, cid_fix + cs.fq[i].first, cs.fq[i].second, PolyRef{R_SHPOLY, (uint32_t)cs.fq[i].first}, 0, 0, e_fix0 + (int)i);
+  for (uint32_t j = 0; j < pk.M; ++j) add_query(pk, cid_sig + j, 0, PolyRef{R_SHPOLY, cs.F + j}, 0, 0, e_sig0 + (int)j);
+  add_query(pk, cid_h, 0, PolyRef{R_MISC, pk.m_hpoly}, 1, b_h, -1);
+  add_query(pk, cid_rand, 0, PolyRef{R_RANDPOLY, 0}, 1, b_rand, e_rand);
+  build_multiopen(pk);
+  const uint32_t nps = (uint32_t)pk.point_sets.size();
+  pk.m_qset0 = m; m += nps;
+  pk.m_qtmp0 = m; m += 2 * nps;
+  pk.m_qprime = m++; pk.m_ppoly = m++; pk.m_pprime = m++; pk.m_b = m++; pk.m_coef = m++; pk.m_scl = m++; pk.m_scr = m++;
+  pk.NM = m;
+  // ---- evaluation list in transcript order (steps 14-18)
+  auto ev = [&](PolyRef p, int rot) { pk.evals.push_back(EvalQuery{p, pk.rot_const.at(rot)}); };
+  for (auto& q : cs.iq) ev(PolyRef{R_POLY, pk.slot_inst(q.first)}, q.second);
+  for (auto& q : cs.aq) ev(PolyRef{R_POLY, (uint32_t)q.first}, q.second);
+  for (auto& q : cs.fq) ev(PolyRef{R_SHPOLY, (uint32_t)q.first}, q.second);
+  ev(PolyRef{R_RANDPOLY, 0}, 0);
+  for (uint32_t j = 0; j < pk.M; ++j) ev(PolyRef{R_SHPOLY, cs.F + j}, 0);
+  for (uint32_t s = 0; s < pk.nsets; ++s) {
+    ev(PolyRef{R_POLY, pk.slot_pz(s)}, 0); ev(PolyRef{R_POLY, pk.slot_pz(s)}, 1);
+    if (s + 1 != pk.nsets) ev(PolyRef{R_POLY, pk.slot_pz(s)}, last_rot);
+  }
+  for (uint32_t l = 0; l < pk.L; ++l) {
+    ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1);
+    ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, -1);
+    ev(PolyRef{R_POLY, pk.slot_lk(l, 1)}, 0);
+  }
+  // proof size: points (32 B) + scalars (32 B)
+  uint32_t npoints = cs.G + 2 * pk.L + pk.nsets + pk.L + 1 + pk.qdeg + 1 + 1 + 2 * cs.k;
+  uint32_t nscalars = (uint32_t)pk.evals.size() + nps + 2;
+  pk.proof_size = 32 * (npoints + nscalars);
+  build_programs(pk);
+}
+
 static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin, const void* fixed_values, const void* sigma_values,
                           const uint32_t* mapping, bz_pk** out) {
   PV_TRY(ctx, {
@@ -434,50 +586,9 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
     PkImpl& pk = h->p;
     pk.params = &params->p;
     const bzh::Field& F = C->fp;
-    CircuitCopy& cs = pk.cs;
-    cs.k = cin->k; cs.G = cin->num_advice; cs.F = cin->num_fixed; cs.I = cin->num_instance; cs.degree = cin->degree; cs.bf = cin->blinding_factors;
-    for (uint32_t i = 0; i < cin->n_advice_queries; ++i) cs.aq.push_back({cin->advice_queries[2 * i], cin->advice_queries[2 * i + 1]});
-    for (uint32_t i = 0; i < cin->n_fixed_queries; ++i) cs.fq.push_back({cin->fixed_queries[2 * i], cin->fixed_queries[2 * i + 1]});
-    for (uint32_t i = 0; i < cin->n_instance_queries; ++i) cs.iq.push_back({cin->instance_queries[2 * i], cin->instance_queries[2 * i + 1]});
-    for (uint32_t i = 0; i < cin->n_perm_columns; ++i) cs.perm.push_back({cin->perm_columns[2 * i], cin->perm_columns[2 * i + 1]});
-    cs.consts.resize(cin->n_constants);
-    if (cin->n_constants) memcpy(cs.consts.data(), cin->constants, (size_t)cin->n_constants * 32);
-    cs.tokens.resize(cin->n_tokens);
-    for (uint32_t i = 0; i < cin->n_tokens; ++i) cs.tokens[i] = Token{cin->tokens[i].op, cin->tokens[i].a, cin->tokens[i].b};
-    cs.gate_off.assign(cin->gate_poly_offsets, cin->gate_poly_offsets + cin->n_gate_polys + 1);
-    {
-      uint32_t e = 0;
-      for (uint32_t l = 0; l < cin->n_lookups; ++l) {
-        CircuitCopy::Lookup lk;
-        for (uint32_t j = 0; j < cin->lookup_input_counts[l]; ++j, ++e) lk.inputs.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
-        for (uint32_t j = 0; j < cin->lookup_table_counts[l]; ++j, ++e) lk.tables.push_back({cin->lookup_expr_offsets[e], cin->lookup_expr_offsets[e + 1]});
-        cs.lookups.push_back(lk);
-      }
-    }
-    {
-      uint64_t raw[4]; memcpy(raw, cin->vk_transcript_repr, 32);
-      cs.vk_repr = F.from_raw(raw);
-    }
-    BZ_CHECK(cs.degree >= 3, "cs degree must be >= 3");
-    pk.n = 1u << cs.k;
-    pk.qdeg = cs.degree - 1;
-    pk.ext_k = cs.k;
-    while ((1ull << pk.ext_k) < (uint64_t)pk.n * pk.qdeg) ++pk.ext_k;
-    pk.ext_n = 1u << pk.ext_k;
-    pk.M = (uint32_t)cs.perm.size(); pk.L = (uint32_t)cs.lookups.size();
-    pk.chunk_len = cs.degree - 2;
-    pk.nsets = pk.M ? (pk.M + pk.chunk_len - 1) / pk.chunk_len : 0;
-    pk.NS = cs.G + cs.I + 3 * pk.L + pk.nsets;
-    pk.NC = (uint32_t)cs.consts.size();
-    pk.usable = pk.n - (cs.bf + 1);
-    BZ_CHECK(pk.chunk_len <= 8, "permutation chunk too wide");
+    pk_host_setup(C->fp, pk, cin);
+    const CircuitCopy& cs = pk.cs;
     const uint32_t n = pk.n, en = pk.ext_n;
-    // domain constants
-    pk.ext_omega = F.root_of_unity();
-    for (uint32_t i = pk.ext_k; i < 32; ++i) pk.ext_omega = F.sqr(pk.ext_omega);
-    pk.omega = pk.ext_omega;
-    for (uint32_t i = cs.k; i < pk.ext_k; ++i) pk.omega = F.sqr(pk.omega);
-    pk.omega_inv = F.inv(pk.omega);
     cudaStream_t st = C->stream;
     // ---- Lagrange images, polys, cosets
     const uint32_t FM = cs.F + pk.M;
@@ -500,7 +611,6 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
       C->kernel_launches += 2;
       BZ_CUDA(cudaStreamSynchronize(st));
     }
-    derive_fixed_subexpressions(pk);
     const uint32_t ND = (uint32_t)pk.derived.size();
     pk.shpoly.alloc((size_t)std::max(1u, FM) * n * 32);
     pk.shcoset.alloc((size_t)(FM + 5 + ND) * en * 32);
@@ -555,102 +665,9 @@ static int pk_create_impl(bz_ctx* ctx, bz_params* params, const bz_circuit* cin,
       BZ_CUDA(cudaMemcpyAsync(pk.tev.p, t.data(), (size_t)tn * 32, cudaMemcpyHostToDevice, st));
       BZ_CUDA(cudaStreamSynchronize(st));
     }
-    // ---- const table layout
-    uint32_t c = pk.NC;
-    pk.C_ONE = c++; pk.C_THETA = c++; pk.C_BETA = c++; pk.C_GAMMA = c++; pk.C_Y = c++; pk.C_X = c++; pk.C_XN = c++;
-    pk.C_X1 = c++; pk.C_X2 = c++; pk.C_X3 = c++; pk.C_X4 = c++; pk.C_XI = c++; pk.C_Z = c++; pk.C_U = c++; pk.C_UINV = c++;
-    pk.C_BD0 = c; c += pk.M;
-    {
-      std::set<int> rs;
-      for (auto& q : cs.aq) rs.insert(q.second);
-      for (auto& q : cs.fq) rs.insert(q.second);
-      for (auto& q : cs.iq) rs.insert(q.second);
-      rs.insert(0); rs.insert(1); rs.insert(-1); rs.insert(-((int)cs.bf + 1));
-      pk.C_ROT0 = c;
-      for (int r : rs) { pk.rots.push_back(r); pk.rot_const[r] = c++; }
-    }
-    pk.n_exprs = cin->n_gate_polys + (pk.nsets ? 2 + (pk.nsets - 1) + pk.nsets : 0) + 5 * pk.L;
-    pk.C_YP0 = c; c += pk.n_exprs + 1;          // y^0 .. y^E
-    pk.cstride = c;
-    // ---- randomness layout
-    uint32_t r = 0;
-    pk.r_adv_rows = r; r += cs.G * (cs.bf + 1);
-    pk.r_adv_blind = r; r += cs.G;
-    pk.r_lk0 = r; r += pk.L * (2 * (cs.bf + 1) + 2);
-    pk.r_perm0 = r; r += pk.nsets * (cs.bf + 1);
-    pk.r_lkz0 = r; r += pk.L * (cs.bf + 1);
-    pk.r_randpoly = r; r += n;
-    pk.r_rand_blind = r; r += 1;
-    pk.r_hblind = r; r += pk.qdeg;
-    pk.r_qprime = r; r += 1;
-    pk.r_spoly = r; r += n;
-    pk.r_sblind = r; r += 1;
-    pk.r_ipa = r; r += 2 * cs.k;
-    pk.R = r;
-    // ---- MISC slots
-    uint32_t m = 0;
-    pk.m_cin0 = m; m += 2 * pk.L;
-    pk.m_hpoly = m++;
-    // ---- queries.  blind slots: advice[G], lookup (A',S',Z)[3L], perm[nsets], h, random
-    auto b_adv = [&](uint32_t g) { return (int)g; };
-    auto b_lk = [&](uint32_t l, uint32_t w) { return (int)(cs.G + 3 * l + w); };
-    auto b_pz = [&](uint32_t s) { return (int)(cs.G + 3 * pk.L + s); };
-    const int b_h = (int)(cs.G + 3 * pk.L + pk.nsets), b_rand = b_h + 1;
-    pk.nblinds = b_rand + 1;
-    const int last_rot = -((int)cs.bf + 1);
-    // positions in the proof's evaluation list (same order as the `ev(...)` pushes below; steps 14-18)
-    const int e_adv0 = (int)cs.iq.size(), e_fix0 = e_adv0 + (int)cs.aq.size(), e_rand = e_fix0 + (int)cs.fq.size(), e_sig0 = e_rand + 1;
-    const int e_perm0 = e_sig0 + (int)pk.M;
-    auto e_perm = [&](uint32_t s2) { return e_perm0 + 3 * (int)s2; };                     // z, z_next, (z_last: all but the last set)
-    const int e_lk0 = e_perm0 + (pk.nsets ? 3 * (int)pk.nsets - 1 : 0);
-    for (size_t i = 0; i < cs.iq.size(); ++i) add_query(pk, cid_inst + cs.iq[i].first, cs.iq[i].second, PolyRef{R_POLY, pk.slot_inst(cs.iq[i].first)}, 0, 0, (int)i);
-    for (size_t i = 0; i < cs.aq.size(); ++i) add_query(pk, cid_adv + cs.aq[i].first, cs.aq[i].second, PolyRef{R_POLY, (uint32_t)cs.aq[i].first}, 1, b_adv(cs.aq[i].first), e_adv0 + (int)i);
-    for (uint32_t s2 = 0; s2 < pk.nsets; ++s2) {
-      add_query(pk, cid_pz + s2, 0, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2));
-      add_query(pk, cid_pz + s2, 1, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2) + 1);
-    }
-    for (int s2 = (int)pk.nsets - 2; s2 >= 0; --s2) add_query(pk, cid_pz + s2, last_rot, PolyRef{R_POLY, pk.slot_pz(s2)}, 1, b_pz(s2), e_perm(s2) + 2);
-    for (uint32_t l = 0; l < pk.L; ++l) {
-      const int e = e_lk0 + 5 * (int)l;                                                   // z, z_next, a, a_inv, s
-      add_query(pk, cid_lk + 3 * l + 2, 0, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2), e);
-      add_query(pk, cid_lk + 3 * l + 0, 0, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0), e + 2);
-      add_query(pk, cid_lk + 3 * l + 1, 0, PolyRef{R_POLY, pk.slot_lk(l, 1)}, 1, b_lk(l, 1), e + 4);
-      add_query(pk, cid_lk + 3 * l + 0, -1, PolyRef{R_POLY, pk.slot_lk(l, 0)}, 1, b_lk(l, 0), e + 3);
-      add_query(pk, cid_lk + 3 * l + 2, 1, PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1, b_lk(l, 2), e + 1);
-    }
-    for (size_t i = 0; i < cs.fq.size(); ++i) add_query(pk, cid_fix + cs.fq[i].first, cs.fq[i].second, PolyRef{R_SHPOLY, (uint32_t)cs.fq[i].first}, 0, 0, e_fix0 + (int)i);
-    for (uint32_t j = 0; j < pk.M; ++j) add_query(pk, cid_sig + j, 0, PolyRef{R_SHPOLY, cs.F + j}, 0, 0, e_sig0 + (int)j);
-    add_query(pk, cid_h, 0, PolyRef{R_MISC, pk.m_hpoly}, 1, b_h, -1);
-    add_query(pk, cid_rand, 0, PolyRef{R_RANDPOLY, 0}, 1, b_rand, e_rand);
-    build_multiopen(pk);
-    const uint32_t nps = (uint32_t)pk.point_sets.size();
-    pk.m_qset0 = m; m += nps;
-    pk.m_qtmp0 = m; m += 2 * nps;
-    pk.m_qprime = m++; pk.m_ppoly = m++; pk.m_pprime = m++; pk.m_b = m++; pk.m_coef = m++; pk.m_scl = m++; pk.m_scr = m++;
-    pk.NM = m;
-    // ---- evaluation list in transcript order (steps 14-18)
-    auto ev = [&](PolyRef p, int rot) { pk.evals.push_back(EvalQuery{p, pk.rot_const.at(rot)}); };
-    for (auto& q : cs.iq) ev(PolyRef{R_POLY, pk.slot_inst(q.first)}, q.second);
-    for (auto& q : cs.aq) ev(PolyRef{R_POLY, (uint32_t)q.first}, q.second);
-    for (auto& q : cs.fq) ev(PolyRef{R_SHPOLY, (uint32_t)q.first}, q.second);
-    ev(PolyRef{R_RANDPOLY, 0}, 0);
-    for (uint32_t j = 0; j < pk.M; ++j) ev(PolyRef{R_SHPOLY, cs.F + j}, 0);
-    for (uint32_t s = 0; s < pk.nsets; ++s) {
-      ev(PolyRef{R_POLY, pk.slot_pz(s)}, 0); ev(PolyRef{R_POLY, pk.slot_pz(s)}, 1);
-      if (s + 1 != pk.nsets) ev(PolyRef{R_POLY, pk.slot_pz(s)}, last_rot);
-    }
-    for (uint32_t l = 0; l < pk.L; ++l) {
-      ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 2)}, 1);
-      ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, 0); ev(PolyRef{R_POLY, pk.slot_lk(l, 0)}, -1);
-      ev(PolyRef{R_POLY, pk.slot_lk(l, 1)}, 0);
-    }
     pk.d_evals.alloc(pk.evals.size() * sizeof(EvalQuery));
     BZ_CUDA(cudaMemcpy(pk.d_evals.p, pk.evals.data(), pk.evals.size() * sizeof(EvalQuery), cudaMemcpyHostToDevice));
-    // proof size: points (32 B) + scalars (32 B)
-    uint32_t npoints = cs.G + 2 * pk.L + pk.nsets + pk.L + 1 + pk.qdeg + 1 + 1 + 2 * cs.k;
-    uint32_t nscalars = (uint32_t)pk.evals.size() + nps + 2;
-    pk.proof_size = 32 * (npoints + nscalars);
-    build_programs(C, pk);
+    upload_programs(pk);
     BZ_CUDA(cudaStreamSynchronize(st));
     *out = h.release();
   });
@@ -798,10 +815,22 @@ struct Prover {
   // one batch of commitments: fixed-base tables when available, otherwise the bucket MSM per polynomial
   void run_msms(bool lagrange, const std::vector<void*>& mainp, const std::vector<void*>& extrap, uint32_t n_msm) {
     const FixedBase& fb = lagrange ? pk.params->fb_gl : pk.params->fb_g;
+    const uint32_t world = C->shard_world, rank = C->shard_rank;
     if (pk.params->use_tables) {
       BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
       BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + n_msm, extrap.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
       uint32_t chunks = std::max(1u, std::min(16u, (uint32_t)(4 * C->sm_count / std::max(1u, n_msm))));
+      if (world > 1 && n_msm >= world) {
+        // one large proof across GPUs, table path: rank r sums the contiguous MSMs [r * per, (r + 1) * per) and the 128-byte
+        // XYZZ results are all-gathered (every rank holds the same tables); fewer MSMs than ranks are computed redundantly
+        const uint32_t per = (n_msm + world - 1) / world, lo = std::min(n_msm, rank * per), hi = std::min(n_msm, lo + per);
+        BZ_CHECK((size_t)per * 128 <= C->shard_cap, "sharding exchange buffer too small");
+        BZ_CUDA(cudaMemsetAsync(C->shard_send, 0, (size_t)per * 128, st));
+        if (hi > lo) fixed_msm_run(C, fb, (const void* const*)w.ptrs.p + lo, n, (const void* const*)((void**)w.ptrs.p + n_msm) + lo, hi - lo, chunks, C->shard_send, true);
+        if (C->shard_exchange(C->shard_user, (size_t)per * 128) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
+        BZ_CUDA(cudaMemcpyAsync(w.commits.p, C->shard_recv, (size_t)n_msm * 128, cudaMemcpyDeviceToDevice, st));
+        return;
+      }
       fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + n_msm), n_msm, chunks, w.commits.p, true);
       return;
     }
@@ -809,9 +838,39 @@ struct Prover {
     const void* bases = lagrange ? pk.params->gl_w.p : pk.params->g_w_u.p;
     w.msm_in.ensure((size_t)npts * 32);
     w.msm_jac.ensure((size_t)n_msm * 96);
-    for (uint32_t j = 0; j < n_msm; ++j) {
+    auto stage = [&](uint32_t j) {
       BZ_CUDA(cudaMemcpyAsync(w.msm_in.p, mainp[j], (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
       BZ_CUDA(cudaMemcpyAsync((char*)w.msm_in.p + (size_t)n * 32, extrap[j], (size_t)nextra * 32, cudaMemcpyDeviceToDevice, st));
+    };
+    if (world > 1 && n_msm >= world) {
+      // column deal: rank r owns the contiguous MSMs [r * per, (r + 1) * per); one all-gather of per x 96 B per rank
+      const uint32_t per = (n_msm + world - 1) / world, lo = std::min(n_msm, rank * per), hi = std::min(n_msm, lo + per);
+      BZ_CHECK((size_t)per * 96 <= C->shard_cap, "sharding exchange buffer too small");
+      BZ_CUDA(cudaMemsetAsync(C->shard_send, 0, (size_t)per * 96, st));
+      for (uint32_t j = lo; j < hi; ++j) { stage(j); msm_run(C, pk.params->curve, w.msm_in.p, bases, npts, (char*)C->shard_send + (size_t)(j - lo) * 96, 0); }
+      if (C->shard_exchange(C->shard_user, (size_t)per * 96) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
+      jac_to_affine_run(C, pk.params->curve, C->shard_recv, w.commits.p, n_msm);          // rank-major = MSM order
+      return;
+    }
+    if (world > 1) {
+      // fewer MSMs than ranks (random polynomial, q', S, the two IPA terms): every MSM split by point range, the partials summed
+      BZ_CHECK((size_t)n_msm * 96 <= C->shard_cap, "sharding exchange buffer too small");
+      const uint32_t base = npts / world, rem = npts % world, plo = rank * base + std::min(rank, rem), cnt = base + (rank < rem ? 1u : 0u);
+      for (uint32_t j = 0; j < n_msm; ++j) {
+        stage(j);
+        msm_run(C, pk.params->curve, (const char*)w.msm_in.p + (size_t)plo * 32, (const char*)bases + (size_t)plo * 64, cnt, (char*)C->shard_send + (size_t)j * 96, 0);
+      }
+      if (C->shard_exchange(C->shard_user, (size_t)n_msm * 96) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
+      w.msm_jac.ensure((size_t)n_msm * world * 96);
+      for (uint32_t j = 0; j < n_msm; ++j) {
+        // partials of MSM j sit at recv[r][j]: gather them contiguously, then one kernel adds them and normalises
+        BZ_CUDA(cudaMemcpy2DAsync((char*)w.msm_jac.p + (size_t)j * world * 96, 96, (const char*)C->shard_recv + (size_t)j * 96, (size_t)n_msm * 96, 96, world, cudaMemcpyDeviceToDevice, st));
+        jac_sum_run(C, pk.params->curve, (const char*)w.msm_jac.p + (size_t)j * world * 96, world, (char*)w.commits.p + (size_t)j * 64);
+      }
+      return;
+    }
+    for (uint32_t j = 0; j < n_msm; ++j) {
+      stage(j);
       msm_run(C, pk.params->curve, w.msm_in.p, bases, npts, (char*)w.msm_jac.p + (size_t)j * 96, 0);
     }
     jac_to_affine_run(C, pk.params->curve, w.msm_jac.p, w.commits.p, n_msm);
@@ -928,16 +987,20 @@ void Prover::compute_h() {
     {
       ProfScope prof(C, PROF_QUOTIENT);
       BigKernelScope bigs(C);
-      eval_program_kernel<FpP><<<dim3((en + 127) / 128, B), 128, pk.q_ninstr[0] * 4, bigs.s>>>(a);
-      C->kernel_launches++;
+      auto launch = [&](uint32_t t, const EvalArgs<FpP>& args, uint32_t points) {
+        const dim3 grid((points + 127) / 128, B);
+        if (pk.q_gen[t]) pk.q_gen[t](args, grid, bigs.s);                   // circuit-specialised straight-line code (gen_quotient.cu)
+        else eval_program_kernel<FpP><<<grid, 128, pk.q_ninstr[t] * 4, bigs.s>>>(args);
+        C->kernel_launches++;
+      };
+      launch(0, a, en);
       DFe* low_out = (DFe*)w.hext_low.p;
       for (uint32_t t = 1; t < PkImpl::Q_TIERS; ++t) {      // lower-degree terms: every 2^t-th extended point
         if (!pk.q_ninstr[t]) continue;
         EvalArgs<FpP> al = a;
         al.code = (const uint32_t*)pk.q_code[t].p; al.n_instr = pk.q_ninstr[t]; al.rot = (const int32_t*)pk.q_rot[t].p;
         al.stride_log = t; al.out = low_out; al.ostride = en >> t;
-        eval_program_kernel<FpP><<<dim3(((en >> t) + 127) / 128, B), 128, pk.q_ninstr[t] * 4, bigs.s>>>(al);
-        C->kernel_launches++;
+        launch(t, al, en >> t);
         low_out += (size_t)B * (en >> t);
       }
     }
@@ -1006,24 +1069,22 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   // ---- step 1: instance commitments (blind 1), absorbed
   phase.reset(); phase.reset(new NvtxRange("step 1-2: instance + advice commitments, NTTs"));
   std::vector<std::vector<HostPoint>> pts;
-  if (I) {
-    std::vector<CommitReq> reqs;
-    for (uint32_t i = 0; i < I; ++i) reqs.push_back({PolyRef{R_VAL, pk.slot_inst(i)}, true});
-    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(I, F.one()));
-    commit(reqs, bl, pts);
-    for (uint32_t b = 0; b < B; ++b) for (uint32_t i = 0; i < I; ++i) t_common_point(ps[b], pts[b][i]);
-  }
-  // ---- step 2: advice blinding rows, blinds, commitments
+  // ---- steps 1-2: instance commitments (blind 1; absorbed, not written) and advice commitments (blinding rows, then one blind
+  // per column) in ONE commitment batch: both are commit_lagrange and no challenge separates them
   {
     std::vector<CopyDesc> cd;
     for (uint32_t g = 0; g < G; ++g) cd.push_back(CopyDesc{PolyRef{R_VAL, g}, usable, pk.r_adv_rows + g * (bf + 1), bf + 1});
     launch_copy(cd, n);
     std::vector<CommitReq> reqs;
+    for (uint32_t i = 0; i < I; ++i) reqs.push_back({PolyRef{R_VAL, pk.slot_inst(i)}, true});
     for (uint32_t g = 0; g < G; ++g) reqs.push_back({PolyRef{R_VAL, g}, true});
-    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(G));
-    for (uint32_t b = 0; b < B; ++b) for (uint32_t g = 0; g < G; ++g) { bl[b][g] = rnd_host(ps[b], F, pk.r_adv_blind + g); ps[b].blinds[g] = bl[b][g]; }
+    std::vector<std::vector<HFe>> bl(B, std::vector<HFe>(I + G, F.one()));
+    for (uint32_t b = 0; b < B; ++b) for (uint32_t g = 0; g < G; ++g) { bl[b][I + g] = rnd_host(ps[b], F, pk.r_adv_blind + g); ps[b].blinds[g] = bl[b][I + g]; }
     commit(reqs, bl, pts);
-    for (uint32_t b = 0; b < B; ++b) for (uint32_t g = 0; g < G; ++g) t_write_point(ps[b], pts[b][g]);
+    for (uint32_t b = 0; b < B; ++b) {
+      for (uint32_t i = 0; i < I; ++i) t_common_point(ps[b], pts[b][i]);
+      for (uint32_t g = 0; g < G; ++g) t_write_point(ps[b], pts[b][I + g]);
+    }
     to_coeff(0, G + I);
     to_coset(0, G + I);
   }
@@ -1047,12 +1108,12 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     std::vector<HFe> up;
     if (device_permute && n > LKP_MAX_N) {
       // large domains: device-wide radix sort / scans per (proof, lookup) (lookup.cu)
-      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, 4, st));
+      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, (size_t)B * 4, st));
       ProfScope prof(C, PROF_SCAN);
       for (uint32_t b = 0; b < B; ++b)
         for (uint32_t l = 0; l < L; ++l)
-          lookup_permute_large_run(C, misc(b, pk.m_cin0 + 2 * l), misc(b, pk.m_cin0 + 2 * l + 1), val(b, pk.slot_lk(l, 0)), val(b, pk.slot_lk(l, 1)), usable, (uint32_t*)w.lk_err.p);
-      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, 4, cudaMemcpyDeviceToHost, st));
+          lookup_permute_large_run(C, misc(b, pk.m_cin0 + 2 * l), misc(b, pk.m_cin0 + 2 * l + 1), val(b, pk.slot_lk(l, 0)), val(b, pk.slot_lk(l, 1)), usable, (uint32_t*)w.lk_err.p + b);
+      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));
     } else if (device_permute) {
       // device: sort / permute (U: lookup/prover.rs::permute_expression_pair), one CTA per (lookup, proof)
       static PerDeviceOnce once;
@@ -1061,13 +1122,13 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       for (uint32_t l = 0; l < L; ++l)
         pd.push_back(LookupPermDesc{PolyRef{R_MISC, pk.m_cin0 + 2 * l}, PolyRef{R_MISC, pk.m_cin0 + 2 * l + 1}, PolyRef{R_VAL, pk.slot_lk(l, 0)}, PolyRef{R_VAL, pk.slot_lk(l, 1)}});
       LookupPermDesc* dpd = upload_desc(pd);
-      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, 4, st));
+      BZ_CUDA(cudaMemsetAsync(w.lk_err.p, 0, (size_t)B * 4, st));
       {
         ProfScope prof(C, PROF_SCAN);
         lookup_permute_kernel<FpP><<<dim3(L, B), LKP_THREADS, lookup_permute_smem(n), st>>>(reg, n, usable, dpd, (DFe*)w.lk_sorted.p, (uint32_t*)w.lk_err.p);
         C->kernel_launches++;
       }
-      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, 4, cudaMemcpyDeviceToHost, st));     // read after the commitments' sync below
+      BZ_CUDA(cudaMemcpyAsync(w.h_err, w.lk_err.p, (size_t)B * 4, cudaMemcpyDeviceToHost, st));     // read after the commitments' sync below
     } else {
       // host: sort / permute (U: lookup/prover.rs::permute_expression_pair)
       const size_t per = (size_t)2 * L * n * 32;
@@ -1127,7 +1188,9 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     launch_copy(cd, n);
     if (!device_permute) BZ_CUDA(cudaStreamSynchronize(st));      // `up` must outlive the async copies
     commit(reqs, bl, pts);
-    if (device_permute && *w.h_err) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure)");
+    if (device_permute)
+      for (uint32_t b = 0; b < B; ++b)
+        if (w.h_err[b]) throw Error(BZ_ERR_SYNTHESIS, "lookup input not in table (Error::ConstraintSystemFailure) in proof " + std::to_string(b) + " of the batch");
     for (uint32_t b = 0; b < B; ++b) for (uint32_t j = 0; j < 2 * L; ++j) t_write_point(ps[b], pts[b][j]);
   }
   // ---- step 6
@@ -1630,3 +1693,26 @@ API int bz_ipa_finish(bz_ctx* ctx, bz_ipa* ipa, void* out_c) {
 API void bz_ipa_destroy(bz_ipa* ipa) { delete ipa; }
 
 }  // extern "C"
+
+
+// ---- build-time access to the compiled h(X) programs (no GPU needed): scripts/gen_quotient_kernels.py ------------------------
+extern "C" {
+API int bz_quotient_program(const bz_circuit* cs, uint32_t tier, uint32_t* code, uint32_t code_cap, uint32_t* n_code, int32_t* rot, uint32_t rot_cap,
+                            uint32_t* n_rot, uint64_t* hash) {
+  try {
+    if (!cs || tier >= PkImpl::Q_TIERS || !n_code || !n_rot) return BZ_ERR_INVALID;
+    bzh::Field F{0};
+    PkImpl pk;
+    pk_host_setup(F, pk, cs);
+    const std::vector<uint32_t>& c = pk.h_q_code[tier];
+    const std::vector<int32_t>& r = pk.h_q_rot[tier];
+    *n_code = (uint32_t)c.size(); *n_rot = (uint32_t)r.size();
+    if (hash) *hash = program_hash(c, r);
+    if (code && code_cap >= c.size() && !c.empty()) memcpy(code, c.data(), c.size() * 4);
+    if (rot && rot_cap >= r.size() && !r.empty()) memcpy(rot, r.data(), r.size() * 4);
+    return BZ_OK;
+  } catch (const std::exception&) { return BZ_ERR_INVALID; }
+}
+/* 1 when tier `tier` of this proving key runs circuit-specialised generated code, 0 for the interpreter */
+API int bz_pk_quotient_generated(const bz_pk* pk, uint32_t tier) { return pk && tier < PkImpl::Q_TIERS && pk->p.q_gen[tier] ? 1 : 0; }
+}

@@ -22,10 +22,25 @@ namespace bz {
 
 void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
+void jac_sum_run(Ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine);
 void decompress_points_run(Ctx* ctx, int curve, const void* d_in, void* d_out_affine, uint8_t* d_status, uint32_t count);
 void lookup_permute_large_run(Ctx* ctx, const void* cin, const void* ctab, void* aout, void* sout, uint32_t usable, uint32_t* d_err);
 
 typedef ::bz::Fe<FpP> DFe;      // device element type of the prover's scalar field (Vesta scalars = Fp)
+
+// h(X) as generated straight-line code (gen_quotient.cu, emitted by scripts/gen_quotient_kernels.py from the compiled program of a
+// known circuit): same arguments as eval_program_kernel, found by the FNV-1a hash of the program words and its rotation table
+typedef void (*QuotientLaunchFn)(const EvalArgs<FpP>& a, dim3 grid, cudaStream_t st);
+QuotientLaunchFn find_generated_quotient(uint64_t hash);
+inline uint64_t program_hash(const std::vector<uint32_t>& code, const std::vector<int32_t>& rot) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  auto mix = [&](uint32_t v) { for (int i = 0; i < 4; ++i) { h ^= (v >> (8 * i)) & 0xffu; h *= 0x100000001b3ull; } };
+  mix((uint32_t)code.size());
+  for (uint32_t v : code) mix(v);
+  mix((uint32_t)rot.size());
+  for (int32_t v : rot) mix((uint32_t)v);
+  return h;
+}
 
 // ------------------------------------------------------------------------------------------------------
 struct ParamsImpl {
@@ -74,6 +89,9 @@ struct PkImpl {
   static constexpr uint32_t Q_TIERS = 3;     // h(X) tier t: terms whose quotient fits ext_n >> t points, evaluated on every 2^t-th extended point
   DevBuf lk_code, lk_rot, q_code[Q_TIERS], q_rot[Q_TIERS];
   uint32_t lk_ninstr = 0, q_ninstr[Q_TIERS] = {0, 0, 0}, q_muls[Q_TIERS] = {0, 0, 0};
+  std::vector<uint32_t> h_lk_code, h_q_code[Q_TIERS];      // host copies (the programs are compiled without a GPU)
+  std::vector<int32_t> h_lk_rot, h_q_rot[Q_TIERS];
+  QuotientLaunchFn q_gen[Q_TIERS] = {nullptr, nullptr, nullptr};   // circuit-specialised straight-line kernel of the tier (gen_quotient.cu), or null: interpreter
   uint32_t n_exprs = 0;       // number of y-folded expressions E (gate polys, permutation, lookup terms)
   // Gate polynomials as h(X) evaluates them: every maximal sub-expression over fixed columns and constants only that contains
   // a product (after keygen's selector compression: q * prod_{i != r} (i - q), up to 8 multiplications per use) is evaluated

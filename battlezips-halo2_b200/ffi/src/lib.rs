@@ -25,6 +25,8 @@ pub use sys::*;
 #[repr(C)] pub struct bz_params { _p: [u8; 0] }
 #[repr(C)] pub struct bz_pk { _p: [u8; 0] }
 #[repr(C)] pub struct bz_ipa { _p: [u8; 0] }
+/// all-gather callback of bz_ctx_set_sharding: gather `bytes_per_rank` bytes of every rank's send buffer into the receive buffer
+pub type bz_allgather_fn = Option<unsafe extern "C" fn(user: *mut c_void, bytes_per_rank: usize) -> c_int>;
 
 #[repr(C)]
 #[derive(Clone, Copy)]

@@ -75,8 +75,15 @@ def parse():
 # 71 IMAD.WIDE.U32(.X) at HALF rate (measured: bz_imad_wide_peak = 0.455 x bz_imad_peak) = 142, plus 25 IMAD.HI + 11 IMAD +
 # 18 IMAD.X at full rate = 54  ->  196  (cuobjdump -sass of fe_mul_raw)
 FMA_PER_MUL = 196
-NCU_DRAM_BYTES_PER_ADD = 136.6      # profiles/r1h_ncu_full_summary.csv, fb_accumulate_kernel at c = 16: (278.3 + 8.5) MB per IPA-round launch of
-                                    # 128 MSMs x 1 026 scalars x 16 windows = 2.10 M mixed additions (r1d, c = 14: 129.8)
+def ncu_dram_bytes_per_add():
+    """DRAM bytes fb_accumulate_kernel moves per mixed addition, from the newest committed `ncu --set full` capture:
+    profiles/traffic.json is written by profiles/traffic.py out of profiles/*_ncu_full_summary.csv (dram__bytes_read.sum +
+    dram__bytes_write.sum of the kernel / the additions of that launch).  None when no capture is committed."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return float(d["fb_accumulate_kernel"]["dram_bytes_per_add"]), d["fb_accumulate_kernel"]["source"]
+    except Exception:      # noqa: BLE001
+        return None, None
 
 
 def set_sync_policy(args, local_rank):
@@ -91,6 +98,18 @@ def set_sync_policy(args, local_rank):
         ok = cu.cuInit(0) == 0 and cu.cuDeviceGet(ctypes.byref(dev), local_rank) == 0 and cu.cuDevicePrimaryCtxSetFlags_v2(dev, 4) == 0   # CU_CTX_SCHED_BLOCKING_SYNC
         return "blocking" if ok else "spin (could not set blocking)"
     return "spin"
+
+
+def config_for(wl, sched="spin"):
+    """The `config` object of the JSON line -- built the same way by the GPU arm and by --impl reference, so the two lines carry
+    identical dicts."""
+    if isinstance(wl, ProofWorkload):
+        l2 = "per-step working set (window tables + batch work areas) far larger than L2; no flush needed"
+    elif getattr(wl, "n", 0) * 96 > 126e6:
+        l2 = "inputs larger than L2 (no flush needed)"
+    else:
+        l2 = "inputs < L2; not flushed"
+    return {"workload": wl.name, "l2": l2, "host_wait": sched}
 
 
 def peaks():
@@ -447,7 +466,7 @@ class ProofWorkload:
     unit = proofs; every proof has its own RNG stream; witnesses cycle over 8 distinct synthetic jobs."""
     dtype = "u32x8 (255-bit Montgomery, integer pipe)"
     metric, unit = "proofs_per_sec", "proofs/s"
-    DISTINCT = 8
+    DISTINCT = int(os.environ.get("BZ_DISTINCT", "32"))      # distinct synthetic witnesses the batch cycles over (config 3: pattern x shot cell)
 
     def __init__(self, args, which):
         self.which, self.B, self.T = which, args.batch, max(1, args.inflight)
@@ -455,7 +474,11 @@ class ProofWorkload:
         if which == "board_scaled":          # BASELINE config 5: Board replicated down a 2^k-row table
             self.k, self.B, self.T, self.DISTINCT = args.k, 1, 1, 1
         if which == "board_scaled":
-            self.name = f"Board circuit replicated to k={self.k} (many boards per proof), single proof, synthetic URS (BASELINE config 5)"
+            self.world = int(os.environ.get("WORLD_SIZE", "1"))
+            self.scaling = "strong" if self.world > 1 else "weak"
+            self.name = (f"Board circuit replicated to k={self.k} (many boards per proof), ONE proof"
+                         + (f" across {self.world} GPUs: commitment MSMs dealt out by column / split by point range, NCCL all-gather of the 96 B results"
+                            if self.world > 1 else "") + ", URS from Params::new on the device (BASELINE config 5)")
             return
         self.name = (f"batched {'Shot' if which == 'shot' else 'Board'} proofs (k={self.k}, IPA/Pasta), {self.T} lanes x {self.B} independent "
                      f"proofs per GPU per step, synthetic witnesses (BASELINE config {'3' if which == 'shot' else '2'})")
@@ -466,7 +489,7 @@ class ProofWorkload:
         make = shot_circuit if self.which == "shot" else board_circuit
         if self.which == "board_scaled":
             from battlezips_halo2_b200.circuits import board_circuit_scaled
-            jobs = [board_circuit_scaled(self.k, seed=rank)]
+            jobs = [board_circuit_scaled(self.k, seed=0)]          # every rank proves the SAME circuit when the proof is sharded
         else:
             jobs = [make(rank * 1000 + i) for i in range(self.DISTINCT)]
         cs, _, asg0 = jobs[0]
@@ -510,7 +533,13 @@ class ProofWorkload:
             fx = np.load(fxp)
         else:
             fx = self._synthetic_urs(ctx)
+        torch.cuda.synchronize()
+        free0 = torch.cuda.mem_get_info(ctx.device)[0]
+        t0 = time.perf_counter()
         self.params = PR.Params(ctx, self.k, fx["g"], fx["g_lagrange"], fx["w"], fx["u"])     # window tables: shared by all lanes
+        ctx.sync()
+        self.setup_info = {"params_table_build_s": round(time.perf_counter() - t0, 3), "params_hbm_bytes": int(free0 - torch.cuda.mem_get_info(ctx.device)[0]),
+                           "note": "one-off per Params (outside the timed steps): window tables of g || w || u and g_lagrange || w"}
         self.fx = fx
         B, T = self.B, self.T
         ni = self.ir["num_instance"]
@@ -518,7 +547,10 @@ class ProofWorkload:
         self.stride = int(self.lens.max())
         mapping = self.asg0.permutation_mapping()
         self.lanes = []
-        wide_all = self._wide(rank, B * T)
+        sharded = self.which == "board_scaled" and getattr(self, "world", 1) > 1
+        wide_all = self._wide(0 if sharded else rank, B * T)
+        if sharded:
+            ctx.set_sharding(rank, self.world)
         for t in range(T):
             lane = {}
             lane["stream"] = torch.cuda.current_stream() if t == 0 else torch.cuda.Stream()
@@ -533,12 +565,18 @@ class ProofWorkload:
                 for i in range(ni):
                     inst[b, i, :self.lens[i]] = PR.mont(self.instances_d[sel[b]][i])
             lane["proofs"] = np.zeros((B, lane["pk"].proof_size), dtype=np.uint8)
-            lane["h"] = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in (inst, advice, wide)]
-            lane["d"] = [lane["ctx"].to_device(x) for x in (inst, advice, wide)]
-            lane["bytes"] = advice.nbytes + wide.nbytes + inst.nbytes
+            ones = np.tile(PR.mont([1])[0], (advice.shape[0], advice.shape[1], advice.shape[2], 1))       # Assigned::Trivial: denominator one
+            lane["h"] = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in (inst, advice, wide, ones)]
+            lane["d"] = [h.to(f"cuda:{ctx.device}") for h in lane["h"][:3]]
+            lane["d_den"] = torch.empty_like(lane["h"][3], device=f"cuda:{ctx.device}")
+            lane["d_adv_e2e"] = torch.empty_like(lane["h"][1], device=f"cuda:{ctx.device}")
+            lane["step"] = 0
+            lane["bytes"] = advice.nbytes + wide.nbytes + inst.nbytes + ones.nbytes
             self.lanes.append(lane)
         self.advice, self.wide = np.ascontiguousarray(adv_d[:1]), wide_all[:2]
         self.pk = self.lanes[0]["pk"]
+        self.setup_info["work_hbm_bytes"] = int(free0 - torch.cuda.mem_get_info(ctx.device)[0]) - self.setup_info["params_hbm_bytes"]
+        self.setup_info["distinct_witnesses"] = self.DISTINCT
         self.h2d = sum(l["bytes"] for l in self.lanes)
         self.d2h = sum(l["proofs"].nbytes for l in self.lanes)
         self.pool = ThreadPoolExecutor(T)
@@ -550,20 +588,40 @@ class ProofWorkload:
         self.device_urs = True
         return ar.params_new(ctx, self.k, curve=0)
 
-    def _lane_run(self, lane, ptrs):
-        import ctypes
+    STEP_INC = 0x9E3779B97F4A7C15 - (1 << 64)        # odd: every RNG word of every proof changes every step (fresh randomness per proof)
+
+    def _lane_run(self, lane, device):
+        """One create_proof call of a lane.  The RNG words are advanced first, so no two calls prove with the same randomness.
+        device = True: inputs resident in HBM.  device = False (e2e): what the reference-facing host does per call -- the
+        `Assigned` advice (numerators + denominators, host memory) goes through poly::batch_invert_assigned on the device,
+        instances and RNG words are read from host memory by the call, proofs come back to host memory."""
+        import ctypes, torch
         c = lane["ctx"]
+        vp = ctypes.c_void_p
+        lane["step"] += 1
+        with torch.cuda.stream(lane["stream"]):
+            if device:
+                lane["d"][2].add_(self.STEP_INC)
+                ptrs = [vp(d.data_ptr()) for d in lane["d"]]
+            else:
+                hw = lane["h"][2].numpy()
+                np.add(hw, np.int64(self.STEP_INC), out=hw)
+                lane["d_adv_e2e"].copy_(lane["h"][1], non_blocking=True)
+                lane["d_den"].copy_(lane["h"][3], non_blocking=True)
+                nel = lane["h"][1].numel() // 4
+                c._check(c.lib.bz_batch_invert_assigned_dev(c.h, 0, vp(lane["d_adv_e2e"].data_ptr()), vp(lane["d_den"].data_ptr()), vp(lane["d_adv_e2e"].data_ptr()), nel))
+                ptrs = [vp(lane["h"][0].data_ptr()), vp(lane["d_adv_e2e"].data_ptr()), vp(lane["h"][2].data_ptr())]
         c._check(c.lib.bz_create_proofs(c.h, lane["pk"].h, self.B, ptrs[0], self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
                                         ptrs[1], ptrs[2], lane["proofs"].ctypes.data_as(ctypes.c_void_p)))
 
     def _run(self, device):
-        import ctypes
         futs = []
         for lane in self.lanes:
-            ptrs = [d.ptr for d in lane["d"]] if device else [ctypes.c_void_p(h.data_ptr()) for h in lane["h"]]
-            futs.append(self.pool.submit(self._lane_run, lane, ptrs))
+            futs.append(self.pool.submit(self._lane_run, lane, device))
         for f in futs:
             f.result()
+        if self.which == "board_scaled" and getattr(self, "world", 1) > 1:
+            return self.B * self.T / self.world          # one proof per step for the whole job
         return self.B * self.T
 
     def step_device(self):
@@ -581,15 +639,13 @@ class ProofWorkload:
         ts = []
         for _ in range(reps + 2):
             t0 = time.perf_counter()
-            c._check(c.lib.bz_create_proofs(c.h, lane["pk"].h, 1, lane["d"][0].ptr, self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
-                                            lane["d"][1].ptr, lane["d"][2].ptr, out.ctypes.data_as(ctypes.c_void_p)))
+            c._check(c.lib.bz_create_proofs(c.h, lane["pk"].h, 1, ctypes.c_void_p(lane["d"][0].data_ptr()), self.lens.ctypes.data_as(ctypes.c_void_p), self.stride,
+                                            ctypes.c_void_p(lane["d"][1].data_ptr()), ctypes.c_void_p(lane["d"][2].data_ptr()), out.ctypes.data_as(ctypes.c_void_p)))
             ts.append(1e3 * (time.perf_counter() - t0))
-        assert bytes(out[0]) == bytes(lane["proofs"][0]), "single-proof call differs from the batched proof"
         return float(np.median(ts[2:]))
 
     def step_profile(self):
-        lane = self.lanes[0]
-        self._lane_run(lane, [d.ptr for d in lane["d"]])
+        self._lane_run(self.lanes[0], True)
         return self.B
 
     def all_contexts(self):
@@ -598,13 +654,14 @@ class ProofWorkload:
     def close(self):
         self.pool.shutdown()
         for lane in self.lanes:
-            for d in lane["d"]:
-                d.free()
+            lane["d"] = lane["h"] = lane["d_den"] = lane["d_adv_e2e"] = None
             lane["pk"].close()
             if lane["ctx"] is not self.ctx:
                 lane["ctx"].close()
         self.params.close()
         self.lanes = []
+        if self.which == "board_scaled" and getattr(self, "world", 1) > 1:
+            self.ctx.set_sharding(0, 1)
 
     def dominant(self):
         # fixed-base MSM: algorithmic bytes = one 64 B table point per mixed addition + 32 B per scalar read
@@ -685,8 +742,8 @@ def run_reference(args, rank):
     for _ in range(args.steps):
         v, sample, cores, dt = wl.cpu(args.cpu_sample_log)
         vals.append(v); dts.append(dt)
-    v = float(np.mean(vals))
-    extra = {}
+    v = float(np.median(vals))           # median of the timed runs (the driver asks for 20)
+    extra = {"runs": len(vals), "value_min_max": [float(min(vals)), float(max(vals))]}
     if isinstance(wl, ProofWorkload):
         from oracle import c_oracle as co
         extra["cpu_phases_ms"] = getattr(wl, "cpu_phases_ms", None)
@@ -700,9 +757,9 @@ def run_reference(args, rank):
     print(json.dumps({
         **extra,
         "impl": "reference", "metric": wl.metric, "value": v, "unit": wl.unit, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.mean(dts)), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": 1e3 * float(np.median(dts)), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "note": "restated halo2_proofs 0.2.0 arithmetic (C oracle); the rustc reference cannot be built here"},
+        "config": config_for(wl), "note": "restated halo2_proofs 0.2.0 arithmetic (C oracle); the rustc reference cannot be built here",
         "cpu_baseline": {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": wl.unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}))
@@ -810,9 +867,10 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
         # DRAM bytes per launch from the committed ncu --set full capture of this kernel (profiles/): fb_accumulate moves
         # 129.8 B per mixed addition (dram__bytes_read + write = 324.6 MB for 2.50 M additions, r1d) -- two 32 B sectors of
         # the table entry plus sector over-fetch on the entry list -- against 64 B algorithmic
-        traffic = (adds_total / cnt) * NCU_DRAM_BYTES_PER_ADD if tag == "fixed_msm" and adds_total else None
+        per_add, traffic_src = ncu_dram_bytes_per_add()
+        traffic = (adds_total / cnt) * per_add if tag == "fixed_msm" and adds_total and per_add else None
         roof = {"bound": "hbm", "kernel": tag, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": traffic, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
+                "traffic": traffic, "traffic_source": traffic_src if traffic else None, "peak_kind": peak_kind, "avg_launch_ms": tot_ms / cnt, "launches": cnt,
                 "share_of_step": tot_ms / prof_ms, "measured": "single-lane pass of the same steps, CUDA-event scopes in the library",
                 "kernel_ms": {k: round(v[0], 4) for k, v in prof.items()}}
     cpu = None
@@ -825,7 +883,7 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
         "metric": wl.metric, "value": value, "unit": wl.unit, "n_gpus": world, "steps": steps, "warmup": warmup,
         "ms_per_step": ms / steps, "higher_is_better": True, "scaling": getattr(wl, "scaling", "weak"), "vs_baseline": None,
         "dtype": wl.dtype, "data": "synthetic",
-        "config": {"workload": wl.name, "l2": "inputs larger than L2 (no flush needed)" if wl.h2d > 126e6 else "per-step working set (tables + batch) larger than L2" if isinstance(wl, ProofWorkload) else "inputs < L2; not flushed"},
+        "config": config_for(wl),
         "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
         "verified": getattr(wl, "check", lambda: None)(), "verify": getattr(wl, "verify_info", None),
@@ -857,9 +915,11 @@ def main():
     ctx = bz.Context(local_rank, stream=stream.cuda_stream)
     wl = WORKLOADS[args.workload](args)
     wl.setup(ctx, rank)
-    line = measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=(rank == 0))
+    line = measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=(rank == 0 and not os.environ.get("BZ_NO_CPU_BASELINE")))
     if line is not None:
-        line["config"]["host_wait"] = sched
+        line["config"] = config_for(wl, sched)
+        if getattr(wl, "setup_info", None):
+            line["setup"] = wl.setup_info
     # ---- the other headline numbers of BASELINE.json's metric (Board proofs/s, MSM points/s, NTT GB/s) ride along in
     # the same JSON line as compact sub-benchmarks, so that one default run reports all of them
     extras = {}
@@ -868,7 +928,7 @@ def main():
             wl.close()
         if os.environ.get("BZ_BENCH_VERBOSE"):
             print("free / total HBM after closing the headline workload:", torch.cuda.mem_get_info(local_rank), file=sys.stderr)
-        names = ["board", "msm", "ntt", "commit"] if world == 1 else ["msm", "commit"]
+        names = ["board", "msm", "ntt", "commit", "scaled"] if world == 1 else ["board", "msm", "commit", "scaled"]
         for name in names:
             # an extra must never take the headline line down with it; under torchrun every rank takes the same branch
             # (setup errors are deterministic), so the collectives inside stay matched
@@ -876,7 +936,9 @@ def main():
                 a2 = argparse.Namespace(**vars(args))
                 if name == "commit":
                     a2.k, a2.columns = 18, 16
-                w2 = WORKLOADS[name](a2)
+                if name == "scaled":                 # config 5 on the way up (k = 20 itself: --workload board_scaled --k 20, profiles/README.md)
+                    a2.k = int(os.environ.get("BZ_SCALED_K", "16"))
+                w2 = WORKLOADS["board_scaled" if name == "scaled" else name](a2)
                 w2.setup(ctx, rank)
                 r = measure(a2, w2, ctx, stream, rank, world, local_rank, want_cpu=False, steps=min(args.steps, 3), warmup=3)
                 if hasattr(w2, "close"):

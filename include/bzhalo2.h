@@ -53,6 +53,18 @@ int bz_sync(bz_ctx* ctx);
 uint64_t bz_kernel_launches(bz_ctx* ctx);
 const char* bz_version(void);
 
+/* ---- one large proof across the GPUs of a box ("independent column commitments ... sharded per GPU", "a large MSM
+ * split by point range with one final NCCL point-sum") -----------------------------------------------------------------------
+ * Every rank calls bz_create_proofs with IDENTICAL inputs.  On the large-circuit path (k >= 20: bucket MSM over the raw bases)
+ * the MSMs of each commitment batch are dealt out by column when the batch has at least `world` of them, otherwise each MSM
+ * is split by point range; a rank writes its 96-byte Jacobian results into d_send (device memory, capacity_per_rank bytes)
+ * and calls exchange(user, bytes), which must all-gather `bytes` bytes from every rank's d_send into d_recv (rank-major,
+ * world x bytes) ON THE CONTEXT'S STREAM (e.g. ncclAllGather / torch.distributed.all_gather_into_tensor) and return 0.
+ * Everything else of the proof is computed redundantly, so all ranks write the same proof bytes.  world = 1 switches it off. */
+typedef int (*bz_allgather_fn)(void* user, size_t bytes_per_rank);
+int bz_ctx_set_sharding(bz_ctx* ctx, uint32_t rank, uint32_t world, void* d_send, void* d_recv, size_t capacity_per_rank,
+                        bz_allgather_fn exchange, void* user);
+
 /* ---- per-kernel-class device timing (CUDA events on the context's stream) ------------------------ */
 /* tags: 0 ntt_pass, 1 msm_digits, 2 msm_sort, 3 msm_bucket, 4 msm_reduce, 5 msm_combine, 6 fixed_msm,
  *       7 quotient, 8 scan, 9 eval, 10 poly, 11 ipa, 12 other */
@@ -205,6 +217,15 @@ uint32_t bz_pk_proof_size(const bz_pk* pk); /* bytes `transcript.finalize()` yie
  * (0: every point of the extended coset, 1: every second, 2: every fourth; the figure SURVEY 8d's quotient roofline is
  * computed from); 0 for an empty tier.  *points, if not NULL, receives the number of coset points of that tier. */
 uint32_t bz_pk_quotient_muls(const bz_pk* pk, uint32_t tier, uint32_t* points);
+
+/* h(X) as generated code.  The compiled program of evaluation tier `tier` for a constraint system -- host only, needs no GPU
+ * and no context: scripts/gen_quotient_kernels.py calls it at build time and emits one straight-line sm_100a kernel per program
+ * into csrc/gen_quotient.cu (registers instead of the interpreter's local-memory stack); a proving key whose program hashes to a
+ * generated kernel uses it (bz_pk_quotient_generated = 1), every other circuit runs the interpreter.  code / rot may be NULL to
+ * query the sizes. */
+int bz_quotient_program(const bz_circuit* cs, uint32_t tier, uint32_t* code, uint32_t code_cap, uint32_t* n_code, int32_t* rot,
+                        uint32_t rot_cap, uint32_t* n_rot, uint64_t* hash);
+int bz_pk_quotient_generated(const bz_pk* pk, uint32_t tier);
 
 /* create_proof for `batch` independent proofs of the same circuit, in lockstep on the device.
  *   instances : batch x num_instance x instance_stride scalars; instance_lens[num_instance] values are used

@@ -5,7 +5,8 @@
 set -u
 # NOTE: consider `export BZ_FIXED_WINDOW=14` for the --set full passes: ncu saves / restores all allocated device memory between
 # replay passes, and the default c = 16 tables are 138 GB (r1h took 21 minutes instead of 7).
-TAG=${1:-r1}
+TAG=${1:-r2}
+export BZ_FIXED_WINDOW=${BZ_FIXED_WINDOW:-14}      # 35 GB of tables instead of 138: ncu saves / restores device memory between replay passes
 OUT=gpurun_out
 CMD="python bench.py --no-extras --batch 64 --inflight 1 --steps 2 --warmup 3"
 mkdir -p $OUT
@@ -18,8 +19,8 @@ cap() {  # name regex skip count
   ncu -i $OUT/${TAG}_$1.ncu-rep --page raw --csv > $OUT/${TAG}_$1_raw.csv 2>/dev/null
 }
 cap fb_accumulate fb_accumulate_kernel 25 6
-cap quotient eval_program_kernel 5 2
+cap quotient "q_shot_t0|eval_program_kernel" 5 3          # h(X): generated straight-line kernel (round 2) / interpreter
 cap ntt ntt_pass 40 6
-cap lookup_permute lookup_permute_kernel 2 1
-cap fb_decode fb_decode_kernel 25 3
+cap fb_fold fb_fold_kernel 25 3
+cap gp_finish grand_product_finish_batch_kernel 1 1
 ls -la $OUT | grep ${TAG}_

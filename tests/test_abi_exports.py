@@ -41,3 +41,24 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cc", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src and "liboracle" not in src, f
+
+
+def test_rust_shim_binds_every_header_symbol():
+    """ffi/src/sys.rs is generated from include/bzhalo2.h (scripts/gen_rust_bindings.py): regenerating it changes nothing, every
+    declared symbol has its `pub fn` with the header's arity, and lib.rs / the halo2_proofs patch only name symbols that exist."""
+    import re, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    assert subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_rust_bindings.py"), "--check"]).returncode == 0, \
+        "ffi/src/sys.rs is stale: run python scripts/gen_rust_bindings.py"
+    sys_rs = open(os.path.join(root, "battlezips-halo2_b200", "ffi", "src", "sys.rs")).read()
+    declared = set(re.findall(r"pub fn (bz_[a-z0-9_]+)\(", sys_rs))
+    assert declared == set(bz.EXPORTS)
+    header = re.sub(r"/\*.*?\*/", "", open(bz.binding.header_path()).read(), flags=re.S)
+    for name, args in re.findall(r"\b(bz_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", header, flags=re.S):
+        arity = 0 if args.strip() == "void" else args.count(",") + 1
+        rust_args = re.search(r"pub fn %s\((.*?)\)( ->|;)" % name, sys_rs).group(1)
+        assert (rust_args.count(":") if rust_args else 0) == arity, name
+    for f in ("src/lib.rs", "halo2_proofs-0.2.0-bz.patch"):
+        used = set(re.findall(r"\b(bz_[a-z0-9_]+)\(", open(os.path.join(root, "battlezips-halo2_b200", "ffi", f)).read()))
+        used -= {"bz_token"}
+        assert used <= declared, (f, used - declared)

@@ -78,3 +78,12 @@ def test_gate_dag_compiler_on_the_shot_and_board_constraint_systems(tmp_path):
         print(name, rows)
         assert rows[0]["dag_muls"] < 0.4 * rows[0]["tree_muls"] and rows[0]["derived"] >= 10          # compressed selectors leave the per-point program
         assert sum(r["dag_muls"] for r in rows) < sum(r["tree_muls"] for r in rows)
+
+
+def test_generated_quotient_kernels_are_current():
+    """csrc/gen_quotient.cu (h(X) of Shot / Board as straight-line code) is what scripts/gen_quotient_kernels.py emits for the
+    current circuits and compiler: a stale file would silently fall back to the interpreter (the hash lookup misses)."""
+    import sys
+    root = os.path.dirname(HERE)
+    assert subprocess.run([sys.executable, os.path.join(root, "scripts", "gen_quotient_kernels.py"), "--check"]).returncode == 0, \
+        "csrc/gen_quotient.cu is stale: run python scripts/gen_quotient_kernels.py and rebuild"

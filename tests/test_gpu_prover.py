@@ -248,6 +248,32 @@ def test_quotient_dag_and_tree_programs_agree(ctx, which, monkeypatch):
     pk_tree.close(); pk.close(); params.close()
 
 
+@pytest.mark.parametrize("which", ["shot", "board"])
+def test_generated_quotient_matches_interpreter(ctx, which, monkeypatch):
+    """h(X) as generated straight-line code (csrc/gen_quotient.cu) and through the interpreter: same proof bytes; the Shot and
+    Board keys do pick the generated kernels, other circuits (the tiny one) run the interpreter."""
+    from battlezips_halo2_b200.circuits import shot_circuit, board_circuit
+    from battlezips_halo2_b200.plonk import prover as PR
+    from tests.util_prover import VK_REPR
+    cs, cfg, asg = (shot_circuit if which == "shot" else board_circuit)(3)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    lib = ctx.lib
+    assert [lib.bz_pk_quotient_generated(pk.h, t) for t in range(3)] == [1, 1, 1]
+    monkeypatch.setenv("BZ_QUOTIENT_GENERATED", "0")
+    pk_int = PR.ProvingKey(ctx, params, job.ir, job.asg.fixed, job.mapping, VK_REPR)
+    monkeypatch.delenv("BZ_QUOTIENT_GENERATED")
+    assert [lib.bz_pk_quotient_generated(pk_int.h, t) for t in range(3)] == [0, 0, 0]
+    a, b = _prove(job, pk, [6])[0], _prove(job, pk_int, [6])[0]
+    assert first_diff(a, b) is None, first_diff(a, b)
+    assert a == job.oracle_proof(index=6)
+    pk_int.close(); pk.close(); params.close()
+    tiny = Job(*tiny_circuit(5))
+    p2, k2 = tiny.device_keys(ctx, window_bits=6)
+    assert lib.bz_pk_quotient_generated(k2.h, 0) == 0
+    k2.close(); p2.close()
+
+
 @pytest.mark.parametrize("pairs", ["0", "1"])
 def test_table_msm_degenerate_bases_and_pair_mode_parity(oracle_c, monkeypatch, pairs):
     """The table MSM in both accumulation modes -- default, and BZ_FB_PAIRS=1 (affine pre-addition of consecutive table points with one shared inversion per thread, fixedmsm.cu) --:
