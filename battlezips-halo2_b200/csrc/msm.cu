@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const Fe<SP>* __restrict_
   msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool) {
     // uniform scalars: 32 distinct keys per warp, one atomic each.  Only when neighbouring lanes collide (skewed scalars) is the
     // warp's traffic to a bucket combined -- __match_any_sync costs one step per distinct key, too slow for the common case
-    const bool dup = key != 0xffffffffu && key == __shfl_xor_sync(0xffffffffu, key, 1);
+    const uint32_t neighbour = __shfl_xor_sync(0xffffffffu, key, 1);      // unconditional: every lane takes part in the shuffle
+    const bool dup = key != 0xffffffffu && key == neighbour;
     if (__any_sync(0xffffffffu, dup)) {
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       if (key != 0xffffffffu && lane == (uint32_t)(__ffs((int)peers) - 1)) atomicAdd(&counts[key], (uint32_t)__popc(peers));
@@ -63,7 +64,8 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const Fe<SP>* __restri
   Fe<SP> s = fe_zero<SP>();
   if (i < n) s = fe_from_mont(fe_load(scalars + i));
   msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool neg) {
-    const bool dup = key != 0xffffffffu && key == __shfl_xor_sync(0xffffffffu, key, 1);
+    const uint32_t neighbour = __shfl_xor_sync(0xffffffffu, key, 1);      // unconditional: every lane takes part in the shuffle
+    const bool dup = key != 0xffffffffu && key == neighbour;
     if (__any_sync(0xffffffffu, dup)) {
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
       const uint32_t leader = (uint32_t)(__ffs((int)peers) - 1);

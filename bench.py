@@ -549,6 +549,7 @@ class ProofWorkload:
         self.lanes = []
         sharded = self.which == "board_scaled" and getattr(self, "world", 1) > 1
         wide_all = self._wide(0 if sharded else rank, B * T)
+        self.sharded = sharded
         if sharded:
             ctx.set_sharding(rank, self.world)
         for t in range(T):
@@ -705,6 +706,7 @@ class ProofWorkload:
             self._oracle = (H, op, opk)
         H, op, opk = self._oracle
         nproofs = max(1, steps)
+        co.call_timing(True)
         t = time.perf_counter()
         phases = {}
         for i in range(nproofs):
@@ -714,6 +716,9 @@ class ProofWorkload:
             for name, sec in trace.get("phase_s", {}).items():
                 phases[name] = phases.get(name, 0.0) + 1e3 * sec / nproofs
         dt = (time.perf_counter() - t) / nproofs
+        native_s, native_calls = co.call_timing(False)
+        self.cpu_native = {"native_share": round(native_s / (dt * nproofs), 4), "native_calls_per_proof": native_calls // nproofs,
+                           "note": "share of the CPU prover's wall time spent inside the C arithmetic library (the rest is the Python protocol driver)"}
         self.cpu_phases_ms = {k: round(v, 2) for k, v in phases.items()}        # the Amdahl picture of the CPU path
         return 1.0 / dt, (f"{nproofs} {self.which} proof(s) with the restated halo2_proofs 0.2.0 prover (oracle/halo2.py over the C restatement, "
                           f"{co.get_threads()} threads)"), co.get_threads(), dt
@@ -747,6 +752,7 @@ def run_reference(args, rank):
     if isinstance(wl, ProofWorkload):
         from oracle import c_oracle as co
         extra["cpu_phases_ms"] = getattr(wl, "cpu_phases_ms", None)
+        extra["cpu_native"] = getattr(wl, "cpu_native", None)
         nthreads = co.get_threads()
         co.set_threads(1)                    # the same proof on one host thread (SURVEY 8d asks for both figures)
         try:
@@ -833,6 +839,8 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
     if world > 1:
         dist.all_reduce(ms_e, op=dist.ReduceOp.MAX)
     ms_e = float(ms_e.item())
+    # a sharded proof exchanges partial sums in every MSM: its single-proof latency needs all ranks in the call
+    single_ms = wl.single_latency() if hasattr(wl, "single_latency") and (rank == 0 or getattr(wl, "sharded", False)) else None
     if rank != 0:
         return None
     value = units * world / (ms / 1e3)
@@ -877,6 +885,8 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
     if want_cpu:
         v, sample, cores, _ = wl.cpu(args.cpu_sample_log)
         cpu = {"value": v, "unit": wl.unit, "cores": cores, "kind": "port", "sample": sample}
+        if getattr(wl, "cpu_native", None):
+            cpu.update(wl.cpu_native)
         if getattr(wl, "cpu_phases_ms", None):
             cpu["phases_ms"] = wl.cpu_phases_ms          # where the CPU prover spends its time, beside kernel_ms of the GPU arm
     return {
@@ -887,7 +897,7 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
         "e2e": {"value": e2e_value, "unit": wl.unit, "h2d_bytes_per_step": wl.h2d, "d2h_bytes_per_step": wl.d2h},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "int_pipe": int_pipe, "cpu_baseline": cpu,
         "verified": getattr(wl, "check", lambda: None)(), "verify": getattr(wl, "verify_info", None),
-        "single_proof_ms": wl.single_latency() if hasattr(wl, "single_latency") and rank == 0 else None}
+        "single_proof_ms": single_ms}
 
 
 def main():
@@ -905,7 +915,9 @@ def main():
     sched = set_sync_policy(args, local_rank)
     torch.cuda.set_device(local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+        # a mismatched collective should fail in minutes, not after the default 10
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=int(os.environ.get("BZ_NCCL_TIMEOUT_S", "180"))))
     import battlezips_halo2_b200 as bz
     # a non-default torch stream: its handle is what libbzhalo2 launches on, so torch.cuda.Event timings on it
     # bracket exactly our kernels (the legacy default stream has handle 0, which the ABI reads as "private stream")

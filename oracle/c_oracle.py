@@ -24,6 +24,44 @@ def lib():
     return _lib
 
 
+class _TimedLib:
+    """Proxy over the CDLL that adds up the wall time spent inside the C library (bench.py's cpu_baseline reports it as
+    `native_share`: how much of the restated prover's time is C arithmetic rather than the Python protocol driver)."""
+
+    def __init__(self, inner):
+        self.inner, self.seconds, self.calls, self._cache = inner, 0.0, 0, {}
+
+    def __getattr__(self, name):
+        w = self._cache.get(name)
+        if w is None:
+            import time
+            f = getattr(self.inner, name)
+
+            def w(*a, _f=f, _t=time.perf_counter):
+                t0 = _t()
+                r = _f(*a)
+                self.seconds += _t() - t0
+                self.calls += 1
+                return r
+            self._cache[name] = w
+        return w
+
+
+def call_timing(on):
+    """Switch the per-call timer on / off; returns the proxy (on) or the accumulated (seconds, calls) (off)."""
+    global _lib
+    l = lib()
+    if on:
+        if not isinstance(l, _TimedLib):
+            _lib = _TimedLib(l)
+        _lib.seconds, _lib.calls = 0.0, 0
+        return _lib
+    if isinstance(l, _TimedLib):
+        _lib = l.inner
+        return l.seconds, l.calls
+    return 0.0, 0
+
+
 def _p(a):
     return a.ctypes.data_as(ctypes.c_void_p)
 

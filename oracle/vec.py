@@ -12,7 +12,10 @@ class Vec:
         self.f = f
         self.F = co.FIELDS[f]
         self.p = self.F.p
-        self.lib = co.lib()
+
+    @property
+    def lib(self):
+        return co.lib()          # looked up per call: c_oracle.call_timing() may have swapped in its timing proxy
 
     # -- conversions --
     def m(self, x):

@@ -5,7 +5,9 @@ bytes per addition -- what bench.py multiplies with the live addition counter fo
 
 The captured launch is an IPA round of a 64-proof Shot batch: 2 x 64 MSMs over n + 2 = 2050 table points, half the scalars of
 each MSM are zero, 16 windows at c = 16  ->  64 x 2050 x 16 = 2 099 200 mixed additions (counted live by the kernel when
-bz_profile_enable is on; `adds` below overrides it when a capture of another launch shape is committed).
+bz_profile_enable is on; `adds` below overrides it when a capture of another launch shape is committed).  The round-2 capture
+(profiles/capture.sh r2) runs with BZ_FIXED_WINDOW=14 so that ncu's save / restore of device memory handles 35 GB of tables
+instead of 138 GB: 19 windows -> 64 x 2050 x 19 = 2 492 800 additions per launch  (python profiles/traffic.py 2492800).
 Run:  python profiles/traffic.py [adds_per_launch]"""
 import csv, glob, json, os, re, sys
 
