@@ -437,6 +437,66 @@ __global__ void __launch_bounds__(THREADS) fb_fold_kernel(const Xyzz<BP>* __rest
   }
 }
 
+// Few MSMs per launch (one large proof: 1 - 2 MSMs of 2^16+ points): a single CTA per MSM would fold all ~75 000 thread partials
+// of the accumulate wave alone (150 serial additions per thread, 0.8 ms per call at k = 18 -- as long as the accumulation
+// itself).  Two levels instead: G CTAs per MSM fold a slice each, then one small CTA per MSM folds the G slice sums.
+constexpr int FB_PREFOLD_THREADS = 256;
+template <class BP>
+__global__ void __launch_bounds__(FB_PREFOLD_THREADS) fb_prefold_kernel(const Xyzz<BP>* __restrict__ partial, const uint32_t* __restrict__ list_count,
+                                 uint32_t n_msm, uint32_t acc_threads, Xyzz<BP>* __restrict__ slice_sums) {
+  __shared__ uint32_t wsum[33];
+  extern __shared__ uint32_t fb_off[];
+  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(fb_off + (((size_t)n_msm + 1 + 31) & ~size_t(31)));
+  const uint32_t m = blockIdx.x, g = blockIdx.y, G = gridDim.y, tid = threadIdx.x;
+  const uint32_t q = fb_plan(list_count, n_msm, acc_threads, fb_off, wsum);
+  const uint32_t lo = fb_off[m], hi = fb_off[m + 1];
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  if (hi > lo) {
+    const uint32_t w_first = lo / (32u * q), w_last = (hi - 1) / (32u * q);
+    const uint32_t npieces = (w_last - w_first + 1) * 32u, per = (npieces + G - 1) / G;
+    const uint32_t t_end = min(npieces, (g + 1) * per);
+    for (uint32_t t = g * per + tid; t < t_end; t += FB_PREFOLD_THREADS) {
+      const Xyzz<BP>* p = partial + ((size_t)w_first + m) * 32 + t;
+      Xyzz<BP> v; v.x = fe_load(&p->x); v.y = fe_load(&p->y); v.zz = fe_load(&p->zz); v.zzz = fe_load(&p->zzz);
+      acc = xyzz_add(acc, v);
+    }
+  }
+  sh[tid] = acc;
+  __syncthreads();
+  for (uint32_t d = FB_PREFOLD_THREADS >> 1; d > 0; d >>= 1) {
+    if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    Xyzz<BP>* o = slice_sums + (size_t)m * G + g;
+    fe_store(&o->x, sh[0].x); fe_store(&o->y, sh[0].y); fe_store(&o->zz, sh[0].zz); fe_store(&o->zzz, sh[0].zzz);
+  }
+}
+// G (a power of two <= 64) threads per MSM
+template <class BP, bool XYZZ_OUT>
+__global__ void __launch_bounds__(64) fb_fold_slices_kernel(const Xyzz<BP>* __restrict__ slice_sums, void* __restrict__ out_v) {
+  __shared__ Xyzz<BP> sh[64];
+  const uint32_t m = blockIdx.x, tid = threadIdx.x, G = blockDim.x;
+  const Xyzz<BP>* p = slice_sums + (size_t)m * G + tid;
+  Xyzz<BP> v; v.x = fe_load(&p->x); v.y = fe_load(&p->y); v.zz = fe_load(&p->zz); v.zzz = fe_load(&p->zzz);
+  sh[tid] = v;
+  __syncthreads();
+  for (uint32_t d = G >> 1; d > 0; d >>= 1) {
+    if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) {
+    if (XYZZ_OUT) {
+      Xyzz<BP>* o = reinterpret_cast<Xyzz<BP>*>(out_v) + m;
+      fe_store(&o->x, sh[0].x); fe_store(&o->y, sh[0].y); fe_store(&o->zz, sh[0].zz); fe_store(&o->zzz, sh[0].zzz);
+    } else {
+      Affine<BP>* out = reinterpret_cast<Affine<BP>*>(out_v);
+      Affine<BP> r = xyzz_to_affine(sh[0]);
+      fe_store(&out[m].x, r.x); fe_store(&out[m].y, r.y);
+    }
+  }
+}
+
 void field_op_run(Ctx* ctx, int field, int op, const void* a, const void* b, void* out, uint64_t n);      // elementwise.cu (op 3 = batch inversion)
 
 template <class BP, class SP>
@@ -477,7 +537,7 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
     const uint32_t nm = std::min(max_nm, n_msm - m0);
     ctx->scratch[0].ensure((size_t)nm * list_stride * 4);
     ctx->scratch[1].ensure((size_t)nm * 4 + 64);
-    ctx->scratch[3].ensure(((size_t)acc_threads + 32 * (size_t)nm + 32) * sizeof(Xyzz<BP>));
+    ctx->scratch[3].ensure(((size_t)acc_threads + 32 * (size_t)nm + 32 + 64 * 256) * sizeof(Xyzz<BP>));   // thread partials + slice sums of the two-level fold
     uint32_t* lists = ctx->scratch[0].as<uint32_t>();
     uint32_t* counts = ctx->scratch[1].as<uint32_t>();
     Xyzz<BP>* partial = ctx->scratch[3].as<Xyzz<BP>>();
@@ -502,10 +562,21 @@ static void fixed_msm_run_t(Ctx* ctx, const FixedBase& fb, const void* const* d_
         BigKernelScope bigs(ctx);
         fb_accumulate_kernel<BP><<<acc_ctas, FB_THREADS, smem, bigs.s>>>(fb.table.as<Affine<BP>>(), lists, list_stride, counts, nm, partial, cnt);
       }
-      // fold: offsets + one XYZZ slot per thread in dynamic shared memory; wide CTAs when only a few MSMs are in flight
+      // fold: offsets + one XYZZ slot per thread in dynamic shared memory.  A launch with many thread partials per MSM (a few large
+      // MSMs: one big proof) folds in two levels, G CTAs per MSM first
+      const uint64_t pieces_per_msm = ((uint64_t)acc_threads + 32 * (uint64_t)nm) / nm;
+      uint32_t G = 1;
+      while (G < 64 && nm * G < 256 && pieces_per_msm / (G * 2) >= 2 * FB_PREFOLD_THREADS) G *= 2;
       const bool wide = nm < 48;
       const size_t fsm = (((size_t)nm + 1 + 31) & ~size_t(31)) * 4 + (size_t)(wide ? FB_FOLD_THREADS_WIDE : FB_FOLD_THREADS) * sizeof(Xyzz<BP>);
-      if (wide) {
+      if (G > 1) {
+        Xyzz<BP>* slice_sums = partial + (size_t)acc_threads + 32 * (size_t)nm + 32;
+        const size_t psm = (((size_t)nm + 1 + 31) & ~size_t(31)) * 4 + (size_t)FB_PREFOLD_THREADS * sizeof(Xyzz<BP>);
+        fb_prefold_kernel<BP><<<dim3(nm, G), FB_PREFOLD_THREADS, psm, st>>>(partial, counts, nm, acc_threads, slice_sums);
+        if (xyzz_out) fb_fold_slices_kernel<BP, true><<<nm, G, 0, st>>>(slice_sums, (Xyzz<BP>*)d_out + m0);
+        else fb_fold_slices_kernel<BP, false><<<nm, G, 0, st>>>(slice_sums, (Affine<BP>*)d_out + m0);
+        ctx->kernel_launches += 1;
+      } else if (wide) {
         if (xyzz_out) fb_fold_kernel<BP, true, FB_FOLD_THREADS_WIDE><<<nm, FB_FOLD_THREADS_WIDE, fsm, st>>>(partial, counts, nm, acc_threads, (Xyzz<BP>*)d_out + m0);
         else fb_fold_kernel<BP, false, FB_FOLD_THREADS_WIDE><<<nm, FB_FOLD_THREADS_WIDE, fsm, st>>>(partial, counts, nm, acc_threads, (Affine<BP>*)d_out + m0);
       } else {

@@ -40,11 +40,29 @@ __device__ __forceinline__ void msm_for_each_digit(const Fe<SP>& canonical, uint
   }
 }
 
+// Where the scalars of a batch of MSMs over the SAME bases live: one contiguous array (`single`), or per MSM a main polynomial of
+// n_main scalars plus a few trailing extras (blinding factors; the U / W terms of the IPA) -- the layout the table MSM takes
+// too.  `first` shifts the window for a point-range shard.
+template <class SP> struct ScalarSrc {
+  const Fe<SP>* single;
+  const Fe<SP>* const* mains;
+  const Fe<SP>* const* extras;
+  uint32_t n_main, first;
+  __device__ __forceinline__ Fe<SP> load(uint32_t m, uint32_t i) const {
+    if (single) return fe_load(single + i);
+    const uint32_t g = i + first;
+    return g < n_main ? fe_load(mains[m] + g) : fe_load(extras[m] + (g - n_main));
+  }
+};
+
+// grid = (ceil(n / 256), MSMs of the batch).  A batch is sorted as ONE problem with  MSMs x W  "virtual windows": the key of MSM m
+// is shifted by m * W * nb, and everything downstream (scan, segments, bucket sums, window reduction) only sees more windows.
 template <class SP>
-__global__ void __launch_bounds__(256) msm_hist_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb, uint32_t* __restrict__ counts) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) msm_hist_kernel(ScalarSrc<SP> src, uint32_t n, uint32_t c, uint32_t W, uint32_t nb, uint32_t* __restrict__ counts) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, m = blockIdx.y;
+  counts += (size_t)m * W * nb;
   Fe<SP> s = fe_zero<SP>();
-  if (i < n) s = fe_from_mont(fe_load(scalars + i));
+  if (i < n) s = fe_from_mont(src.load(m, i));
   msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool) {
     // uniform scalars: 32 distinct keys per warp, one atomic each.  Only when neighbouring lanes collide (skewed scalars) is the
     // warp's traffic to a bucket combined -- __match_any_sync costs one step per distinct key, too slow for the common case
@@ -58,13 +76,14 @@ __global__ void __launch_bounds__(256) msm_hist_kernel(const Fe<SP>* __restrict_
 }
 
 template <class SP>
-__global__ void __launch_bounds__(256) msm_scatter_kernel(const Fe<SP>* __restrict__ scalars, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
+__global__ void __launch_bounds__(256) msm_scatter_kernel(ScalarSrc<SP> src, uint32_t n, uint32_t c, uint32_t W, uint32_t nb,
                                                           uint32_t* __restrict__ cursor, uint32_t* __restrict__ sorted) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31, m = blockIdx.y;
+  cursor += (size_t)m * W * nb;
   Fe<SP> s = fe_zero<SP>();
-  if (i < n) s = fe_from_mont(fe_load(scalars + i));
+  if (i < n) s = fe_from_mont(src.load(m, i));
   msm_for_each_digit<SP>(s, c, W, nb, [&](uint32_t key, bool neg) {
-    const uint32_t neighbour = __shfl_xor_sync(0xffffffffu, key, 1);      // unconditional: every lane takes part in the shuffle
+    const uint32_t neighbour = __shfl_xor_sync(0xffffffffu, key, 1);
     const bool dup = key != 0xffffffffu && key == neighbour;
     if (__any_sync(0xffffffffu, dup)) {
       const uint32_t peers = __match_any_sync(0xffffffffu, key);
@@ -77,12 +96,26 @@ __global__ void __launch_bounds__(256) msm_scatter_kernel(const Fe<SP>* __restri
   });
 }
 
-// ---- 2. exclusive scan of bucket counts over all windows (single CTA; W*nb <= 2^21) ------------
-__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets,
-                                uint32_t* __restrict__ cursor, uint32_t total) {
+// ---- 2. exclusive scan of the bucket counts over all (virtual) windows, in three launches: sums of 2048-entry tiles, a single
+// CTA scanning the tile sums, and a rescan of every tile with its carry-in (a single-CTA scan of 2^19 counts cost 1 ms per MSM
+// at k = 20 -- more than the sort itself).  Writes offsets and, when asked, a second copy that the scatter uses as its cursors.
+constexpr uint32_t SCAN_TILE = 2048;                 // 256 threads x 8 entries
+__global__ void __launch_bounds__(256) msm_tile_sum_kernel(const uint32_t* __restrict__ counts, uint32_t total, uint32_t* __restrict__ tile_sum) {
+  __shared__ uint32_t wsum[8];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8;
+  uint32_t sum = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j) if (base + j < total) sum += counts[base + j];
+  for (uint32_t d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+  if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) { uint32_t t = 0; for (uint32_t j = 0; j < 8; ++j) t += wsum[j]; tile_sum[blockIdx.x] = t; }
+}
+// single CTA: exclusive scan of `total` values in place-compatible form (offsets may alias nothing of counts)
+__global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* __restrict__ offsets, uint32_t total) {
   __shared__ uint32_t part[1024];
   uint32_t tid = threadIdx.x, per = (total + blockDim.x - 1) / blockDim.x;
-  uint32_t lo = tid * per, hi = min(lo + per, total), sum = 0;
+  uint32_t lo = min(tid * per, total), hi = min(lo + per, total), sum = 0;
   for (uint32_t j = lo; j < hi; ++j) sum += counts[j];
   part[tid] = sum;
   __syncthreads();
@@ -93,7 +126,31 @@ __global__ void msm_scan_kernel(const uint32_t* __restrict__ counts, uint32_t* _
     __syncthreads();
   }
   uint32_t run = part[tid] - sum;
-  for (uint32_t j = lo; j < hi; ++j) { offsets[j] = run; cursor[j] = run; run += counts[j]; }
+  for (uint32_t j = lo; j < hi; ++j) { uint32_t cnt = counts[j]; offsets[j] = run; run += cnt; }
+}
+__global__ void __launch_bounds__(256) msm_tile_scan_kernel(const uint32_t* __restrict__ counts, const uint32_t* __restrict__ tile_off, uint32_t total,
+                                                            uint32_t* __restrict__ offsets, uint32_t* __restrict__ cursor) {
+  __shared__ uint32_t wsum[8];
+  const uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * 8, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t v[8], sum = 0;
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j) { v[j] = base + j < total ? counts[base + j] : 0u; sum += v[j]; }
+  uint32_t inc = sum;                                     // inclusive scan of the per-thread sums inside the warp
+  for (uint32_t d = 1; d < 32; d <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += t; }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t run = tile_off[blockIdx.x] + inc - sum;
+  for (uint32_t j = 0; j < warp; ++j) run += wsum[j];
+#pragma unroll
+  for (uint32_t j = 0; j < 8; ++j)
+    if (base + j < total) { offsets[base + j] = run; if (cursor) cursor[base + j] = run; run += v[j]; }
+}
+// tile_scratch: 2 * ceil(total / SCAN_TILE) words
+static void msm_exclusive_scan(cudaStream_t st, const uint32_t* counts, uint32_t total, uint32_t* offsets, uint32_t* cursor, uint32_t* tile_scratch) {
+  const uint32_t tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+  msm_tile_sum_kernel<<<tiles, 256, 0, st>>>(counts, total, tile_scratch);
+  msm_scan_kernel<<<1, 1024, 0, st>>>(tile_scratch, tile_scratch + tiles, tiles);
+  msm_tile_scan_kernel<<<tiles, 256, 0, st>>>(counts, tile_scratch + tiles, total, offsets, cursor);
 }
 
 // ---- 4. bucket accumulation, skew-proof: every bucket's entry list is cut into segments of <= SEG
@@ -116,7 +173,17 @@ __global__ void msm_segmap_kernel(const uint32_t* __restrict__ nseg, const uint3
   uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
   if (gb >= total_buckets) return;
   uint32_t o = segoff[gb], m = nseg[gb];
+  if (m > FOLD_SERIAL_MAX) return;            // a hot bucket has thousands of segments: msm_segmap_large_kernel
   for (uint32_t j = 0; j < m; ++j) seg_bucket[o + j] = gb;
+}
+__global__ void __launch_bounds__(256) msm_segmap_large_kernel(const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff,
+                                  const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list, uint32_t max_large,
+                                  uint32_t* __restrict__ seg_bucket) {
+  const uint32_t nl = min(*large_count, max_large);
+  for (uint32_t li = blockIdx.x; li < nl; li += gridDim.x) {
+    const uint32_t gb = large_list[li], o = segoff[gb], m = nseg[gb];
+    for (uint32_t j = threadIdx.x; j < m; j += blockDim.x) seg_bucket[o + j] = gb;
+  }
 }
 
 template <class BP>
@@ -233,14 +300,19 @@ __global__ void __launch_bounds__(256) msm_reduce_kernel(const Xyzz<BP>* __restr
   if (tid == 0) xyzz_store(window_partials + (size_t)w * splits + sidx, sh[0]);
 }
 
-// sum the S partials of every window (one thread per window)
+// sum the S partials of every window: one CTA of S threads per window, shared-memory tree (S is a power of two <= 128)
 template <class BP>
-__global__ void msm_window_sum_kernel(const Xyzz<BP>* __restrict__ window_partials, uint32_t W, uint32_t splits, Xyzz<BP>* __restrict__ window_sums) {
-  uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
-  if (w >= W) return;
-  Xyzz<BP> acc = xyzz_identity<BP>();
-  for (uint32_t j = 0; j < splits; ++j) acc = xyzz_add(acc, xyzz_load(window_partials + (size_t)w * splits + j));
-  xyzz_store(window_sums + w, acc);
+__global__ void __launch_bounds__(128) msm_window_sum_kernel(const Xyzz<BP>* __restrict__ window_partials, uint32_t splits, Xyzz<BP>* __restrict__ window_sums) {
+  extern __shared__ unsigned char smem_raw[];
+  Xyzz<BP>* sh = reinterpret_cast<Xyzz<BP>*>(smem_raw);
+  const uint32_t w = blockIdx.x, tid = threadIdx.x;
+  sh[tid] = xyzz_load(window_partials + (size_t)w * splits + tid);
+  __syncthreads();
+  for (uint32_t d = splits >> 1; d > 0; d >>= 1) {
+    if (tid < d) sh[tid] = xyzz_add(sh[tid], sh[tid + d]);
+    __syncthreads();
+  }
+  if (tid == 0) xyzz_store(window_sums + w, sh[0]);
 }
 
 // ---- 6. Horner over windows: R = sum_w 2^(c w) R_w ; writes Jacobian (x,y,z) -----------------------
@@ -290,30 +362,25 @@ static uint32_t pick_window(uint32_t n) {
   return best;
 }
 
+// One chunk of a batch: `n_msm` MSMs over the same `n` bases, sorted and accumulated as one problem with n_msm * W windows.
 template <class BP, class SP>
-static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, uint32_t n, Jac<BP>* out, int c_override) {
+static void msm_run_chunk(Ctx* ctx, const ScalarSrc<SP>& src, const Affine<BP>* bases, uint32_t n, uint32_t n_msm, uint32_t c, Jac<BP>* out) {
   cudaStream_t st = ctx->stream;
   const bzh::Field& BF = ctx->field(BP::ID);
-  if (n == 0) {
-    Jac<BP> id{}; memset(&id, 0, sizeof(id));
-    bzh::Fe one = BF.one(); memcpy(id.y.l, one.l, 32);
-    BZ_CUDA(cudaMemcpyAsync(out, &id, sizeof(id), cudaMemcpyHostToDevice, st));
-    BZ_CUDA(cudaStreamSynchronize(st));
-    return;
-  }
-  uint32_t c = c_override > 0 ? (uint32_t)c_override : pick_window(n);
-  uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1), total = W * nb;
-  BZ_CHECK(total <= (1u << 21), "msm: too many buckets");
-  const uint64_t items64 = (uint64_t)W * n;
-  BZ_CHECK(items64 < (1ull << 31), "msm: n * windows too large");
-  const uint32_t items = (uint32_t)items64;
-  uint32_t splits = nb >= 4096 ? nb / 2048 : 1;                  // CTAs per window in the reduction
-  // scratch layout
-  uint32_t max_segs = (uint32_t)(items64 / SEG + total);
-  ctx->scratch[0].ensure((size_t)items * 4);                      // point indices grouped by (window, bucket)
+  const uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1), WT = W * n_msm, total = WT * nb;
+  const uint64_t items64 = (uint64_t)WT * n;
+  BZ_CHECK(items64 < (1ull << 31) && (uint64_t)WT * nb < (1ull << 28), "msm: batch too large");
+  // CTAs per window in the reduction: enough of them to fill the GPU when the batch is small, but at least 2048 buckets (8 per
+  // thread) each -- every thread pays a ~25-operation scalar multiplication of its running sum on top of 2 additions per bucket,
+  // so 2 buckets per thread (measured: 1.5 ms per 2^22-point MSM) lose against 8 (0.8 ms)
+  uint32_t splits = 1;
+  while (splits < 128 && nb / (splits * 2) >= 2048 && (uint64_t)WT * splits < 4 * 148) splits *= 2;
+  const uint32_t max_segs = (uint32_t)(items64 / SEG + total);
   const uint32_t max_large = (uint32_t)(items64 / (SEG * FOLD_SERIAL_MAX) + 1);
-  ctx->scratch[2].ensure((size_t)total * 4 * 5 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4);
-  ctx->scratch[3].ensure((size_t)(total + W * splits + W + max_segs) * sizeof(Xyzz<BP>));
+  const uint32_t tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+  ctx->scratch[0].ensure((size_t)items64 * 4);                    // point indices grouped by (MSM, window, bucket)
+  ctx->scratch[2].ensure((size_t)total * 4 * 5 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4 + (size_t)tiles * 8 + 64);
+  ctx->scratch[3].ensure(((size_t)total + (size_t)WT * splits + WT + max_segs) * sizeof(Xyzz<BP>));
   uint32_t* sorted = ctx->scratch[0].as<uint32_t>();
   uint32_t* counts = ctx->scratch[2].as<uint32_t>();
   uint32_t* offsets = counts + total;
@@ -323,55 +390,100 @@ static void msm_run_t(Ctx* ctx, const Fe<SP>* scalars, const Affine<BP>* bases, 
   uint32_t* seg_bucket = cursor + total;
   uint32_t* large_count = seg_bucket + max_segs;
   uint32_t* large_list = large_count + 4;
+  uint32_t* tile_scratch = large_list + max_large;
   Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
   Xyzz<BP>* wparts = buckets + total;
-  Xyzz<BP>* wsums = wparts + (size_t)W * splits;
-  Xyzz<BP>* partial = wsums + W;
+  Xyzz<BP>* wsums = wparts + (size_t)WT * splits;
+  Xyzz<BP>* partial = wsums + WT;
 
+  const dim3 sgrid((n + 255) / 256, n_msm);
   { ProfScope p(ctx, PROF_MSM_DIGITS);
     BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)total * 4, st));
-    msm_hist_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, counts); }
+    msm_hist_kernel<SP><<<sgrid, 256, 0, st>>>(src, n, c, W, nb, counts); }
   { ProfScope p(ctx, PROF_MSM_SORT);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(counts, offsets, cursor, total);
-    msm_scatter_kernel<SP><<<(n + 255) / 256, 256, 0, st>>>(scalars, n, c, W, nb, cursor, sorted);
+    msm_exclusive_scan(st, counts, total, offsets, cursor, tile_scratch);
+    msm_scatter_kernel<SP><<<sgrid, 256, 0, st>>>(src, n, c, W, nb, cursor, sorted);
     BZ_CUDA(cudaMemsetAsync(large_count, 0, 16, st));
     msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg, large_count, large_list, max_large);
-    msm_scan_kernel<<<1, 1024, 0, st>>>(nseg, segoff, seg_bucket /*scratch copy, overwritten below*/, total);
-    msm_segmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket); }
+    msm_exclusive_scan(st, nseg, total, segoff, nullptr, tile_scratch);
+    msm_segmap_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket);
+    msm_segmap_large_kernel<<<std::min<uint32_t>(max_large, 2 * 148), 256, 0, st>>>(nseg, segoff, large_count, large_list, max_large, seg_bucket); }
   { ProfScope p(ctx, PROF_MSM_BUCKET);
     msm_segment_kernel<BP><<<(max_segs + 127) / 128, 128, 0, st>>>(bases, sorted, offsets, counts, nseg, segoff, seg_bucket, total, max_segs, partial);
     msm_bucket_fold_kernel<BP><<<(total + 127) / 128, 128, 0, st>>>(partial, nseg, segoff, total, buckets);
     msm_bucket_fold_large_kernel<BP><<<std::min<uint32_t>(max_large, 4 * 148), 256, 0, st>>>(partial, nseg, segoff, large_count, large_list, max_large, buckets); }
-  uint32_t span = nb / splits;
-  uint32_t rthreads = span >= 256 ? 256 : (span >= 32 ? span : 32);
+  const uint32_t span = nb / splits;
+  const uint32_t rthreads = span >= 256 ? 256 : (span >= 32 ? span : 32);
   { ProfScope p(ctx, PROF_MSM_REDUCE);
-    msm_reduce_kernel<BP><<<dim3(W, splits), rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, splits, wparts);
-    msm_window_sum_kernel<BP><<<(W + 31) / 32, 32, 0, st>>>(wparts, W, splits, wsums); }
-  ctx->kernel_launches += 12;
+    msm_reduce_kernel<BP><<<dim3(WT, splits), rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, splits, wparts);
+    msm_window_sum_kernel<BP><<<WT, splits, splits * sizeof(Xyzz<BP>), st>>>(wparts, splits, wsums); }
+  ctx->kernel_launches += 16;
   BZ_CUDA(cudaGetLastError());
-  // ---- Horner over the W window sums on the host: 255 sequential doublings cost ~1.1 ms on one GPU thread and
-  // ~0.1 ms on a CPU core; the data is W * 128 B.
+  // ---- Horner over the W window sums of every MSM on the host: 255 sequential doublings cost ~1.1 ms on one GPU thread and
+  // ~0.1 ms on a CPU core; the data is W * 128 B per MSM, one synchronisation per chunk.
   {
     ProfScope p(ctx, PROF_MSM_COMBINE);
-    std::vector<bzh::HXyzz> hw(W);
-    BZ_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)W * sizeof(bzh::HXyzz), cudaMemcpyDeviceToHost, st));
+    std::vector<bzh::HXyzz> hw(WT);
+    BZ_CUDA(cudaMemcpyAsync(hw.data(), wsums, (size_t)WT * sizeof(bzh::HXyzz), cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
-    bzh::HXyzz acc = bzh::hx_identity();
-    for (int w = (int)W - 1; w >= 0; --w) {
-      for (uint32_t j = 0; j < c; ++j) acc = bzh::hx_dbl(BF, acc);
-      acc = bzh::hx_add(BF, acc, hw[w]);
+    std::vector<bzh::Fe> jac(3 * (size_t)n_msm);
+    for (uint32_t m = 0; m < n_msm; ++m) {
+      bzh::HXyzz acc = bzh::hx_identity();
+      for (int w = (int)W - 1; w >= 0; --w) {
+        for (uint32_t j = 0; j < c; ++j) acc = bzh::hx_dbl(BF, acc);
+        acc = bzh::hx_add(BF, acc, hw[(size_t)m * W + w]);
+      }
+      bzh::hx_to_jac(BF, acc, &jac[3 * (size_t)m]);
     }
-    bzh::Fe jac[3];
-    bzh::hx_to_jac(BF, acc, jac);
-    BZ_CUDA(cudaMemcpyAsync(out, jac, 96, cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync(out, jac.data(), (size_t)n_msm * 96, cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaStreamSynchronize(st));
+  }
+}
+
+template <class BP, class SP>
+static void msm_run_t(Ctx* ctx, ScalarSrc<SP> src, const Affine<BP>* bases, uint32_t n, uint32_t n_msm, Jac<BP>* out, int c_override) {
+  cudaStream_t st = ctx->stream;
+  const bzh::Field& BF = ctx->field(BP::ID);
+  if (n_msm == 0) return;
+  if (n == 0) {
+    std::vector<Jac<BP>> id(n_msm);
+    memset(id.data(), 0, id.size() * sizeof(Jac<BP>));
+    bzh::Fe one = BF.one();
+    for (auto& j : id) memcpy(j.y.l, one.l, 32);
+    BZ_CUDA(cudaMemcpyAsync(out, id.data(), id.size() * sizeof(Jac<BP>), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaStreamSynchronize(st));
+    return;
+  }
+  const uint32_t c = c_override > 0 ? (uint32_t)c_override : pick_window(n);
+  const uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1);
+  BZ_CHECK((uint64_t)W * nb <= (1u << 21), "msm: too many buckets");
+  BZ_CHECK((uint64_t)W * n < (1ull << 31), "msm: n * windows too large");
+  // MSMs per chunk: at most 16, and under 2^30 sorted entries / 2^24 buckets (about 4 GB of scratch at k = 20)
+  uint32_t chunk = 16;
+  while (chunk > 1 && ((uint64_t)chunk * W * n >= (1ull << 30) || (uint64_t)chunk * W * nb > (1ull << 24))) chunk /= 2;
+  for (uint32_t m0 = 0; m0 < n_msm; m0 += chunk) {
+    ScalarSrc<SP> sub = src;
+    if (!sub.single) { sub.mains += m0; sub.extras += m0; }
+    else BZ_CHECK(n_msm == 1, "msm: a contiguous scalar array is one MSM");
+    msm_run_chunk<BP, SP>(ctx, sub, bases, n, std::min(chunk, n_msm - m0), c, out + m0);
   }
 }
 
 // curve: 0 = Vesta (scalars Fp, coordinates Fq), 1 = Pallas (scalars Fq, coordinates Fp).  All pointers device.
 void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override) {
-  if (curve == 0) msm_run_t<FqP, FpP>(ctx, (const Fe<FpP>*)scalars, (const Affine<FqP>*)bases, n, (Jac<FqP>*)out_jac, c_override);
-  else msm_run_t<FpP, FqP>(ctx, (const Fe<FqP>*)scalars, (const Affine<FpP>*)bases, n, (Jac<FpP>*)out_jac, c_override);
+  if (curve == 0) msm_run_t<FqP, FpP>(ctx, ScalarSrc<FpP>{(const Fe<FpP>*)scalars, nullptr, nullptr, 0, 0}, (const Affine<FqP>*)bases, n, 1, (Jac<FqP>*)out_jac, c_override);
+  else msm_run_t<FpP, FqP>(ctx, ScalarSrc<FqP>{(const Fe<FqP>*)scalars, nullptr, nullptr, 0, 0}, (const Affine<FpP>*)bases, n, 1, (Jac<FpP>*)out_jac, c_override);
+}
+
+// A batch of MSMs over the same bases (the commitments of one round of create_proof): MSM m takes scalar g = first + i  (i < n)
+// from d_main[m][g] when g < n_main, else d_extra[m][g - n_main]; `bases` is the base of point `first`.  d_main / d_extra are
+// device arrays of device pointers; out_jac receives n_msm Jacobian points (96 B each).
+void msm_run_batch(Ctx* ctx, int curve, const void* const* d_main, const void* const* d_extra, uint32_t n_main, uint32_t first, uint32_t n,
+                   const void* bases, uint32_t n_msm, void* out_jac) {
+  if (curve == 0) msm_run_t<FqP, FpP>(ctx, ScalarSrc<FpP>{nullptr, (const Fe<FpP>* const*)d_main, (const Fe<FpP>* const*)d_extra, n_main, first},
+                                      (const Affine<FqP>*)bases, n, n_msm, (Jac<FqP>*)out_jac, 0);
+  else msm_run_t<FpP, FqP>(ctx, ScalarSrc<FqP>{nullptr, (const Fe<FqP>* const*)d_main, (const Fe<FqP>* const*)d_extra, n_main, first},
+                           (const Affine<FpP>*)bases, n, n_msm, (Jac<FpP>*)out_jac, 0);
 }
 
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n) {

@@ -401,23 +401,19 @@ API int bz_params_commit_batch_dev(bz_ctx* ctx, bz_params* params, int lagrange_
     d_extra.ensure((size_t)count * nextra * 32); d_ptrs.ensure((size_t)2 * count * sizeof(void*));
     BZ_CUDA(cudaMemsetAsync(d_extra.p, 0, (size_t)count * nextra * 32, st));
     BZ_CUDA(cudaMemcpy2DAsync(d_extra.p, (size_t)nextra * 32, d_blinds, 32, 32, count, cudaMemcpyDeviceToDevice, st));   // blind -> the w slot
+    std::vector<void*> ptrs((size_t)2 * count);
+    for (uint32_t j = 0; j < count; ++j) { ptrs[j] = (char*)d_polys + (size_t)j * p.n * 32; ptrs[count + j] = (char*)d_extra.p + (size_t)j * nextra * 32; }
+    BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
     if (p.use_tables) {
-      std::vector<void*> ptrs((size_t)2 * count);
-      for (uint32_t j = 0; j < count; ++j) { ptrs[j] = (char*)d_polys + (size_t)j * p.n * 32; ptrs[count + j] = (char*)d_extra.p + (size_t)j * nextra * 32; }
-      BZ_CUDA(cudaMemcpyAsync(d_ptrs.p, ptrs.data(), ptrs.size() * sizeof(void*), cudaMemcpyHostToDevice, st));
       fixed_msm_run(C, fb, (const void* const*)d_ptrs.p, p.n, (const void* const*)((void**)d_ptrs.p + count), count, 1, d_out_affine);
-      BZ_CUDA(cudaStreamSynchronize(st));          // ptrs goes out of scope
     } else {
-      DevBuf &d_in = C->stage[5], &d_jac = C->stage[0];
-      d_in.ensure((size_t)fb.npts * 32); d_jac.ensure((size_t)count * 96);
-      for (uint32_t j = 0; j < count; ++j) {
-        BZ_CUDA(cudaMemcpyAsync(d_in.p, (const char*)d_polys + (size_t)j * p.n * 32, (size_t)p.n * 32, cudaMemcpyDeviceToDevice, st));
-        BZ_CUDA(cudaMemcpyAsync((char*)d_in.p + (size_t)p.n * 32, (char*)d_extra.p + (size_t)j * nextra * 32, (size_t)nextra * 32, cudaMemcpyDeviceToDevice, st));
-        msm_run(C, p.curve, d_in.p, lagrange_basis ? p.gl_w.p : p.g_w_u.p, fb.npts, (char*)d_jac.p + (size_t)j * 96, 0);
-      }
+      DevBuf& d_jac = C->stage[0];
+      d_jac.ensure((size_t)count * 96);
+      msm_run_batch(C, p.curve, (const void* const*)d_ptrs.p, (const void* const*)((void**)d_ptrs.p + count), p.n, 0, fb.npts,
+                    lagrange_basis ? p.gl_w.p : p.g_w_u.p, count, d_jac.p);
       jac_to_affine_run(C, p.curve, d_jac.p, d_out_affine, count);
-      BZ_CUDA(cudaStreamSynchronize(st));
     }
+    BZ_CUDA(cudaStreamSynchronize(st));          // ptrs goes out of scope
   });
 }
 
@@ -834,46 +830,41 @@ struct Prover {
       fixed_msm_run(C, fb, (const void* const*)w.ptrs.p, n, (const void* const*)((void**)w.ptrs.p + n_msm), n_msm, chunks, w.commits.p, true);
       return;
     }
-    const uint32_t npts = fb.npts, nextra = npts - n;
+    // bucket MSM (k >= 20, or forced): the MSMs of the call go through the sort / accumulate / reduce pipeline as ONE batch
+    const uint32_t npts = fb.npts;
+    const int curve = pk.params->curve;
     const void* bases = lagrange ? pk.params->gl_w.p : pk.params->g_w_u.p;
-    w.msm_in.ensure((size_t)npts * 32);
+    BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+    BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + n_msm, extrap.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+    const void* const* dm = (const void* const*)w.ptrs.p;
+    const void* const* de = dm + n_msm;
     w.msm_jac.ensure((size_t)n_msm * 96);
-    auto stage = [&](uint32_t j) {
-      BZ_CUDA(cudaMemcpyAsync(w.msm_in.p, mainp[j], (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
-      BZ_CUDA(cudaMemcpyAsync((char*)w.msm_in.p + (size_t)n * 32, extrap[j], (size_t)nextra * 32, cudaMemcpyDeviceToDevice, st));
-    };
     if (world > 1 && n_msm >= world) {
       // column deal: rank r owns the contiguous MSMs [r * per, (r + 1) * per); one all-gather of per x 96 B per rank
       const uint32_t per = (n_msm + world - 1) / world, lo = std::min(n_msm, rank * per), hi = std::min(n_msm, lo + per);
       BZ_CHECK((size_t)per * 96 <= C->shard_cap, "sharding exchange buffer too small");
       BZ_CUDA(cudaMemsetAsync(C->shard_send, 0, (size_t)per * 96, st));
-      for (uint32_t j = lo; j < hi; ++j) { stage(j); msm_run(C, pk.params->curve, w.msm_in.p, bases, npts, (char*)C->shard_send + (size_t)(j - lo) * 96, 0); }
+      msm_run_batch(C, curve, dm + lo, de + lo, n, 0, npts, bases, hi - lo, C->shard_send);
       if (C->shard_exchange(C->shard_user, (size_t)per * 96) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
-      jac_to_affine_run(C, pk.params->curve, C->shard_recv, w.commits.p, n_msm);          // rank-major = MSM order
+      jac_to_affine_run(C, curve, C->shard_recv, w.commits.p, n_msm);          // rank-major = MSM order
       return;
     }
     if (world > 1) {
       // fewer MSMs than ranks (random polynomial, q', S, the two IPA terms): every MSM split by point range, the partials summed
       BZ_CHECK((size_t)n_msm * 96 <= C->shard_cap, "sharding exchange buffer too small");
       const uint32_t base = npts / world, rem = npts % world, plo = rank * base + std::min(rank, rem), cnt = base + (rank < rem ? 1u : 0u);
-      for (uint32_t j = 0; j < n_msm; ++j) {
-        stage(j);
-        msm_run(C, pk.params->curve, (const char*)w.msm_in.p + (size_t)plo * 32, (const char*)bases + (size_t)plo * 64, cnt, (char*)C->shard_send + (size_t)j * 96, 0);
-      }
+      msm_run_batch(C, curve, dm, de, n, plo, cnt, (const char*)bases + (size_t)plo * 64, n_msm, C->shard_send);
       if (C->shard_exchange(C->shard_user, (size_t)n_msm * 96) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
       w.msm_jac.ensure((size_t)n_msm * world * 96);
       for (uint32_t j = 0; j < n_msm; ++j) {
         // partials of MSM j sit at recv[r][j]: gather them contiguously, then one kernel adds them and normalises
         BZ_CUDA(cudaMemcpy2DAsync((char*)w.msm_jac.p + (size_t)j * world * 96, 96, (const char*)C->shard_recv + (size_t)j * 96, (size_t)n_msm * 96, 96, world, cudaMemcpyDeviceToDevice, st));
-        jac_sum_run(C, pk.params->curve, (const char*)w.msm_jac.p + (size_t)j * world * 96, world, (char*)w.commits.p + (size_t)j * 64);
+        jac_sum_run(C, curve, (const char*)w.msm_jac.p + (size_t)j * world * 96, world, (char*)w.commits.p + (size_t)j * 64);
       }
       return;
     }
-    for (uint32_t j = 0; j < n_msm; ++j) {
-      stage(j);
-      msm_run(C, pk.params->curve, w.msm_in.p, bases, npts, (char*)w.msm_jac.p + (size_t)j * 96, 0);
-    }
-    jac_to_affine_run(C, pk.params->curve, w.msm_jac.p, w.commits.p, n_msm);
+    msm_run_batch(C, curve, dm, de, n, 0, npts, bases, n_msm, w.msm_jac.p);
+    jac_to_affine_run(C, curve, w.msm_jac.p, w.commits.p, n_msm);
   }
   // Commitments come back unnormalised from the table MSM (XYZZ, 128 B): one batched inversion on the host for the
   // whole call (Montgomery's trick, ~9 host multiplications per point) instead of a single-thread Fermat chain per
@@ -1648,12 +1639,8 @@ API int bz_ipa_round(bz_ctx* ctx, bz_ipa* ipa, const void* z, const void* l_rand
     if (pr.use_tables) fixed_msm_run(C, pr.fb_g, (const void* const*)ipa->ptrs.p, n, (const void* const*)((void**)ipa->ptrs.p + 2), 2, 16, ipa->out.p, false);
     else {
       // extras are [blind (w), z <p', b> (u)] in the order of g || w || u
-      ipa->msm_in.ensure((size_t)(n + 2) * 32); ipa->msm_jac.ensure(2 * 96);
-      for (int j = 0; j < 2; ++j) {
-        BZ_CUDA(cudaMemcpyAsync(ipa->msm_in.p, (DFe*)ipa->vec.p + (size_t)(3 + j) * n, (size_t)n * 32, cudaMemcpyDeviceToDevice, st));
-        BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->msm_in.p + n, (DFe*)ipa->extras.p + 2 * j, 64, cudaMemcpyDeviceToDevice, st));
-        msm_run(C, pr.curve, ipa->msm_in.p, pr.g_w_u.p, n + 2, (char*)ipa->msm_jac.p + (size_t)j * 96, 0);
-      }
+      ipa->msm_jac.ensure(2 * 96);
+      msm_run_batch(C, pr.curve, (const void* const*)ipa->ptrs.p, (const void* const*)((void**)ipa->ptrs.p + 2), n, 0, n + 2, pr.g_w_u.p, 2, ipa->msm_jac.p);
       jac_to_affine_run(C, pr.curve, ipa->msm_jac.p, ipa->out.p, 2);
     }
     BZ_CUDA(cudaMemcpyAsync(out_l_affine, ipa->out.p, 64, cudaMemcpyDeviceToHost, st));

@@ -21,6 +21,8 @@ typedef bzh::Fe HFe;
 namespace bz {
 
 void msm_run(Ctx* ctx, int curve, const void* scalars, const void* bases, uint32_t n, void* out_jac, int c_override);
+void msm_run_batch(Ctx* ctx, int curve, const void* const* d_main, const void* const* d_extra, uint32_t n_main, uint32_t first, uint32_t n,
+                   const void* bases, uint32_t n_msm, void* out_jac);
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n);
 void jac_sum_run(Ctx* ctx, int curve, const void* d_jac, uint32_t count, void* d_out_affine);
 void decompress_points_run(Ctx* ctx, int curve, const void* d_in, void* d_out_affine, uint8_t* d_status, uint32_t count);

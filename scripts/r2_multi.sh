@@ -1,14 +1,25 @@
-# 2-GPU run: sharded-proof parity test, then the scaled proof benched at world 1 and 2
+# N-GPU run (N = $1, default 2): sharded-proof parity test, the scaled proof at world N, then the default bench line with extras
+N=${1:-2}
 mkdir -p gpurun_out
-python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3
-for k in 16 18; do
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus 2 --workload board_scaled --k $k --steps 2 --warmup 3 > gpurun_out/scaled${k}_n2.log 2>&1
+timeout 600 python -m pytest tests/test_gpu_multi.py -x -q 2>&1 | tail -3
+export BZ_NO_CPU_BASELINE=1
+for k in 16 18 20; do
+timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533 bench.py --gpus $N --workload board_scaled --k $k --steps 2 --warmup 3 > gpurun_out/scaled${k}_n$N.log 2>&1
 done
-python - <<'PY'
-import json,glob
-for f in sorted(glob.glob('gpurun_out/scaled*_n?.log')):
+unset BZ_NO_CPU_BASELINE
+timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29534 bench.py --gpus $N > gpurun_out/bench_n$N.log 2>&1
+python - $N <<'PY'
+import json,glob,sys
+N=sys.argv[1]
+for f in sorted(glob.glob(f'gpurun_out/scaled*_n{N}.log')):
+    ok=False
     for l in open(f):
         if l.startswith('{'):
-            d=json.loads(l); print(f, round(d['value'],2), round(d['ms_per_step'],1), d['n_gpus'], d['scaling'], d['roofline']['kernel_ms'] if d['roofline'] else None, d['verified'])
+            ok=True
+            d=json.loads(l); print(f, round(d['value'],3), round(d['ms_per_step'],1), d['n_gpus'], d['scaling'], d['roofline']['kernel_ms'] if d['roofline'] else None, d['verified'], d['single_proof_ms'])
+    if not ok: print(f, 'NO LINE:', [l[:200] for l in open(f) if 'Error' in l or 'error' in l][-3:])
+for l in open(f'gpurun_out/bench_n{N}.log'):
+    if l.startswith('{'):
+        d=json.loads(l); print('bench', N, round(d['value'],1), 'e2e', round(d['e2e']['value'],1), d['config'], d['clocks'])
+        for k,v in (d.get('extras') or {}).items(): print('  ', k, v.get('metric'), round(v.get('value',0),2), v.get('scaling'), v.get('verified'), v.get('single_proof_ms'))
 PY
-grep -v "^\[W\|^W1018\|^\*\*\*" gpurun_out/scaled16_n2.log | grep -i "error" | tail -3
