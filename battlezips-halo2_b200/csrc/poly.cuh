@@ -42,6 +42,7 @@ template <class P> struct EvalArgs {
   const Fe<P>* tev;              // t_evaluations (for OP_MUL_T_STORE), length tn (power of two)
   uint32_t tn;
   uint32_t stride_log;           // evaluate at domain points j = i << stride_log only (outputs stay dense, indexed by i)
+  uint32_t first;                // this launch covers the points i >= first (one large proof across GPUs: every rank a range)
 };
 
 template <class P>
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128) eval_program_kernel(const __grid_constant
   for (uint32_t t = threadIdx.x; t < a.n_instr; t += blockDim.x) s_code[t] = a.code[t];
   __syncthreads();
   const uint32_t N = 1u << a.logN;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = a.first + blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t b = blockIdx.y;
   if (i >= (N >> a.stride_log)) return;
   const uint32_t jp = i << a.stride_log;         // the domain point this thread evaluates

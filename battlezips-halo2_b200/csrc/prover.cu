@@ -975,10 +975,18 @@ void Prover::compute_h() {
     a.out = (DFe*)w.hext.p; a.ostride = en; a.tev = (const DFe*)pk.tev.p; a.tn = 1u << (pk.ext_k - k);
     static PerDeviceOnce once;
     once.run(C->device, [] { cudaFuncSetAttribute(eval_program_kernel<FpP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); });
+    // One large proof across GPUs: every rank evaluates a contiguous range of the extended-coset points of each tier and the
+    // ranges are exchanged with one all-gather (32 B per point) -- h(X) is point-wise, so the evaluation shards perfectly.
+    // Only for a batch of one (the slices of a batch would be strided) and when the exchange buffers were sized for it.
+    const uint32_t world = C->shard_world, rank = C->shard_rank;
+    uint64_t slice_bytes = 0;
+    for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) if (t == 0 || pk.q_ninstr[t]) slice_bytes += (uint64_t)(en >> t) / std::max(1u, world) * 32;
+    const bool split = world > 1 && B == 1 && (en >> (PkImpl::Q_TIERS - 1)) >= 128u * world && (en >> (PkImpl::Q_TIERS - 1)) % world == 0 && slice_bytes <= C->shard_cap;
     {
       ProfScope prof(C, PROF_QUOTIENT);
       BigKernelScope bigs(C);
-      auto launch = [&](uint32_t t, const EvalArgs<FpP>& args, uint32_t points) {
+      auto launch = [&](uint32_t t, EvalArgs<FpP> args, uint32_t points) {
+        if (split) { points /= world; args.first = rank * points; }
         const dim3 grid((points + 127) / 128, B);
         if (pk.q_gen[t]) pk.q_gen[t](args, grid, bigs.s);                   // circuit-specialised straight-line code (gen_quotient.cu)
         else eval_program_kernel<FpP><<<grid, 128, pk.q_ninstr[t] * 4, bigs.s>>>(args);
@@ -993,6 +1001,33 @@ void Prover::compute_h() {
         al.stride_log = t; al.out = low_out; al.ostride = en >> t;
         launch(t, al, en >> t);
         low_out += (size_t)B * (en >> t);
+      }
+    }
+    if (split) {
+      // send = [tier 0 slice | tier 1 slice | ...] of this rank; recv = the same layout of every rank, rank-major
+      DFe* tier_out[PkImpl::Q_TIERS];
+      uint32_t tier_pts[PkImpl::Q_TIERS];
+      DFe* lo_ptr = (DFe*)w.hext_low.p;
+      for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) {
+        tier_pts[t] = (t == 0 || pk.q_ninstr[t]) ? (en >> t) / world : 0;
+        tier_out[t] = t == 0 ? (DFe*)w.hext.p : lo_ptr;
+        if (t > 0 && pk.q_ninstr[t]) lo_ptr += (size_t)(en >> t);
+      }
+      size_t off = 0;
+      for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) {
+        if (!tier_pts[t]) continue;
+        BZ_CUDA(cudaMemcpyAsync((char*)C->shard_send + off, tier_out[t] + (size_t)rank * tier_pts[t], (size_t)tier_pts[t] * 32, cudaMemcpyDeviceToDevice, st));
+        off += (size_t)tier_pts[t] * 32;
+      }
+      if (C->shard_exchange(C->shard_user, slice_bytes) != 0) throw Error(BZ_ERR_CUDA, "sharding: all-gather callback failed");
+      for (uint32_t r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        size_t o = (size_t)r * slice_bytes;
+        for (uint32_t t = 0; t < PkImpl::Q_TIERS; ++t) {
+          if (!tier_pts[t]) continue;
+          BZ_CUDA(cudaMemcpyAsync(tier_out[t] + (size_t)r * tier_pts[t], (const char*)C->shard_recv + o, (size_t)tier_pts[t] * 32, cudaMemcpyDeviceToDevice, st));
+          o += (size_t)tier_pts[t] * 32;
+        }
       }
     }
     NttFusion fu; fu.post_mode = 3;

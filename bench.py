@@ -551,7 +551,8 @@ class ProofWorkload:
         wide_all = self._wide(0 if sharded else rank, B * T)
         self.sharded = sharded
         if sharded:
-            ctx.set_sharding(rank, self.world)
+            # exchange buffers: the MSM partial sums are tiny; the point-range split of h(X) moves (8n + 4n + 2n) x 32 B per proof
+            ctx.set_sharding(rank, self.world, capacity=14 * (1 << self.k) * 32 // self.world + (1 << 16))
         for t in range(T):
             lane = {}
             lane["stream"] = torch.cuda.current_stream() if t == 0 else torch.cuda.Stream()

@@ -55,12 +55,14 @@ const char* bz_version(void);
 
 /* ---- one large proof across the GPUs of a box ("independent column commitments ... sharded per GPU", "a large MSM
  * split by point range with one final NCCL point-sum") -----------------------------------------------------------------------
- * Every rank calls bz_create_proofs with IDENTICAL inputs.  On the large-circuit path (k >= 20: bucket MSM over the raw bases)
- * the MSMs of each commitment batch are dealt out by column when the batch has at least `world` of them, otherwise each MSM
- * is split by point range; a rank writes its 96-byte Jacobian results into d_send (device memory, capacity_per_rank bytes)
- * and calls exchange(user, bytes), which must all-gather `bytes` bytes from every rank's d_send into d_recv (rank-major,
- * world x bytes) ON THE CONTEXT'S STREAM (e.g. ncclAllGather / torch.distributed.all_gather_into_tensor) and return 0.
- * Everything else of the proof is computed redundantly, so all ranks write the same proof bytes.  world = 1 switches it off. */
+ * Every rank calls bz_create_proofs with IDENTICAL inputs.  The MSMs of each commitment batch (table path and bucket path alike)
+ * are dealt out by column when the batch has at least `world` of them, otherwise each bucket MSM is split by point range; a rank
+ * writes its partial sums (128-byte XYZZ / 96-byte Jacobian) into d_send (device memory, capacity_per_rank bytes) and calls
+ * exchange(user, bytes), which must all-gather `bytes` bytes from every rank's d_send into d_recv (rank-major, world x bytes) ON
+ * THE CONTEXT'S STREAM (e.g. ncclAllGather / torch.distributed.all_gather_into_tensor) and return 0.  For a batch of one proof,
+ * h(X) on the extended coset is evaluated by point range as well when capacity_per_rank >= 14 * 2^k * 32 / world bytes (the
+ * slices of the 8n / 4n / 2n evaluation tiers); with a smaller buffer it is computed redundantly.  Everything else of the
+ * proof (NTTs, scans, transcript) is computed redundantly, so all ranks write the same proof bytes.  world = 1 switches it off. */
 typedef int (*bz_allgather_fn)(void* user, size_t bytes_per_rank);
 int bz_ctx_set_sharding(bz_ctx* ctx, uint32_t rank, uint32_t world, void* d_send, void* d_recv, size_t capacity_per_rank,
                         bz_allgather_fn exchange, void* user);

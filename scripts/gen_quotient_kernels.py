@@ -86,7 +86,7 @@ def emit_kernel(name, code, rot):
     decl = ", ".join([f"s{i}" for i in range(max_sp)] + [f"t{j}" for j in sorted(tmps)])
     head = [f"__global__ void __launch_bounds__(128) {name}(const __grid_constant__ EvalArgs<FpP> a) {{",
             "  const uint32_t N = 1u << a.logN, mask = N - 1;",
-            "  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;",
+            "  const uint32_t i = a.first + blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;",
             "  if (i >= (N >> a.stride_log)) return;",
             "  const uint32_t jp = i << a.stride_log;",
             "  const Fe<FpP>* pb = a.pbase + (uint64_t)b * a.pstride;",

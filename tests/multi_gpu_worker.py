@@ -1,6 +1,6 @@
 """Worker of tests/test_gpu_multi.py, launched by `python -m torch.distributed.run --nproc-per-node N` (one rank per GPU, NCCL):
   * one large proof across the GPUs (bz_ctx_set_sharding): the MSMs of every commitment batch dealt out by column / split by
-    point range, exchanged by NCCL all-gather -- the proof bytes must equal the single-GPU proof and the oracle-checked verifier
+    point range, h(X) evaluated by point range (second pass), exchanged by NCCL all-gather -- the proof bytes must equal the single-GPU proof and the oracle-checked verifier
     must accept;
   * two contexts on two devices inside ONE process (per-device kernel attributes): a 2^13 NTT (64 KB of dynamic
     shared memory) and a table MSM on the second device give the first device's results."""
@@ -38,7 +38,8 @@ def main():
         dist.broadcast_object_list(bl := [wide if rank == 0 else None], src=0)
         wide = bl[0]
         single = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
-        ctx.set_sharding(rank, world)
+        # second pass: exchange buffers large enough for the point-range split of h(X) (8n + 4n + 2n points of 32 B, per rank)
+        ctx.set_sharding(rank, world, capacity=(1 << 16) if general == "1" else 14 * (1 << k) * 32 // world + (1 << 16))
         sharded = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
         ctx.set_sharding(0, 1)
         again = PR.create_proofs(pk, [asg.instance], advice[None], wide[None])[0]
