@@ -1,6 +1,8 @@
 // Shared internal declarations of libbzhalo2 (not part of the C ABI; see include/bzhalo2.h).
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
 #include <cstdint>
 #include <cstdio>
 #include <map>
@@ -135,9 +137,22 @@ struct BigKernelScope {
 
 // NVTX range (header-only nvtx3; a no-op unless a profiler is attached): prover phases and kernel classes show up by name
 // in Nsight timelines and can be used as ncu range filters
+// BZ_PHASE_TIMES=1 (diagnosis only): every phase range also prints its wall time, device drained at both ends
+inline bool phase_times_enabled() { static const bool on = [] { const char* e = getenv("BZ_PHASE_TIMES"); return e && atoi(e) != 0; }(); return on; }
 struct NvtxRange {
-  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
-  ~NvtxRange() { nvtxRangePop(); }
+  const char* name_;
+  std::chrono::steady_clock::time_point t0_;
+  explicit NvtxRange(const char* name) : name_(name) {
+    nvtxRangePushA(name);
+    if (phase_times_enabled()) { cudaDeviceSynchronize(); t0_ = std::chrono::steady_clock::now(); }
+  }
+  ~NvtxRange() {
+    if (phase_times_enabled()) {
+      cudaDeviceSynchronize();
+      fprintf(stderr, "[phase] %-60s %9.3f ms\n", name_, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0_).count());
+    }
+    nvtxRangePop();
+  }
   NvtxRange(const NvtxRange&) = delete;
   NvtxRange& operator=(const NvtxRange&) = delete;
 };

@@ -176,6 +176,13 @@ __global__ void msm_segmap_kernel(const uint32_t* __restrict__ nseg, const uint3
   if (m > FOLD_SERIAL_MAX) return;            // a hot bucket has thousands of segments: msm_segmap_large_kernel
   for (uint32_t j = 0; j < m; ++j) seg_bucket[o + j] = gb;
 }
+__global__ void msm_segmap_all_kernel(const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff, uint32_t total_buckets,
+                                      uint32_t* __restrict__ seg_bucket) {
+  uint32_t gb = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gb >= total_buckets) return;
+  uint32_t o = segoff[gb], m = nseg[gb];
+  for (uint32_t j = 0; j < m; ++j) seg_bucket[o + j] = gb;
+}
 __global__ void __launch_bounds__(256) msm_segmap_large_kernel(const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff,
                                   const uint32_t* __restrict__ large_count, const uint32_t* __restrict__ large_list, uint32_t max_large,
                                   uint32_t* __restrict__ seg_bucket) {
@@ -484,6 +491,117 @@ void msm_run_batch(Ctx* ctx, int curve, const void* const* d_main, const void* c
                                       (const Affine<FqP>*)bases, n, n_msm, (Jac<FqP>*)out_jac, 0);
   else msm_run_t<FpP, FqP>(ctx, ScalarSrc<FqP>{nullptr, (const Fe<FqP>* const*)d_main, (const Fe<FqP>* const*)d_extra, n_main, first},
                            (const Affine<FpP>*)bases, n, n_msm, (Jac<FpP>*)out_jac, 0);
+}
+
+// ---- shared scalars, many base sets -------------------------------------------------------------------------------------
+// out[m] = sum_q s[q] * bases[q * stride + m]  for m in [0, outputs): `outputs` MSMs that share ONE scalar vector (nq scalars)
+// over interleaved base sets.  This is what materialising the folded generators G' of the inner product argument needs
+// (prover.cu, step 21): s = the products of the round challenges, bases = the original g.  The scalars are sorted once; the
+// segment / bucket kernels take the output index as their fastest-moving thread index, so the base loads of a warp are 32
+// consecutive points.  Buckets are laid out [m][window][bucket], i.e. as outputs x W virtual windows for the reduction.
+template <class BP>
+__global__ void __launch_bounds__(128) msm_segment_multi_kernel(const Affine<BP>* __restrict__ bases, uint32_t stride, uint32_t outputs,
+                                  const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ counts,
+                                  const uint32_t* __restrict__ nseg, const uint32_t* __restrict__ segoff, const uint32_t* __restrict__ seg_bucket,
+                                  uint32_t total_buckets, Xyzz<BP>* __restrict__ partial /* [segment][output] */) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x, s = blockIdx.y;
+  const uint32_t total_segs = segoff[total_buckets - 1] + nseg[total_buckets - 1];
+  if (s >= total_segs || m >= outputs) return;
+  const uint32_t gb = seg_bucket[s];
+  const uint32_t j0 = (s - segoff[gb]) * SEG;
+  const uint32_t off = offsets[gb] + j0, cnt = min(SEG, counts[gb] - j0);
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = 0; j < cnt; ++j) {
+    const uint32_t e = sorted[off + j];
+    const Affine<BP> pt = aff_load(bases + (size_t)(e & 0x7fffffffu) * stride + m);
+    xyzz_add_mixed_signed(acc, pt, (e >> 31) != 0);
+  }
+  xyzz_store(partial + (size_t)s * outputs + m, acc);
+}
+template <class BP>
+__global__ void __launch_bounds__(128) msm_bucket_fold_multi_kernel(const Xyzz<BP>* __restrict__ partial, uint32_t outputs, const uint32_t* __restrict__ nseg,
+                                  const uint32_t* __restrict__ segoff, uint32_t total_buckets, Xyzz<BP>* __restrict__ buckets /* [output][bucket] */) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x, gb = blockIdx.y;
+  if (m >= outputs) return;
+  const uint32_t o = segoff[gb], ns = nseg[gb];
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (uint32_t j = 0; j < ns; ++j) {
+    const Xyzz<BP> v = xyzz_load(partial + (size_t)(o + j) * outputs + m);
+    acc = (j == 0) ? v : xyzz_add(acc, v);
+  }
+  xyzz_store(buckets + (size_t)m * total_buckets + gb, acc);
+}
+// Horner over the W window sums of every output, one thread per output -> Jacobian
+template <class BP>
+__global__ void __launch_bounds__(64) msm_combine_multi_kernel(const Xyzz<BP>* __restrict__ window_sums, uint32_t W, uint32_t c, uint32_t outputs, Jac<BP>* __restrict__ out) {
+  const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= outputs) return;
+  Xyzz<BP> acc = xyzz_identity<BP>();
+  for (int w = (int)W - 1; w >= 0; --w) {
+    for (uint32_t j = 0; j < c; ++j) acc = xyzz_dbl(acc);
+    acc = xyzz_add(acc, xyzz_load(window_sums + (size_t)m * W + w));
+  }
+  Jac<BP> j = xyzz_to_jac(acc);
+  fe_store(&out[m].x, j.x); fe_store(&out[m].y, j.y); fe_store(&out[m].z, j.z);
+}
+
+template <class BP, class SP>
+static void msm_multi_run_t(Ctx* ctx, const Fe<SP>* scalars, uint32_t nq, const Affine<BP>* bases, uint32_t stride, uint32_t outputs, Jac<BP>* out) {
+  cudaStream_t st = ctx->stream;
+  BZ_CHECK(nq >= 1 && outputs >= 1 && nq <= (1u << 20) && outputs <= (1u << 16), "msm (shared scalars): bad shape");
+  const uint32_t c = pick_window(nq);
+  const uint32_t W = (256 + c - 1) / c, nb = 1u << (c - 1), total = W * nb;
+  const uint32_t items = W * nq;
+  const uint32_t max_segs = items / SEG + total, max_large = items / (SEG * FOLD_SERIAL_MAX) + 1;
+  const uint32_t tiles = (total + SCAN_TILE - 1) / SCAN_TILE;
+  const uint64_t WT = (uint64_t)W * outputs;
+  BZ_CHECK(WT * nb < (1ull << 28), "msm (shared scalars): too many buckets");
+  BZ_CHECK(max_segs <= 65535 && total <= 65535, "msm (shared scalars): too many scalars for the (output, segment) grid");
+  uint32_t splits = 1;                                     // the reduction sees outputs x W windows: one CTA per window fills the GPU
+  ctx->scratch[0].ensure((size_t)items * 4);
+  ctx->scratch[2].ensure((size_t)total * 4 * 5 + (size_t)max_segs * 4 + (size_t)(max_large + 4) * 4 + (size_t)tiles * 8 + 64);
+  ctx->scratch[3].ensure(((size_t)WT * nb + WT * splits + WT + (size_t)max_segs * outputs) * sizeof(Xyzz<BP>));
+  uint32_t* sorted = ctx->scratch[0].as<uint32_t>();
+  uint32_t* counts = ctx->scratch[2].as<uint32_t>();
+  uint32_t* offsets = counts + total;
+  uint32_t* nseg = offsets + total;
+  uint32_t* segoff = nseg + total;
+  uint32_t* cursor = segoff + total;
+  uint32_t* seg_bucket = cursor + total;
+  uint32_t* large_count = seg_bucket + max_segs;
+  uint32_t* large_list = large_count + 4;
+  uint32_t* tile_scratch = large_list + max_large;
+  Xyzz<BP>* buckets = ctx->scratch[3].as<Xyzz<BP>>();
+  Xyzz<BP>* wparts = buckets + (size_t)WT * nb;
+  Xyzz<BP>* wsums = wparts + (size_t)WT * splits;
+  Xyzz<BP>* partial = wsums + WT;
+  const ScalarSrc<SP> src{scalars, nullptr, nullptr, 0, 0};
+  const dim3 sgrid((nq + 255) / 256, 1);
+  { ProfScope p(ctx, PROF_MSM_SORT);
+    BZ_CUDA(cudaMemsetAsync(counts, 0, (size_t)total * 4, st));
+    msm_hist_kernel<SP><<<sgrid, 256, 0, st>>>(src, nq, c, W, nb, counts);
+    msm_exclusive_scan(st, counts, total, offsets, cursor, tile_scratch);
+    msm_scatter_kernel<SP><<<sgrid, 256, 0, st>>>(src, nq, c, W, nb, cursor, sorted);
+    BZ_CUDA(cudaMemsetAsync(large_count, 0, 16, st));
+    msm_segcount_kernel<<<(total + 255) / 256, 256, 0, st>>>(counts, total, nseg, large_count, large_list, max_large);
+    msm_exclusive_scan(st, nseg, total, segoff, nullptr, tile_scratch);
+    // every bucket's segments are written by its own thread here (a bucket of <= nq entries has few segments)
+    msm_segmap_all_kernel<<<(total + 255) / 256, 256, 0, st>>>(nseg, segoff, total, seg_bucket); }
+  { ProfScope p(ctx, PROF_MSM_BUCKET);
+    msm_segment_multi_kernel<BP><<<dim3((outputs + 127) / 128, max_segs), 128, 0, st>>>(bases, stride, outputs, sorted, offsets, counts, nseg, segoff, seg_bucket, total, partial);
+    msm_bucket_fold_multi_kernel<BP><<<dim3((outputs + 127) / 128, total), 128, 0, st>>>(partial, outputs, nseg, segoff, total, buckets); }
+  const uint32_t rthreads = nb >= 256 ? 256 : (nb >= 32 ? nb : 32);
+  { ProfScope p(ctx, PROF_MSM_REDUCE);
+    msm_reduce_kernel<BP><<<dim3((uint32_t)WT, splits), rthreads, rthreads * sizeof(Xyzz<BP>), st>>>(buckets, nb, splits, wparts);
+    msm_window_sum_kernel<BP><<<(uint32_t)WT, splits, splits * sizeof(Xyzz<BP>), st>>>(wparts, splits, wsums);
+    msm_combine_multi_kernel<BP><<<(outputs + 63) / 64, 64, 0, st>>>(wsums, W, c, outputs, out); }
+  ctx->kernel_launches += 16;
+  BZ_CUDA(cudaGetLastError());
+}
+
+void msm_multi_run(Ctx* ctx, int curve, const void* scalars, uint32_t nq, const void* bases, uint32_t stride, uint32_t outputs, void* out_jac) {
+  if (curve == 0) msm_multi_run_t<FqP, FpP>(ctx, (const Fe<FpP>*)scalars, nq, (const Affine<FqP>*)bases, stride, outputs, (Jac<FqP>*)out_jac);
+  else msm_multi_run_t<FpP, FqP>(ctx, (const Fe<FqP>*)scalars, nq, (const Affine<FpP>*)bases, stride, outputs, (Jac<FpP>*)out_jac);
 }
 
 void jac_to_affine_run(Ctx* ctx, int curve, const void* jac, void* aff, uint32_t n) {

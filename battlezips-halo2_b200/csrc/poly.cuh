@@ -603,10 +603,11 @@ __global__ void powers_kernel(Regions reg, uint32_t n, PolyRef out, const Fe<P>*
 // scalars over the ORIGINAL generators g[0..n):  o = i' + t*(2*half);  G'_j[i'] = sum_t coef[o] g[o]
 //   L_j uses p'[half + i'] on i' <  half,   R_j uses p'[i' - half] on i' >= half
 template <class P>
-__global__ void ipa_scalars_kernel(Regions reg, uint32_t n, uint32_t half, PolyRef pprime, PolyRef coef, PolyRef scl, PolyRef scr) {
+// `count` = length of the generator vector the scalars refer to: n, or the length of the materialised G' (prover.cu step 21)
+__global__ void ipa_scalars_kernel(Regions reg, uint32_t n, uint32_t count, uint32_t half, PolyRef pprime, PolyRef coef, PolyRef scl, PolyRef scr) {
   uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = blockIdx.y;
-  if (o >= n) return;
+  if (o >= count) return;
   uint32_t ip = o & (2 * half - 1);
   const Fe<P>* pp = region_ptr<P>(reg, pprime, b, n);
   Fe<P> c = fe_load(region_ptr<P>(reg, coef, b, n) + o);
@@ -651,11 +652,11 @@ __global__ void __launch_bounds__(IPA_THREADS) ipa_inner_kernel(Regions reg, uin
 
 // p'[i] += u^-1 p'[i+half];  b[i] += u b[i+half]  (i < half);  coef[o] *= u where bit (o / half) is odd
 template <class P>
-__global__ void ipa_fold_kernel(Regions reg, uint32_t n, uint32_t half, PolyRef pprime, PolyRef bvec, PolyRef coef,
+__global__ void ipa_fold_kernel(Regions reg, uint32_t n, uint32_t count, uint32_t half, PolyRef pprime, PolyRef bvec, PolyRef coef,
                                 const Fe<P>* __restrict__ consts, uint32_t cstride, uint32_t u_const, uint32_t uinv_const) {
   uint32_t o = blockIdx.x * blockDim.x + threadIdx.x;
   uint32_t b = blockIdx.y;
-  if (o >= n) return;
+  if (o >= count) return;
   const Fe<P>* cb = consts + (uint64_t)b * cstride;
   Fe<P> u = fe_load(cb + u_const);
   if ((o / half) & 1) {

@@ -869,8 +869,8 @@ struct Prover {
   // Commitments come back unnormalised from the table MSM (XYZZ, 128 B): one batched inversion on the host for the
   // whole call (Montgomery's trick, ~9 host multiplications per point) instead of a single-thread Fermat chain per
   // commitment on the device (~0.1 ms of latency per launch).  The bucket-MSM path (large k) returns affine points.
-  void read_points(uint32_t n_msm, uint32_t nr, std::vector<std::vector<HostPoint>>& pts) {
-    const bool xyzz = pk.params->use_tables;
+  void read_points(uint32_t n_msm, uint32_t nr, std::vector<std::vector<HostPoint>>& pts, bool force_affine = false) {
+    const bool xyzz = pk.params->use_tables && !force_affine;
     BZ_CUDA(cudaMemcpyAsync(w.h_pinned, w.commits.p, (size_t)n_msm * (xyzz ? 128 : 64), cudaMemcpyDeviceToHost, st));
     BZ_CUDA(cudaStreamSynchronize(st));
     const uint64_t* h = (const uint64_t*)w.h_pinned;
@@ -1066,14 +1066,21 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
   // ---- upload: randomness (reduced on device), advice, instances.  Inputs may live in host or device memory
   // (cudaMemcpyDefault); blinds are re-derived on the host from the same RNG words, so a device-resident stream
   // is mirrored to the host once.
-  std::vector<uint8_t> wide_host;
+  // The host reads a few dozen words (blinds); the two n-word slices (random polynomial, the IPA's S polynomial) are only ever
+  // used on the device, so only the three short ranges around them are mirrored (at k = 20 the whole stream is 134 MB and a
+  // pageable copy of it cost 40 ms per proof).  The mirror keeps the stream's indexing; untouched pages are never committed.
+  std::unique_ptr<uint8_t[]> wide_host;
   {
     cudaPointerAttributes at{};
     if (cudaPointerGetAttributes(&at, rand_wide) == cudaSuccess && at.type == cudaMemoryTypeDevice) {
-      wide_host.resize((size_t)B * pk.R * 64);
-      BZ_CUDA(cudaMemcpyAsync(wide_host.data(), rand_wide, wide_host.size(), cudaMemcpyDeviceToHost, st));
+      wide_host.reset(new uint8_t[(size_t)B * pk.R * 64]);
+      const uint32_t ranges[3][2] = {{0, pk.r_randpoly}, {pk.r_randpoly + n, pk.r_spoly}, {pk.r_spoly + n, pk.R}};
+      for (const auto& rg : ranges)          // one strided copy per range: row b = proof b
+        if (rg[1] > rg[0])
+          BZ_CUDA(cudaMemcpy2DAsync(wide_host.get() + (size_t)rg[0] * 64, (size_t)pk.R * 64, (const uint8_t*)rand_wide + (size_t)rg[0] * 64, (size_t)pk.R * 64,
+                                    (size_t)(rg[1] - rg[0]) * 64, B, cudaMemcpyDeviceToHost, st));
       BZ_CUDA(cudaStreamSynchronize(st));
-      for (uint32_t b = 0; b < B; ++b) ps[b].wide = wide_host.data() + (size_t)b * pk.R * 64;
+      for (uint32_t b = 0; b < B; ++b) ps[b].wide = wide_host.get() + (size_t)b * pk.R * 64;
     } else cudaGetLastError();
   }
   BZ_CUDA(cudaMemcpyAsync(w.wide.p, rand_wide, (size_t)B * pk.R * 64, cudaMemcpyDefault, st));
@@ -1517,18 +1524,54 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
     }
     const uint32_t n_msm = 2 * B;
     pts.assign(B, std::vector<HostPoint>(2));
+    // Late rounds of one LARGE proof.  L_j / R_j are MSMs over the ORIGINAL g with the scalars p'[i' ^ half] * coef[o], n points
+    // in every round however short p' has become (no generator folding).  Once G'_j is down to len0 = 2^mat_log
+    // points it is materialised instead:  G'[i'] = sum_q coef[q * len0 + i'] * g[q * len0 + i'],  where coef depends on q only (the
+    // challenges so far act on the high index bits) -- len0 MSMs that share ONE scalar vector (msm_multi_run: one sort, coalesced
+    // base loads, the cost of about one round) -- and the remaining rounds are the same algorithm on len0 points (coef := 1).
+    // k = 20: 10 of the 20 rounds shrink from n to 1024 points (proof 335 -> 290 ms; k = 18: 100 -> 83 ms; at k = 16 a table-MSM
+    // round is already cheaper than the fixed latency of a small bucket MSM: 26 -> 32 ms, so the default starts at k = 18).  Batch
+    // of one only (G' differs per proof); BZ_IPA_MATERIALIZE_LOG picks log2(len0) (0 = off).
+    uint32_t mat_log = (B == 1 && k >= 18) ? 10u : 0u;
+    if (const char* e = getenv("BZ_IPA_MATERIALIZE_LOG")) mat_log = (B == 1) ? (uint32_t)atoi(e) : 0u;
+    if (mat_log < 2 || mat_log + 1 > k || (n >> mat_log) > 4096) mat_log = 0;
+    const uint32_t len0 = mat_log ? (1u << mat_log) : 0, j_mat = mat_log ? k - mat_log : k;
+    uint32_t count = n;                       // length of the generator vector the scalars of the current round refer to
+    const int curve = pk.params->curve;
     for (uint32_t j = 0; j < k; ++j) {
       const uint32_t half = 1u << (k - j - 1);
+      if (mat_log && j == j_mat) {
+        ProfScope prof(C, PROF_IPA);
+        const uint32_t nq = n >> mat_log;
+        w.ipa_coefq.ensure((size_t)nq * 32); w.ipa_gm.ensure(((size_t)len0 + 2) * 64); w.msm_jac.ensure((size_t)len0 * 96);
+        BZ_CUDA(cudaMemcpy2DAsync(w.ipa_coefq.p, 32, misc(0, pk.m_coef), (size_t)len0 * 32, 32, nq, cudaMemcpyDeviceToDevice, st));
+        msm_multi_run(C, curve, w.ipa_coefq.p, nq, pk.params->g_w_u.p, len0, len0, w.msm_jac.p);
+        jac_to_affine_run(C, curve, w.msm_jac.p, w.ipa_gm.p, len0);
+        BZ_CUDA(cudaMemcpyAsync((char*)w.ipa_gm.p + (size_t)len0 * 64, (const char*)pk.params->g_w_u.p + (size_t)n * 64, 128, cudaMemcpyDeviceToDevice, st));   // w, u
+        fill_kernel<FpP><<<dim3((len0 + 127) / 128, B), 128, 0, st>>>(reg, n, PolyRef{R_MISC, pk.m_coef}, len0, dfe(F.one()));
+        C->kernel_launches++;
+        count = len0;
+      }
       {
         ProfScope prof(C, PROF_IPA);
-        ipa_scalars_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_coef},
-                                                                        PolyRef{R_MISC, pk.m_scl}, PolyRef{R_MISC, pk.m_scr});
+        ipa_scalars_kernel<FpP><<<dim3((count + 127) / 128, B), 128, 0, st>>>(reg, n, count, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_coef},
+                                                                            PolyRef{R_MISC, pk.m_scl}, PolyRef{R_MISC, pk.m_scr});
         ipa_inner_kernel<FpP><<<B, IPA_THREADS, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, (const DFe*)w.consts.p, pk.cstride,
                                                         pk.C_Z, (const DFe*)w.rnd.p, pk.R, pk.r_ipa + 2 * j, pk.r_ipa + 2 * j + 1, (DFe*)w.extras.p);
         C->kernel_launches += 2;
       }
-      run_msms(false, mainp, extrap, n_msm);
-      read_points(n_msm, 2, pts);
+      if (count == n) {
+        run_msms(false, mainp, extrap, n_msm);
+        read_points(n_msm, 2, pts);
+      } else {
+        // bucket MSM of the two short vectors over G' || w || u; every rank of a sharded proof computes it (it is tiny)
+        BZ_CUDA(cudaMemcpyAsync(w.ptrs.p, mainp.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+        BZ_CUDA(cudaMemcpyAsync((void**)w.ptrs.p + n_msm, extrap.data(), (size_t)n_msm * sizeof(void*), cudaMemcpyHostToDevice, st));
+        w.msm_jac.ensure((size_t)n_msm * 96);
+        msm_run_batch(C, curve, (const void* const*)w.ptrs.p, (const void* const*)w.ptrs.p + n_msm, count, 0, count + 2, w.ipa_gm.p, n_msm, w.msm_jac.p);
+        jac_to_affine_run(C, curve, w.msm_jac.p, w.commits.p, n_msm);
+        read_points(n_msm, 2, pts, true);
+      }
       std::vector<HFe> us(B), uinvs(B);
       for (uint32_t b = 0; b < B; ++b) {
         t_write_point(ps[b], pts[b][0]);
@@ -1545,7 +1588,7 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
       }
       upload_consts();
       ProfScope prof(C, PROF_IPA);
-      ipa_fold_kernel<FpP><<<dim3((n + 127) / 128, B), 128, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, PolyRef{R_MISC, pk.m_coef},
+      ipa_fold_kernel<FpP><<<dim3((count + 127) / 128, B), 128, 0, st>>>(reg, n, count, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, PolyRef{R_MISC, pk.m_coef},
                                                                    (const DFe*)w.consts.p, pk.cstride, pk.C_U, pk.C_UINV);
       C->kernel_launches++;
     }
@@ -1666,7 +1709,7 @@ API int bz_ipa_round(bz_ctx* ctx, bz_ipa* ipa, const void* z, const void* l_rand
     BZ_CUDA(cudaMemcpyAsync(ipa->consts.p, z, 32, cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaMemcpyAsync(ipa->rnd.p, l_rand, 32, cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->rnd.p + 1, r_rand, 32, cudaMemcpyHostToDevice, st));
-    ipa_scalars_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 2}, PolyRef{R_MISC, 3}, PolyRef{R_MISC, 4});
+    ipa_scalars_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 2}, PolyRef{R_MISC, 3}, PolyRef{R_MISC, 4});
     ipa_inner_kernel<FpP><<<1, IPA_THREADS, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 1}, (const DFe*)ipa->consts.p, 8, 0,
                                                     (const DFe*)ipa->rnd.p, 0, 0, 1, (DFe*)ipa->extras.p);
     C->kernel_launches += 2;
@@ -1694,7 +1737,7 @@ API int bz_ipa_fold(bz_ctx* ctx, bz_ipa* ipa, const void* u, const void* u_inv) 
     const uint32_t n = ipa->n, half = 1u << (ipa->k - ipa->round - 1);
     BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->consts.p + 1, u, 32, cudaMemcpyHostToDevice, st));
     BZ_CUDA(cudaMemcpyAsync((DFe*)ipa->consts.p + 2, u_inv, 32, cudaMemcpyHostToDevice, st));
-    ipa_fold_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 1}, PolyRef{R_MISC, 2}, (const DFe*)ipa->consts.p, 8, 1, 2);
+    ipa_fold_kernel<FpP><<<dim3((n + 127) / 128, 1), 128, 0, st>>>(ipa->reg, n, n, half, PolyRef{R_MISC, 0}, PolyRef{R_MISC, 1}, PolyRef{R_MISC, 2}, (const DFe*)ipa->consts.p, 8, 1, 2);
     C->kernel_launches++;
     BZ_CUDA(cudaStreamSynchronize(st));
     ipa->round++;

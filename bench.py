@@ -54,6 +54,8 @@ def parse():
     ap.add_argument("--log2n", dest="log", type=int, default=22, help="log2 of the problem size (msm / ntt workloads)")
     ap.add_argument("--k", type=int, default=16, help="rows = 2^k of the board_scaled workload (BASELINE config 5 asks k=20)")
     ap.add_argument("--curve", type=int, default=1, help="0 Vesta, 1 Pallas (msm workload)")
+    ap.add_argument("--scalars", default="uniform", choices=["uniform", "witness"],
+                    help="msm workload: uniform scalars, or SURVEY config 4 (W): 70 %% zero, 20 %% one, 5 %% in [2, 2^10), 5 %% uniform")
     ap.add_argument("--columns", type=int, default=32, help="independent column commitments per step (commit workload)")
     ap.add_argument("--cpu-sample-log", type=int, default=18)
     ap.add_argument("--no-extras", dest="extras", action="store_false",
@@ -204,7 +206,9 @@ class MsmWorkload:
         self.log, self.curve = args.log, args.curve
         self.n = 1 << self.log
         self.metric, self.unit = "msm_points_per_sec", "points/s"
-        self.name = f"raw {'Pallas' if self.curve else 'Vesta'} MSM 2^{self.log} points, uniform scalars (BASELINE config 4)"
+        self.scalar_kind = getattr(args, "scalars", "uniform")
+        kind = "uniform scalars" if self.scalar_kind == "uniform" else "witness-like scalars (70 % zero, 20 % one, 5 % below 2^10, 5 % uniform)"
+        self.name = f"raw {'Pallas' if self.curve else 'Vesta'} MSM 2^{self.log} points, {kind} (BASELINE config 4)"
 
     def host_inputs(self, rank):
         from oracle import c_oracle as co            # setup only: valid curve points for the synthetic bases
@@ -215,6 +219,13 @@ class MsmWorkload:
         pts = make_bases(co, self.curve, m)
         bases = np.tile(pts, (self.n // m, 1))
         scalars = rand_field(rng, self.n)
+        if self.scalar_kind == "witness":
+            # Montgomery images of 0 .. 1023 as a table; the scalar field of curve id c is field id c (Vesta: Fp, Pallas: Fq)
+            p = co.FIELDS[self.curve].p
+            small = np.array([[((v << 256) % p >> (64 * j)) & 0xFFFFFFFFFFFFFFFF for j in range(4)] for v in range(1024)], dtype=np.uint64)
+            u = rng.random(self.n)
+            pick = np.where(u < 0.70, 0, np.where(u < 0.90, 1, rng.integers(2, 1024, size=self.n)))
+            scalars = np.where((u < 0.95)[:, None], small[pick], scalars)
         return scalars, bases
 
     def setup(self, ctx, rank):

@@ -100,6 +100,26 @@ def test_scaled_board_k13_both_commit_paths(ctx, force_general, monkeypatch):
     pk.close(); params.close()
 
 
+@pytest.mark.parametrize("force_general", [False, True])
+@pytest.mark.parametrize("mat_log", [3, 6, 10])
+def test_ipa_with_materialised_generators_gives_the_same_proof(ctx, force_general, mat_log, monkeypatch):
+    """Large single proofs (k >= 16) materialise the folded generators G' once they are down to 2^10 points and run the late IPA
+    rounds on them (prover.cu step 21, msm_multi_run: MSMs with shared scalars).  Forced here on the k = 13 scaled Board at three
+    lengths of G', on both commitment paths: the proof bytes must not change."""
+    from battlezips_halo2_b200.circuits import board_circuit_scaled
+    if force_general:
+        monkeypatch.setenv("BZ_FORCE_GENERAL_MSM", "1")
+    monkeypatch.setenv("BZ_IPA_MATERIALIZE_LOG", str(mat_log))
+    cs, cfg, asg = board_circuit_scaled(13)
+    job = Job(cs, asg)
+    params, pk = job.device_keys(ctx)
+    proof = _prove(job, pk, [3])[0]
+    exp = job.oracle_proof(index=3)
+    assert first_diff(proof, exp) is None, first_diff(proof, exp)
+    assert job.verify(proof)
+    pk.close(); params.close()
+
+
 @pytest.mark.parametrize("which", ["tiny", "shot"])
 def test_keygen_on_device_matches_oracle(ctx, oracle_c, which):
     """keygen_vk / keygen_pk on the device (reference call sites /root/reference/benches/shot.rs:60-61):
