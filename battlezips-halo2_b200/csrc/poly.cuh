@@ -650,6 +650,51 @@ __global__ void __launch_bounds__(IPA_THREADS) ipa_inner_kernel(Regions reg, uin
   }
 }
 
+// The same two inner products for a LONG vector (one large proof: half up to 2^19): grid = (proofs, parts), every CTA sums a
+// slice into tmp[b][part][2]; ipa_inner_finish_kernel (parts threads per proof) adds the slices and writes the extras.
+template <class P>
+__global__ void __launch_bounds__(IPA_THREADS) ipa_inner_partial_kernel(Regions reg, uint32_t n, uint32_t half, PolyRef pprime, PolyRef bvec, Fe<P>* __restrict__ tmp) {
+  __shared__ Fe<P> shl[IPA_THREADS], shr[IPA_THREADS];
+  const uint32_t b = blockIdx.x, part = blockIdx.y, parts = gridDim.y, tid = threadIdx.x;
+  const Fe<P>* pp = region_ptr<P>(reg, pprime, b, n);
+  const Fe<P>* bv = region_ptr<P>(reg, bvec, b, n);
+  const uint32_t per = (half + parts - 1) / parts, lo = part * per, hi = min(half, lo + per);
+  Fe<P> al = fe_zero<P>(), ar = fe_zero<P>();
+  for (uint32_t i = lo + tid; i < hi; i += IPA_THREADS) {
+    al = fe_add(al, fe_mul(fe_load(pp + half + i), fe_load(bv + i)));
+    ar = fe_add(ar, fe_mul(fe_load(pp + i), fe_load(bv + half + i)));
+  }
+  shl[tid] = al; shr[tid] = ar;
+  __syncthreads();
+  for (uint32_t d = IPA_THREADS >> 1; d > 0; d >>= 1) {
+    if (tid < d) { shl[tid] = fe_add(shl[tid], shl[tid + d]); shr[tid] = fe_add(shr[tid], shr[tid + d]); }
+    __syncthreads();
+  }
+  if (tid == 0) { fe_store(tmp + ((uint64_t)b * parts + part) * 2, shl[0]); fe_store(tmp + ((uint64_t)b * parts + part) * 2 + 1, shr[0]); }
+}
+template <class P>
+__global__ void __launch_bounds__(128) ipa_inner_finish_kernel(const Fe<P>* __restrict__ tmp, uint32_t parts,
+                                 const Fe<P>* __restrict__ consts, uint32_t cstride, uint32_t z_const,
+                                 const Fe<P>* __restrict__ rnd, uint64_t rnd_stride, uint32_t l_rand_idx, uint32_t r_rand_idx, Fe<P>* __restrict__ extra) {
+  __shared__ Fe<P> shl[128], shr[128];
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  shl[tid] = tid < parts ? fe_load(tmp + ((uint64_t)b * parts + tid) * 2) : fe_zero<P>();
+  shr[tid] = tid < parts ? fe_load(tmp + ((uint64_t)b * parts + tid) * 2 + 1) : fe_zero<P>();
+  __syncthreads();
+  for (uint32_t d = 64; d > 0; d >>= 1) {
+    if (tid < d) { shl[tid] = fe_add(shl[tid], shl[tid + d]); shr[tid] = fe_add(shr[tid], shr[tid + d]); }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    Fe<P> z = fe_load(consts + (uint64_t)b * cstride + z_const);
+    Fe<P>* e = extra + (uint64_t)b * 4;
+    fe_store(e + 0, fe_load(rnd + (uint64_t)b * rnd_stride + l_rand_idx));
+    fe_store(e + 1, fe_mul(shl[0], z));
+    fe_store(e + 2, fe_load(rnd + (uint64_t)b * rnd_stride + r_rand_idx));
+    fe_store(e + 3, fe_mul(shr[0], z));
+  }
+}
+
 // p'[i] += u^-1 p'[i+half];  b[i] += u b[i+half]  (i < half);  coef[o] *= u where bit (o / half) is odd
 template <class P>
 __global__ void ipa_fold_kernel(Regions reg, uint32_t n, uint32_t count, uint32_t half, PolyRef pprime, PolyRef bvec, PolyRef coef,

@@ -1556,6 +1556,15 @@ void Prover::run(const void* instances, const uint32_t* instance_lens, uint32_t 
         ProfScope prof(C, PROF_IPA);
         ipa_scalars_kernel<FpP><<<dim3((count + 127) / 128, B), 128, 0, st>>>(reg, n, count, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_coef},
                                                                             PolyRef{R_MISC, pk.m_scl}, PolyRef{R_MISC, pk.m_scr});
+        if (half >= (1u << 15)) {
+          // long vectors: a single CTA per proof took 0.4 ms per round at k = 20 (3 % of the proof); slices across the GPU instead
+          const uint32_t parts = std::min<uint32_t>(128, half >> 12);
+          w.ipa_tmp.ensure((size_t)B * parts * 2 * 32);
+          ipa_inner_partial_kernel<FpP><<<dim3(B, parts), IPA_THREADS, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, (DFe*)w.ipa_tmp.p);
+          ipa_inner_finish_kernel<FpP><<<B, 128, 0, st>>>((const DFe*)w.ipa_tmp.p, parts, (const DFe*)w.consts.p, pk.cstride, pk.C_Z, (const DFe*)w.rnd.p, pk.R,
+                                                         pk.r_ipa + 2 * j, pk.r_ipa + 2 * j + 1, (DFe*)w.extras.p);
+          C->kernel_launches++;
+        } else
         ipa_inner_kernel<FpP><<<B, IPA_THREADS, 0, st>>>(reg, n, half, PolyRef{R_MISC, pk.m_pprime}, PolyRef{R_MISC, pk.m_b}, (const DFe*)w.consts.p, pk.cstride,
                                                         pk.C_Z, (const DFe*)w.rnd.p, pk.R, pk.r_ipa + 2 * j, pk.r_ipa + 2 * j + 1, (DFe*)w.extras.p);
         C->kernel_launches += 2;
