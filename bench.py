@@ -111,7 +111,10 @@ def config_for(wl, sched="spin"):
         l2 = "inputs larger than L2 (no flush needed)"
     else:
         l2 = "inputs < L2; not flushed"
-    return {"workload": wl.name, "l2": l2, "host_wait": sched}
+    cfg = {"workload": wl.name, "l2": l2, "host_wait": sched}
+    if isinstance(wl, ProofWorkload):
+        cfg["lanes"] = "every lane proves its K batches back to back inside the timed region (independent proofs: no barrier between the steps of different lanes)"
+    return cfg
 
 
 def peaks():
@@ -643,6 +646,21 @@ class ProofWorkload:
     def step_e2e(self):
         return self._run(False)
 
+    def run_steps(self, device, steps):
+        """K steps with the lanes free-running: every lane issues its K create_proof calls back to back, the way a proving
+        service keeps its GPU fed.  With a barrier after every step all lanes would stage their next inputs (host -> device
+        copies, witness inversion) at the same moment and leave the GPU idle meanwhile.  A sharded proof (collectives inside
+        the call) stays in lockstep."""
+        if getattr(self, "sharded", False) or len(self.lanes) == 1:
+            return sum(self._run(device) for _ in range(steps))
+
+        def loop(lane):
+            for _ in range(steps):
+                self._lane_run(lane, device)
+        for f in [self.pool.submit(loop, lane) for lane in self.lanes]:
+            f.result()
+        return self.B * self.T * steps
+
     def single_latency(self, reps=7):
         """latency of ONE proof (batch 1, one lane, device-resident inputs): median wall ms of `reps` calls"""
         import ctypes
@@ -807,9 +825,7 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
-    units = 0.0
-    for _ in range(steps):
-        units += wl.step_device()
+    units = wl.run_steps(True, steps) if hasattr(wl, "run_steps") else sum(wl.step_device() for _ in range(steps))
     e1.record(stream)
     barrier()
     ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
@@ -841,9 +857,7 @@ def measure(args, wl, ctx, stream, rank, world, local_rank, want_cpu=True, steps
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
     t0 = time.perf_counter()
-    units_e = 0.0
-    for _ in range(steps):
-        units_e += wl.step_e2e()
+    units_e = wl.run_steps(False, steps) if hasattr(wl, "run_steps") else sum(wl.step_e2e() for _ in range(steps))
     e3.record(stream)
     barrier()
     wall_e = time.perf_counter() - t0
